@@ -1,0 +1,72 @@
+"""ctypes binding of libdgcnn_b200.so (include/dgcnn_b200.h).  No fallback: a missing library is fatal."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdgcnn_b200.so")
+
+c_void_p, c_int, c_float, c_double, c_size_t, c_int64 = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t, C.c_int64
+
+
+class EdgeConvArgs(C.Structure):
+    """mirror of `dgcnn_edgeconv_args`"""
+    _fields_ = [("rows", c_void_p), ("ld", c_int), ("idx", c_void_p),
+                ("B", c_int), ("C", c_int), ("N", c_int), ("k", c_int),
+                ("w_a", c_void_p), ("w_b", c_void_p), ("out", c_void_p), ("ld_out", c_int)]
+
+
+_P = c_void_p
+_ARGS = C.POINTER(EdgeConvArgs)
+# name -> (restype, argtypes); must list every symbol declared in include/dgcnn_b200.h
+SIGNATURES = {
+    "dgcnn_version": (c_int, []),
+    "dgcnn_last_error": (C.c_char_p, []),
+    "dgcnn_num_sms": (c_int, []),
+    "dgcnn_pack_rows_f32": (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, c_int, _P, c_int, _P]),
+    "dgcnn_unpack_rows_f32": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
+    "dgcnn_knn_f32": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "dgcnn_graph_feature_f32": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "dgcnn_edgeconv_fwd_eval": (c_int, [_ARGS, _P, _P, _P]),
+    "dgcnn_edgeconv_partials_bytes": (c_size_t, []),
+    "dgcnn_edgeconv_conv_a_train": (c_int, [_ARGS, _P, _P, _P, _P, _P, _P, _P]),
+    "dgcnn_edgeconv_conv_b_train": (c_int, [_ARGS, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "dgcnn_bn_finalize": (c_int, [_P, c_int, c_double, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P]),
+    "dgcnn_edgeconv_select": (c_int, [c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
+    "dgcnn_edgeconv_bwd_prep": (c_int, [c_int, _P, c_int, _P, _P, _P, _P, _P]),
+    "dgcnn_bn_bwd_reduce": (c_int, [_P, c_int, c_double, _P, _P, _P, _P, _P, _P, _P]),
+    "dgcnn_edgeconv_dw_partials_bytes": (c_size_t, []),
+    "dgcnn_edgeconv_bwd_b": (c_int, [_ARGS, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "dgcnn_edgeconv_bwd_a": (c_int, [_ARGS, _P, _P, _P, _P, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library once; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C ahn3-dgcnn.pytorch_b200/csrc`).  There is no CPU or PyTorch fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class DgcnnError(RuntimeError):
+    pass
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().dgcnn_last_error().decode("utf-8", "replace")
+        raise DgcnnError(f"libdgcnn_b200 error {rc}: {msg}")

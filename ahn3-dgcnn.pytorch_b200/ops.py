@@ -1,0 +1,250 @@
+"""Host-side operators over the C-ABI (include/dgcnn_b200.h).
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every per-edge computation
+runs in libdgcnn_b200.so.  All tensors must live on a CUDA device — there is no CPU path.
+
+Internal layout: features are point-major "rows" [B*N, C] (row p = b*N + n), neighbour tables are
+int32 [B*N, k] with block-local indices.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+COUT = 64
+BN_EPS_DEFAULT = 1e-5
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: expected a CUDA tensor (the B200 path has no CPU fallback), got {t.device}")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{what}: expected float32, got {t.dtype}")
+
+
+# per-device scratch for the per-CTA partial reductions
+_scratch = {}
+
+
+def _partials(dev: torch.device) -> Tuple[torch.Tensor, torch.Tensor]:
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _scratch:
+        lib = _lib.load()
+        _scratch[key] = (
+            torch.empty(lib.dgcnn_edgeconv_partials_bytes() // 8, dtype=torch.float64, device=dev),
+            torch.empty(lib.dgcnn_edgeconv_dw_partials_bytes() // 4, dtype=torch.float32, device=dev),
+        )
+    return _scratch[key]
+
+
+def _rows_view(rows: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """Accept [M, C] with unit inner stride, 16-byte aligned rows; return (tensor, ld)."""
+    if rows.dim() != 2 or rows.stride(1) != 1 or rows.stride(0) % 4 or rows.data_ptr() % 16:
+        rows = rows.contiguous()
+        if rows.size(1) % 4:
+            pad = 4 - rows.size(1) % 4
+            rows = torch.nn.functional.pad(rows, (0, pad))
+    return rows, rows.stride(0)
+
+
+# ------------------------------------------------------------------------------------------------
+# layout
+# ------------------------------------------------------------------------------------------------
+def pack_rows(x: torch.Tensor) -> torch.Tensor:
+    """x [B,C,N] (any strides) -> rows [B*N, round4(C)], padding columns zero (model.py:73)."""
+    _need_cuda(x, "pack_rows")
+    B, Cn, N = x.shape
+    c4 = (Cn + 3) // 4 * 4
+    rows = torch.empty(B * N, c4, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().dgcnn_pack_rows_f32(_ptr(x), x.stride(0), x.stride(1), x.stride(2), B, Cn, N,
+                                               _ptr(rows), c4, _stream()))
+    return rows
+
+
+def unpack_rows(rows: torch.Tensor, B: int, Cn: int, N: int) -> torch.Tensor:
+    """rows [B*N, >=C] -> contiguous [B,C,N]."""
+    rows, ld = _rows_view(rows)
+    y = torch.empty(B, Cn, N, dtype=torch.float32, device=rows.device)
+    _lib.check(_lib.load().dgcnn_unpack_rows_f32(_ptr(rows), ld, B, Cn, N, _ptr(y), _stream()))
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# kNN / graph feature
+# ------------------------------------------------------------------------------------------------
+def knn_rows(rows: torch.Tensor, B: int, Cn: int, N: int, k: int) -> torch.Tensor:
+    """Neighbour table int32 [B*N, k] of point-major rows (model.py:25-40)."""
+    _need_cuda(rows, "knn")
+    rows, ld = _rows_view(rows)
+    idx = torch.empty(B * N, k, dtype=torch.int32, device=rows.device)
+    norms = torch.empty(B * N, dtype=torch.float32, device=rows.device)
+    _lib.check(_lib.load().dgcnn_knn_f32(_ptr(rows), ld, B, Cn, N, k, _ptr(idx), _ptr(norms), _stream()))
+    return idx
+
+
+def graph_feature_rows(rows: torch.Tensor, idx: torch.Tensor, B: int, Cn: int, N: int, k: int) -> torch.Tensor:
+    """[B,N,k,2C] edge-feature buffer (model.py:74-81); API-parity path, not used by DGCNN.forward."""
+    rows, ld = _rows_view(rows)
+    out = torch.empty(B, N, k, 2 * Cn, dtype=torch.float32, device=rows.device)
+    _lib.check(_lib.load().dgcnn_graph_feature_f32(_ptr(rows), ld, _ptr(idx), B, Cn, N, k, _ptr(out), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# EdgeConv block
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class BNState:
+    """The non-differentiable part of one BatchNorm2d(64) (model.py:107-111)."""
+    running_mean: Optional[torch.Tensor]
+    running_var: Optional[torch.Tensor]
+    eps: float = BN_EPS_DEFAULT
+    momentum: float = 0.1
+
+
+def _args(rows, ld, idx, B, Cn, N, k, w_a, w_b, out, ld_out):
+    return _lib.EdgeConvArgs(rows.data_ptr(), ld, idx.data_ptr(), B, Cn, N, k, w_a.data_ptr(),
+                             0 if w_b is None else w_b.data_ptr(), 0 if out is None else out.data_ptr(), ld_out)
+
+
+def eval_affine(gamma: torch.Tensor, beta: torch.Tensor, bn: BNState) -> torch.Tensor:
+    """float[192] = running_mean | gamma/sqrt(running_var+eps) | beta."""
+    return torch.cat((bn.running_mean, gamma * torch.rsqrt(bn.running_var + bn.eps), beta)).float().contiguous()
+
+
+def edgeconv_eval(rows: torch.Tensor, idx: torch.Tensor, B: int, Cn: int, N: int, k: int,
+                  w_a: torch.Tensor, aff_a: torch.Tensor,
+                  w_b: Optional[torch.Tensor] = None, aff_b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused inference EdgeConv block -> [B*N, 64].  Not differentiable."""
+    _need_cuda(rows, "edgeconv_eval")
+    rows, ld = _rows_view(rows)
+    out = torch.empty(B * N, COUT, dtype=torch.float32, device=rows.device)
+    wa = w_a.detach().reshape(COUT, -1).contiguous()
+    wb = None if w_b is None else w_b.detach().reshape(COUT, COUT).contiguous()
+    a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, out, COUT)
+    _lib.check(_lib.load().dgcnn_edgeconv_fwd_eval(C.byref(a), _ptr(aff_a), _ptr(aff_b), _stream()))
+    return out
+
+
+class EdgeConvTrain(torch.autograd.Function):
+    """Training-mode EdgeConv block (batch-statistics BN) with a hand-written backward.
+
+    forward(x_rows[M,C], idx, meta, w_a, gamma_a, beta_a, w_b|None, gamma_b|None, beta_b|None, bn_a, bn_b)
+    """
+
+    @staticmethod
+    def forward(ctx, x, idx, meta, w_a, gamma_a, beta_a, w_b, gamma_b, beta_b, bn_a: BNState, bn_b: Optional[BNState]):
+        lib = _lib.load()
+        B, Cn, N, k = meta
+        M, E = B * N, B * N * k
+        dev = x.device
+        rows, ld = _rows_view(x.detach())
+        two = w_b is not None
+        wa = w_a.detach().reshape(COUT, 2 * Cn).contiguous()
+        wb = w_b.detach().reshape(COUT, COUT).contiguous() if two else None
+        partials, _ = _partials(dev)
+        st = _stream()
+
+        f32 = dict(dtype=torch.float32, device=dev)
+        y_a = torch.empty(E, COUT, **f32)
+        ymax = torch.empty(M, COUT, **f32)
+        ymin = torch.empty(M, COUT, **f32)
+        amax = torch.empty(M, COUT, dtype=torch.uint8, device=dev)
+        amin = torch.empty(M, COUT, dtype=torch.uint8, device=dev)
+        out = torch.empty(M, COUT, **f32)
+        ysel = torch.empty(M, COUT, **f32)
+        arg = torch.empty(M, COUT, dtype=torch.uint8, device=dev)
+        stat_a = torch.empty(2 + 3, COUT, **f32)     # mean, rstd, affine(mean|scale|beta)
+        a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, None, COUT)
+
+        _lib.check(lib.dgcnn_edgeconv_conv_a_train(C.byref(a), _ptr(y_a), _ptr(partials), _ptr(ymax), _ptr(ymin),
+                                                   _ptr(amax), _ptr(amin), st))
+        _lib.check(lib.dgcnn_bn_finalize(_ptr(partials), COUT, float(E), _ptr(gamma_a.detach()), _ptr(beta_a.detach()),
+                                         bn_a.eps, bn_a.momentum, _ptr(bn_a.running_mean), _ptr(bn_a.running_var),
+                                         _ptr(stat_a[0]), _ptr(stat_a[1]), _ptr(stat_a[2:]), st))
+        stat_b = None
+        if two:
+            stat_b = torch.empty(2 + 3, COUT, **f32)
+            _lib.check(lib.dgcnn_edgeconv_conv_b_train(C.byref(a), _ptr(y_a), _ptr(stat_a[2:]), _ptr(partials),
+                                                       _ptr(ymax), _ptr(ymin), _ptr(amax), _ptr(amin), st))
+            _lib.check(lib.dgcnn_bn_finalize(_ptr(partials), COUT, float(E), _ptr(gamma_b.detach()), _ptr(beta_b.detach()),
+                                             bn_b.eps, bn_b.momentum, _ptr(bn_b.running_mean), _ptr(bn_b.running_var),
+                                             _ptr(stat_b[0]), _ptr(stat_b[1]), _ptr(stat_b[2:]), st))
+        last = stat_b if two else stat_a
+        _lib.check(lib.dgcnn_edgeconv_select(M, _ptr(ymax), _ptr(ymin), _ptr(amax), _ptr(amin), _ptr(last[2:]),
+                                             _ptr(out), COUT, _ptr(ysel), _ptr(arg), st))
+        ctx.meta = meta
+        ctx.two = two
+        ctx.save_for_backward(rows, idx, wa, wb if two else wa, gamma_a.detach(), gamma_b.detach() if two else gamma_a.detach(),
+                              y_a, stat_a, stat_b if two else stat_a, ysel, arg)
+        ctx.x_shape = tuple(x.shape)
+        ctx.ld = ld
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        rows, idx, wa, wb, gamma_a, gamma_b, y_a, stat_a, stat_b, ysel, arg = ctx.saved_tensors
+        B, Cn, N, k = ctx.meta
+        two = ctx.two
+        M, E = B * N, B * N * k
+        dev = dout.device
+        st = _stream()
+        partials, dw_partials = _partials(dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        if dout.stride(1) != 1:
+            dout = dout.contiguous()
+        a = _args(rows, ctx.ld, idx, B, Cn, N, k, wa, wb if two else None, None, COUT)
+
+        g = torch.empty(M, COUT, **f32)
+        last = stat_b if two else stat_a
+        gamma_last = gamma_b if two else gamma_a
+        _lib.check(lib.dgcnn_edgeconv_bwd_prep(M, _ptr(dout), dout.stride(0), _ptr(ysel), _ptr(last[2:]), _ptr(g),
+                                               _ptr(partials), st))
+        dgl = torch.empty(2, COUT, **f32)      # dgamma, dbeta of the last BN
+        coef_l = torch.empty(3, COUT, **f32)
+        _lib.check(lib.dgcnn_bn_bwd_reduce(_ptr(partials), COUT, float(E), _ptr(gamma_last), _ptr(last[0]), _ptr(last[1]),
+                                           _ptr(dgl[0]), _ptr(dgl[1]), _ptr(coef_l), st))
+        dw_b = dga = None
+        if two:
+            dz_a = torch.empty(E, COUT, **f32)
+            dw_b = torch.empty(COUT, COUT, **f32)
+            _lib.check(lib.dgcnn_edgeconv_bwd_b(C.byref(a), _ptr(y_a), _ptr(stat_a[2:]), _ptr(g), _ptr(arg), _ptr(coef_l),
+                                                _ptr(dz_a), _ptr(dw_b), _ptr(partials), _ptr(dw_partials), st))
+            dga = torch.empty(2, COUT, **f32)
+            coef_a = torch.empty(3, COUT, **f32)
+            _lib.check(lib.dgcnn_bn_bwd_reduce(_ptr(partials), COUT, float(E), _ptr(gamma_a), _ptr(stat_a[0]), _ptr(stat_a[1]),
+                                               _ptr(dga[0]), _ptr(dga[1]), _ptr(coef_a), st))
+        else:
+            dz_a, coef_a, dga = None, coef_l, dgl
+        s = torch.empty(M, COUT, **f32)
+        r = torch.zeros(M, COUT, **f32)
+        _lib.check(lib.dgcnn_edgeconv_bwd_a(C.byref(a), _ptr(y_a), _ptr(dz_a), _ptr(g), _ptr(arg), _ptr(coef_a),
+                                            _ptr(s), _ptr(r), st))
+        # point-level GEMMs (M x 64 x C): dX = r Wa1 + s (Wa2 - Wa1);  dWa = [(r - s)^T X | s^T X]
+        X = rows[:, :Cn]
+        wa1, wa2 = wa[:, :Cn], wa[:, Cn:]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = r @ wa1 + s @ (wa2 - wa1)
+            if dx.shape != ctx.x_shape:
+                dx = dx.reshape(ctx.x_shape)
+        dwa = torch.cat(((r - s).t() @ X, s.t() @ X), dim=1)
+        # returns: x, idx, meta, w_a, gamma_a, beta_a, w_b, gamma_b, beta_b, bn_a, bn_b
+        if two:
+            return (dx, None, None, dwa.view(COUT, 2 * Cn, 1, 1), dga[0], dga[1], dw_b.view(COUT, COUT, 1, 1),
+                    dgl[0], dgl[1], None, None)
+        return dx, None, None, dwa.view(COUT, 2 * Cn, 1, 1), dga[0], dga[1], None, None, None, None, None

@@ -1,0 +1,133 @@
+/* dgcnn_b200.h — C-ABI of libdgcnn_b200.so: the B200 (sm_100a) EdgeConv hot path of DGCNN.
+ *
+ * The reference (BenCurran98/AHN3-dgcnn.pytorch) has no FFI: its boundary is the Python surface of
+ * model.py.  These entry points are what a ctypes binding for that path binds; the in-tree Python
+ * host (`ahn3-dgcnn.pytorch_b200/model.py`) is such a binding and INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.  Each function names the reference lines it replaces.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless stated; nothing is allocated, freed or synchronised here.
+ *  - Work is enqueued on `stream` (a cudaStream_t passed as void*); NULL = legacy default stream.
+ *  - "rows" = point-major feature matrix: row p = b*N + n holds the C channels of point n of block b,
+ *    consecutive floats, `ld` floats between rows (ld >= C, ld % 4 == 0, 16-byte aligned base).
+ *  - idx = int32 [B*N, k], neighbour indices LOCAL to the block (0..N-1), unordered (a set).
+ *  - Return value: 0 ok; <0 error (DGCNN_E_*).  dgcnn_last_error() gives a thread-local message.
+ *  - Every *_partials / *_ws buffer is caller-provided scratch sized by the matching *_bytes() call.
+ */
+#ifndef DGCNN_B200_H
+#define DGCNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGCNN_OK 0
+#define DGCNN_E_INVALID (-1)     /* bad argument (null pointer, k > N, misaligned ld ...)            */
+#define DGCNN_E_UNSUPPORTED (-2) /* shape outside the compiled range (C > 128, k > 128 ...)           */
+#define DGCNN_E_CUDA (-3)        /* a CUDA runtime call failed; message holds cudaGetErrorString      */
+#define DGCNN_E_WORKSPACE (-4)   /* workspace too small                                                */
+
+#define DGCNN_COUT 64            /* every EdgeConv conv has 64 output channels (model.py:116-130)     */
+
+int dgcnn_version(void);                 /* 100*major + minor */
+const char* dgcnn_last_error(void);      /* host pointer, thread-local, never NULL */
+int dgcnn_num_sms(void);                 /* SM count of the current device (cached), <0 on error */
+
+/* ---- layout: x[B,C,N] with arbitrary element strides  ->  rows[B*N, ld] (cols C..Cpad-1 zeroed) ----
+ * replaces x.transpose(2,1).contiguous() at model.py:73.  Cpad = C rounded up to a multiple of 4.    */
+int dgcnn_pack_rows_f32(const float* x, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                        int B, int C, int N, float* rows, int ld, void* stream);
+/* rows[B*N, ld] (C channels) -> y[B,C,N] contiguous (for the depth=1..3 early returns, model.py:151-165) */
+int dgcnn_unpack_rows_f32(const float* rows, int ld, int B, int C, int N, float* y, void* stream);
+
+/* ---- kNN graph (model.py:25-40) -------------------------------------------------------------------
+ * score[i,j] = fl(fl(2*dot(x_i,x_j) - |x_j|^2) - |x_i|^2) with dot an FP32 FMA chain over channels in
+ * increasing order and |x|^2 torch.sum's order (sequential in blocks of 16) — the exact roundings of the
+ * reference's CPU path; idx[p,:] = the k largest per row (ties: lower index wins), self included.
+ * `norms` = scratch float[B*N].  Exact FP32 path for every C <= 128.                                  */
+int dgcnn_knn_f32(const float* rows, int ld, int B, int C, int N, int k,
+                  int32_t* idx, float* norms, void* stream);
+
+/* ---- get_graph_feature (model.py:43-83), materialising form kept for API parity -------------------
+ * out[B,N,k,2C] = cat(x_j - x_i, x_i); the reference returns permute(0,3,1,2) of this buffer.        */
+int dgcnn_graph_feature_f32(const float* rows, int ld, const int32_t* idx, int B, int C, int N, int k,
+                            float* out, void* stream);
+
+/* ---- EdgeConv block ---------------------------------------------------------------------------------
+ * One block = gather + [x_j-x_i, x_i] + conv_a(2C->64) + BN + LeakyReLU(0.2) [+ conv_b(64->64) + BN +
+ * LeakyReLU] + max over k (model.py:147-150, 154-157, 161-163).  Weights are the Conv2d tensors as
+ * stored: w_a[64, 2C] row-major, w_b[64, 64] (NULL for the single-conv block 3).
+ * The [B,2C,N,k] edge tensor is never formed in HBM.                                                   */
+typedef struct dgcnn_edgeconv_args {
+  const float* rows;      /* input features, point-major                                              */
+  int ld;                 /* row stride of `rows` (floats)                                            */
+  const int32_t* idx;     /* [B*N, k] local neighbour indices                                         */
+  int B, C, N, k;         /* C = input channels (<= 64)                                               */
+  const float* w_a;       /* [64, 2C]                                                                 */
+  const float* w_b;       /* [64, 64] or NULL                                                         */
+  float* out;             /* [B*N, 64] block output, row stride ld_out                                */
+  int ld_out;
+} dgcnn_edgeconv_args;
+
+/* BN "affine" vectors are float[192] = mean[64] | scale[64] | beta[64]; the kernels apply
+ * z = (y - mean) * scale + beta (one subtraction + one FMA, the accurate form when |mean| >> std).
+ * eval: mean = running_mean, scale = gamma / sqrt(running_var + eps);  train: from dgcnn_bn_finalize.   */
+
+/* Inference: single fused kernel (gather -> conv_a -> BN -> LReLU -> [conv_b -> BN -> LReLU] -> max_k). */
+int dgcnn_edgeconv_fwd_eval(const dgcnn_edgeconv_args* a, const float* affine_a, const float* affine_b,
+                            void* stream);
+
+/* Training forward (batch-statistics BN; SURVEY.md §7 hard part 2).  Sequence per block:
+ *   conv_a_train  -> bn_finalize(a) -> [conv_b_train -> bn_finalize(b)] -> select
+ * y_a: float[B*N*k, 64] pre-BN conv_a output (kept for backward).  partials: scratch of
+ * dgcnn_edgeconv_partials_bytes().  ymax/ymin float[B*N,64], amax/amin uint8[B*N,64] = per point/channel
+ * extrema over k of the LAST conv's raw output and their slots (NULL allowed in conv_a_train when w_b != NULL). */
+size_t dgcnn_edgeconv_partials_bytes(void);
+int dgcnn_edgeconv_conv_a_train(const dgcnn_edgeconv_args* a, float* y_a, double* partials,
+                                float* ymax, float* ymin, uint8_t* amax, uint8_t* amin, void* stream);
+int dgcnn_edgeconv_conv_b_train(const dgcnn_edgeconv_args* a, const float* y_a, const float* affine_a,
+                                double* partials, float* ymax, float* ymin, uint8_t* amax, uint8_t* amin,
+                                void* stream);
+/* Reduce the per-CTA partial sums (sum, sum of squares) in double, produce batch mean / rstd and the
+ * affine triple, and update running_mean/var (momentum, unbiased var) like nn.BatchNorm2d (model.py:107-111;
+ * running_* may both be NULL).  count = values per channel (B*N*k).  C must be 64.                      */
+int dgcnn_bn_finalize(const double* partials, int C, double count, const float* gamma, const float* beta,
+                      float eps, float momentum, float* running_mean, float* running_var,
+                      float* mean, float* rstd, float* affine, void* stream);
+/* out = LeakyReLU(BN(sel)), sel = scale>=0 ? ymax : ymin (BN-affine and LeakyReLU are monotone, so
+ * max_k LReLU(BN(y)) = LReLU(BN(max_k y)) for scale >= 0 and LReLU(BN(min_k y)) otherwise);
+ * ysel float[B*N,64] and arg uint8[B*N,64] (slot of sel) are saved for backward.                       */
+int dgcnn_edgeconv_select(int M, const float* ymax, const float* ymin, const uint8_t* amax, const uint8_t* amin,
+                          const float* affine, float* out, int ld_out, float* ysel, uint8_t* arg, void* stream);
+
+/* Training backward (dense because of batch-stat BN; SURVEY.md §7 hard part 3).  Sequence:
+ *   bwd_prep -> bn_bwd_reduce(last BN) -> [bwd_b -> bn_bwd_reduce(BN a)] -> bwd_a
+ * then dX = r*Wa1 + s*(Wa2-Wa1), dWa = [(r-s)^T X, s^T X] are small point-level GEMMs done by the host.  */
+/* g = dout * LeakyReLU'(BN(ysel)); partials <- (sum g, sum g*ysel) per channel.                        */
+int dgcnn_edgeconv_bwd_prep(int M, const float* dout, int ld_dout, const float* ysel, const float* affine,
+                            float* g, double* partials, void* stream);
+/* From partial sums (S1 = sum dz, S2 = sum dz*y) of one BN: dgamma, dbeta and the coefficients
+ * dy = cA*dz - cB - cC*y  of the BN input gradient.  coef = float[3*64] = cA | cB | cC.                 */
+int dgcnn_bn_bwd_reduce(const double* partials, int C, double count, const float* gamma,
+                        const float* mean, const float* rstd, float* dgamma, float* dbeta, float* coef,
+                        void* stream);
+/* Edge pass through conv_b: recompute h = LReLU(BN_a(y_a)), y_b = W_b h; dy_b from (g, arg, coef_b);
+ * dW_b (float[64*64], overwritten); dz_a = (dy_b W_b) * LReLU'(.) -> float[B*N*k,64]; partials <- BN_a sums.
+ * dw_partials: scratch of dgcnn_edgeconv_dw_partials_bytes().                                           */
+size_t dgcnn_edgeconv_dw_partials_bytes(void);
+int dgcnn_edgeconv_bwd_b(const dgcnn_edgeconv_args* a, const float* y_a, const float* affine_a,
+                         const float* g, const uint8_t* arg, const float* coef_b,
+                         float* dz_a, float* dw_b, double* partials, float* dw_partials, void* stream);
+/* Edge pass through BN_a: dy_a = cA*dz_a - cB - cC*y_a; s[p,:] = sum_k dy_a; r[j,:] += dy_a (scatter).
+ * dz_a == NULL selects the single-conv form (dz_a given implicitly by g/arg).  r must be zero-filled. */
+int dgcnn_edgeconv_bwd_a(const dgcnn_edgeconv_args* a, const float* y_a, const float* dz_a,
+                         const float* g, const uint8_t* arg, const float* coef_a,
+                         float* s, float* r, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGCNN_B200_H */
