@@ -35,6 +35,50 @@ def _need_cuda(t: torch.Tensor, what: str) -> None:
         raise RuntimeError(f"{what}: expected float32, got {t.dtype}")
 
 
+class KernelLog:
+    """Counts kernel launches made through the C-ABI and (optionally) brackets each call with CUDA events on
+    the launching stream, so bench.py can report per-kernel device time measured inside the timed region."""
+
+    def __init__(self):
+        self.launches = 0
+        self.timing = False
+        self.events = []          # (name, start_event, end_event)
+
+    def reset(self, timing: bool = False):
+        self.launches = 0
+        self.timing = timing
+        self.events = []
+
+    def summary(self):
+        """name -> (calls, total_ms); call after torch.cuda.synchronize()."""
+        out = {}
+        for name, a, b in self.events:
+            c, t = out.get(name, (0, 0.0))
+            out[name] = (c + 1, t + a.elapsed_time(b))
+        return out
+
+
+LOG = KernelLog()
+
+# kernels launched by each entry point
+_LAUNCHES = {"dgcnn_knn_f32": 2, "dgcnn_edgeconv_bwd_b": 2}
+
+
+def _call(name: str, *args) -> None:
+    fn = getattr(_lib.load(), name)
+    LOG.launches += _LAUNCHES.get(name, 1)
+    if LOG.timing:
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        LOG.events.append((name, a, b))
+    else:
+        rc = fn(*args)
+    _lib.check(rc)
+
+
 # per-device scratch for the per-CTA partial reductions
 _scratch = {}
 
@@ -69,8 +113,8 @@ def pack_rows(x: torch.Tensor) -> torch.Tensor:
     B, Cn, N = x.shape
     c4 = (Cn + 3) // 4 * 4
     rows = torch.empty(B * N, c4, dtype=torch.float32, device=x.device)
-    _lib.check(_lib.load().dgcnn_pack_rows_f32(_ptr(x), x.stride(0), x.stride(1), x.stride(2), B, Cn, N,
-                                               _ptr(rows), c4, _stream()))
+    _call("dgcnn_pack_rows_f32", _ptr(x), x.stride(0), x.stride(1), x.stride(2), B, Cn, N,
+                                               _ptr(rows), c4, _stream())
     return rows
 
 
@@ -78,7 +122,7 @@ def unpack_rows(rows: torch.Tensor, B: int, Cn: int, N: int) -> torch.Tensor:
     """rows [B*N, >=C] -> contiguous [B,C,N]."""
     rows, ld = _rows_view(rows)
     y = torch.empty(B, Cn, N, dtype=torch.float32, device=rows.device)
-    _lib.check(_lib.load().dgcnn_unpack_rows_f32(_ptr(rows), ld, B, Cn, N, _ptr(y), _stream()))
+    _call("dgcnn_unpack_rows_f32", _ptr(rows), ld, B, Cn, N, _ptr(y), _stream())
     return y
 
 
@@ -91,7 +135,7 @@ def knn_rows(rows: torch.Tensor, B: int, Cn: int, N: int, k: int) -> torch.Tenso
     rows, ld = _rows_view(rows)
     idx = torch.empty(B * N, k, dtype=torch.int32, device=rows.device)
     norms = torch.empty(B * N, dtype=torch.float32, device=rows.device)
-    _lib.check(_lib.load().dgcnn_knn_f32(_ptr(rows), ld, B, Cn, N, k, _ptr(idx), _ptr(norms), _stream()))
+    _call("dgcnn_knn_f32", _ptr(rows), ld, B, Cn, N, k, _ptr(idx), _ptr(norms), _stream())
     return idx
 
 
@@ -99,7 +143,7 @@ def graph_feature_rows(rows: torch.Tensor, idx: torch.Tensor, B: int, Cn: int, N
     """[B,N,k,2C] edge-feature buffer (model.py:74-81); API-parity path, not used by DGCNN.forward."""
     rows, ld = _rows_view(rows)
     out = torch.empty(B, N, k, 2 * Cn, dtype=torch.float32, device=rows.device)
-    _lib.check(_lib.load().dgcnn_graph_feature_f32(_ptr(rows), ld, _ptr(idx), B, Cn, N, k, _ptr(out), _stream()))
+    _call("dgcnn_graph_feature_f32", _ptr(rows), ld, _ptr(idx), B, Cn, N, k, _ptr(out), _stream())
     return out
 
 
@@ -135,7 +179,7 @@ def edgeconv_eval(rows: torch.Tensor, idx: torch.Tensor, B: int, Cn: int, N: int
     wa = w_a.detach().reshape(COUT, -1).contiguous()
     wb = None if w_b is None else w_b.detach().reshape(COUT, COUT).contiguous()
     a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, out, COUT)
-    _lib.check(_lib.load().dgcnn_edgeconv_fwd_eval(C.byref(a), _ptr(aff_a), _ptr(aff_b), _stream()))
+    _call("dgcnn_edgeconv_fwd_eval", C.byref(a), _ptr(aff_a), _ptr(aff_b), _stream())
     return out
 
 
@@ -170,22 +214,22 @@ class EdgeConvTrain(torch.autograd.Function):
         stat_a = torch.empty(2 + 3, COUT, **f32)     # mean, rstd, affine(mean|scale|beta)
         a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, None, COUT)
 
-        _lib.check(lib.dgcnn_edgeconv_conv_a_train(C.byref(a), _ptr(y_a), _ptr(partials), _ptr(ymax), _ptr(ymin),
-                                                   _ptr(amax), _ptr(amin), st))
-        _lib.check(lib.dgcnn_bn_finalize(_ptr(partials), COUT, float(E), _ptr(gamma_a.detach()), _ptr(beta_a.detach()),
+        _call("dgcnn_edgeconv_conv_a_train", C.byref(a), _ptr(y_a), _ptr(partials), _ptr(ymax), _ptr(ymin),
+                                                   _ptr(amax), _ptr(amin), st)
+        _call("dgcnn_bn_finalize", _ptr(partials), COUT, float(E), _ptr(gamma_a.detach()), _ptr(beta_a.detach()),
                                          bn_a.eps, bn_a.momentum, _ptr(bn_a.running_mean), _ptr(bn_a.running_var),
-                                         _ptr(stat_a[0]), _ptr(stat_a[1]), _ptr(stat_a[2:]), st))
+                                         _ptr(stat_a[0]), _ptr(stat_a[1]), _ptr(stat_a[2:]), st)
         stat_b = None
         if two:
             stat_b = torch.empty(2 + 3, COUT, **f32)
-            _lib.check(lib.dgcnn_edgeconv_conv_b_train(C.byref(a), _ptr(y_a), _ptr(stat_a[2:]), _ptr(partials),
-                                                       _ptr(ymax), _ptr(ymin), _ptr(amax), _ptr(amin), st))
-            _lib.check(lib.dgcnn_bn_finalize(_ptr(partials), COUT, float(E), _ptr(gamma_b.detach()), _ptr(beta_b.detach()),
+            _call("dgcnn_edgeconv_conv_b_train", C.byref(a), _ptr(y_a), _ptr(stat_a[2:]), _ptr(partials),
+                                                       _ptr(ymax), _ptr(ymin), _ptr(amax), _ptr(amin), st)
+            _call("dgcnn_bn_finalize", _ptr(partials), COUT, float(E), _ptr(gamma_b.detach()), _ptr(beta_b.detach()),
                                              bn_b.eps, bn_b.momentum, _ptr(bn_b.running_mean), _ptr(bn_b.running_var),
-                                             _ptr(stat_b[0]), _ptr(stat_b[1]), _ptr(stat_b[2:]), st))
+                                             _ptr(stat_b[0]), _ptr(stat_b[1]), _ptr(stat_b[2:]), st)
         last = stat_b if two else stat_a
-        _lib.check(lib.dgcnn_edgeconv_select(M, _ptr(ymax), _ptr(ymin), _ptr(amax), _ptr(amin), _ptr(last[2:]),
-                                             _ptr(out), COUT, _ptr(ysel), _ptr(arg), st))
+        _call("dgcnn_edgeconv_select", M, _ptr(ymax), _ptr(ymin), _ptr(amax), _ptr(amin), _ptr(last[2:]),
+                                             _ptr(out), COUT, _ptr(ysel), _ptr(arg), st)
         ctx.meta = meta
         ctx.two = two
         ctx.save_for_backward(rows, idx, wa, wb if two else wa, gamma_a.detach(), gamma_b.detach() if two else gamma_a.detach(),
@@ -212,28 +256,28 @@ class EdgeConvTrain(torch.autograd.Function):
         g = torch.empty(M, COUT, **f32)
         last = stat_b if two else stat_a
         gamma_last = gamma_b if two else gamma_a
-        _lib.check(lib.dgcnn_edgeconv_bwd_prep(M, _ptr(dout), dout.stride(0), _ptr(ysel), _ptr(last[2:]), _ptr(g),
-                                               _ptr(partials), st))
+        _call("dgcnn_edgeconv_bwd_prep", M, _ptr(dout), dout.stride(0), _ptr(ysel), _ptr(last[2:]), _ptr(g),
+                                               _ptr(partials), st)
         dgl = torch.empty(2, COUT, **f32)      # dgamma, dbeta of the last BN
         coef_l = torch.empty(3, COUT, **f32)
-        _lib.check(lib.dgcnn_bn_bwd_reduce(_ptr(partials), COUT, float(E), _ptr(gamma_last), _ptr(last[0]), _ptr(last[1]),
-                                           _ptr(dgl[0]), _ptr(dgl[1]), _ptr(coef_l), st))
+        _call("dgcnn_bn_bwd_reduce", _ptr(partials), COUT, float(E), _ptr(gamma_last), _ptr(last[0]), _ptr(last[1]),
+                                           _ptr(dgl[0]), _ptr(dgl[1]), _ptr(coef_l), st)
         dw_b = dga = None
         if two:
             dz_a = torch.empty(E, COUT, **f32)
             dw_b = torch.empty(COUT, COUT, **f32)
-            _lib.check(lib.dgcnn_edgeconv_bwd_b(C.byref(a), _ptr(y_a), _ptr(stat_a[2:]), _ptr(g), _ptr(arg), _ptr(coef_l),
-                                                _ptr(dz_a), _ptr(dw_b), _ptr(partials), _ptr(dw_partials), st))
+            _call("dgcnn_edgeconv_bwd_b", C.byref(a), _ptr(y_a), _ptr(stat_a[2:]), _ptr(g), _ptr(arg), _ptr(coef_l),
+                                                _ptr(dz_a), _ptr(dw_b), _ptr(partials), _ptr(dw_partials), st)
             dga = torch.empty(2, COUT, **f32)
             coef_a = torch.empty(3, COUT, **f32)
-            _lib.check(lib.dgcnn_bn_bwd_reduce(_ptr(partials), COUT, float(E), _ptr(gamma_a), _ptr(stat_a[0]), _ptr(stat_a[1]),
-                                               _ptr(dga[0]), _ptr(dga[1]), _ptr(coef_a), st))
+            _call("dgcnn_bn_bwd_reduce", _ptr(partials), COUT, float(E), _ptr(gamma_a), _ptr(stat_a[0]), _ptr(stat_a[1]),
+                                               _ptr(dga[0]), _ptr(dga[1]), _ptr(coef_a), st)
         else:
             dz_a, coef_a, dga = None, coef_l, dgl
         s = torch.empty(M, COUT, **f32)
         r = torch.zeros(M, COUT, **f32)
-        _lib.check(lib.dgcnn_edgeconv_bwd_a(C.byref(a), _ptr(y_a), _ptr(dz_a), _ptr(g), _ptr(arg), _ptr(coef_a),
-                                            _ptr(s), _ptr(r), st))
+        _call("dgcnn_edgeconv_bwd_a", C.byref(a), _ptr(y_a), _ptr(dz_a), _ptr(g), _ptr(arg), _ptr(coef_a),
+                                            _ptr(s), _ptr(r), st)
         # point-level GEMMs (M x 64 x C): dX = r Wa1 + s (Wa2 - Wa1);  dWa = [(r - s)^T X | s^T X]
         X = rows[:, :Cn]
         wa1, wa2 = wa[:, :Cn], wa[:, Cn:]
