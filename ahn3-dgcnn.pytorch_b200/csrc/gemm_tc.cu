@@ -1,0 +1,214 @@
+// gemm_tc.cu — FP32-accurate GEMM on the 5th-gen tensor cores:  D[M,N] = A[M,K] * B[N,K]^T  (FP32 in/out).
+//
+// Operands are pre-split into bf16 planes in the swizzled unit format of tc.cuh (split_planes_kernel), staged
+// with bulk async copies through an mbarrier ring, multiplied with tcgen05.mma (accumulator in TMEM) by one
+// elected thread, and read back with tcgen05.ld by four epilogue warps.  Used for the dense GEMMs of the
+// shared MLP / segmentation head (model.py:167-193) and as the validation vehicle for the tcgen05 primitives
+// that the tensor-core kNN and EdgeConv kernels build on.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace dg {
+
+// ---------------------------------------------------------------------------------------------
+// FP32 [R,K] (element strides sr, sc) -> NS bf16 planes in 64x64 swizzled units, zero padded to R_pad x K_pad.
+// One thread produces one 16-byte chunk (8 consecutive k) of every plane.
+// ---------------------------------------------------------------------------------------------
+template <int NS>
+__global__ void split_planes_kernel(const float* __restrict__ X, long long sr, long long sc, int R, int K, int R_pad,
+                                    int KA, unsigned char* __restrict__ out) {
+  const long long total = static_cast<long long>(R_pad) * KA * 8;   // chunks
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // consecutive threads walk the 8 chunks of a row, then the rows of a unit: 128-byte coalesced stores
+    const int ch = static_cast<int>(i & 7);
+    const long long t = i >> 3;
+    const int rl = static_cast<int>(t & 63);
+    const long long u = t >> 6;              // unit index = rt * KA + ka
+    const int ka = static_cast<int>(u % KA);
+    const int rt = static_cast<int>(u / KA);
+    const int r = rt * 64 + rl, c0 = ka * 64 + ch * 8;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = c0 + e;
+      v[e] = (r < R && c < K) ? X[r * sr + c * sc] : 0.f;
+    }
+    unsigned char* unit = out + static_cast<size_t>(u) * NS * tc::kUnitBytes;
+    const uint32_t off = tc::unit_elem_offset(rl, ch * 8);
+#pragma unroll
+    for (int p = 0; p < NS; ++p) {
+      __nv_bfloat16 h[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        h[e] = __float2bfloat16_rn(v[e]);
+        v[e] -= __bfloat162float(h[e]);       // exact in FP32
+      }
+      *reinterpret_cast<uint4*>(unit + static_cast<size_t>(p) * tc::kUnitBytes + off) = *reinterpret_cast<const uint4*>(h);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM kernel: one 128 x BN output tile per CTA, K streamed in 64-wide atoms through a STAGES-deep ring.
+// warp 0: bulk-copy producer | warp 1: TMEM owner + MMA issuer | warps 2-5: epilogue (one TMEM lane quarter each)
+// ---------------------------------------------------------------------------------------------
+template <int NS, int BN, int STAGES>
+struct GemmSmem {
+  static constexpr uint32_t a_plane = 128 * 128;          // 128 rows x 128 B
+  static constexpr uint32_t b_plane = BN * 128;
+  static constexpr uint32_t stage = NS * (a_plane + b_plane);
+  static constexpr uint32_t bytes = STAGES * stage + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int NS, int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __restrict__ Bp, float* __restrict__ D,
+               int ldd, int M, int N, int KA) {
+  using SM = GemmSmem<NS, BN, STAGES>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * SM::stage);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accfull = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = blockIdx.x, mt = blockIdx.y;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(full + s, 1);
+      tc::mbar_init(empty + s, 1);
+    }
+    tc::mbar_init(accfull, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, BN);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t taddr = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int ka = 0; ka < KA; ++ka) {
+        const int s = ka % STAGES;
+        tc::mbar_wait(empty + s, ((ka / STAGES) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(full + s, SM::stage);
+        unsigned char* a_s = tiles + s * SM::stage;
+        unsigned char* b_s = a_s + NS * SM::a_plane;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const unsigned char* src = Ap + (static_cast<size_t>(2 * mt + h) * KA + ka) * NS * tc::kUnitBytes;
+#pragma unroll
+          for (int p = 0; p < NS; ++p)
+            tc::bulk_g2s(a_s + p * SM::a_plane + h * tc::kUnitBytes, src + p * tc::kUnitBytes, tc::kUnitBytes, full + s);
+        }
+#pragma unroll
+        for (int h = 0; h < BN / 64; ++h) {
+          const unsigned char* src = Bp + (static_cast<size_t>(nt * (BN / 64) + h) * KA + ka) * NS * tc::kUnitBytes;
+#pragma unroll
+          for (int p = 0; p < NS; ++p)
+            tc::bulk_g2s(b_s + p * SM::b_plane + h * tc::kUnitBytes, src + p * tc::kUnitBytes, tc::kUnitBytes, full + s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::idesc_bf16(128, BN);
+      for (int ka = 0; ka < KA; ++ka) {
+        const int s = ka % STAGES;
+        tc::mbar_wait(full + s, (ka / STAGES) & 1);
+        tc::fence_after_sync();
+        const uint32_t a_s = tc::smem_u32(tiles + s * SM::stage);
+        tc::mma_split_katom<NS>(taddr, a_s, SM::a_plane, a_s + NS * SM::a_plane, SM::b_plane, idesc, ka == 0);
+        tc::mma_commit(empty + s);       // frees the stage once these MMAs have read it
+      }
+      tc::mma_commit(accfull);
+    }
+  } else {
+    const int quarter = warp & 3;        // TMEM lanes this warp may read: 32*quarter .. +31
+    tc::mbar_wait(accfull, 0);
+    tc::fence_after_sync();
+    const int row = mt * 128 + quarter * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
+      const int n0 = nt * BN + c0;
+      if (row < M) {
+        float* dst = D + static_cast<size_t>(row) * ldd + n0;
+        if (n0 + 32 <= N && (ldd & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (n0 + i < N) dst[i] = v[i];
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(taddr, BN);
+}
+
+static size_t planes_bytes(int rows_pad, int KA, int NS) {
+  return static_cast<size_t>(rows_pad / 64) * KA * NS * tc::kUnitBytes;
+}
+
+template <int NS>
+static int launch_split(const float* X, long long sr, long long sc, int R, int K, int R_pad, int KA, unsigned char* out,
+                        cudaStream_t st) {
+  const long long total = static_cast<long long>(R_pad) * KA * 8;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
+  split_planes_kernel<NS><<<blocks, 256, 0, st>>>(X, sr, sc, R, K, R_pad, KA, out);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}
+
+template <int NS, int BN, int STAGES>
+static int launch_gemm(const unsigned char* Ap, const unsigned char* Bp, float* D, int ldd, int M, int N, int KA,
+                       cudaStream_t st) {
+  using SM = GemmSmem<NS, BN, STAGES>;
+  auto kern = tc_gemm_kernel<NS, BN, STAGES>;
+  DG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SM::bytes)));
+  dim3 grid((N + BN - 1) / BN, (M + 127) / 128);
+  kern<<<grid, 192, SM::bytes, st>>>(Ap, Bp, D, ldd, M, N, KA);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}
+
+}  // namespace dg
+
+using namespace dg;
+
+extern "C" size_t dgcnn_tc_gemm_workspace_bytes(int M, int N, int K, int nsplit) {
+  if (M <= 0 || N <= 0 || K <= 0 || nsplit < 2 || nsplit > 3) return 0;
+  const int KA = (K + 63) / 64;
+  return planes_bytes((M + 127) / 128 * 128, KA, nsplit) + planes_bytes((N + 127) / 128 * 128, KA, nsplit) + 2048;
+}
+
+extern "C" int dgcnn_tc_gemm_f32(const float* A, int64_t a_sr, int64_t a_sc, const float* B, int64_t b_sr, int64_t b_sc,
+                                 float* D, int ldd, int M, int N, int K, int nsplit, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  DG_REQUIRE(A && B && D && workspace, DGCNN_E_INVALID, "tc_gemm: null pointer");
+  DG_REQUIRE(M > 0 && N > 0 && K > 0 && ldd >= N, DGCNN_E_INVALID, "tc_gemm: bad shape M=%d N=%d K=%d ldd=%d", M, N, K, ldd);
+  DG_REQUIRE(nsplit == 2 || nsplit == 3, DGCNN_E_UNSUPPORTED, "tc_gemm: nsplit must be 2 or 3");
+  DG_REQUIRE(workspace_bytes >= dgcnn_tc_gemm_workspace_bytes(M, N, K, nsplit), DGCNN_E_WORKSPACE, "tc_gemm: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int KA = (K + 63) / 64, Mp = (M + 127) / 128 * 128, Np = (N + 127) / 128 * 128;
+  unsigned char* Ap = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  unsigned char* Bp = Ap + planes_bytes(Mp, KA, nsplit);
+  int rc;
+  if (nsplit == 3) {
+    if ((rc = launch_split<3>(A, a_sr, a_sc, M, K, Mp, KA, Ap, st))) return rc;
+    if ((rc = launch_split<3>(B, b_sr, b_sc, N, K, Np, KA, Bp, st))) return rc;
+    return launch_gemm<3, 128, 2>(Ap, Bp, D, ldd, M, N, KA, st);
+  }
+  if ((rc = launch_split<2>(A, a_sr, a_sc, M, K, Mp, KA, Ap, st))) return rc;
+  if ((rc = launch_split<2>(B, b_sr, b_sc, N, K, Np, KA, Bp, st))) return rc;
+  return launch_gemm<2, 128, 3>(Ap, Bp, D, ldd, M, N, KA, st);
+}

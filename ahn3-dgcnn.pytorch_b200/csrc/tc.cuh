@@ -1,0 +1,154 @@
+// tc.cuh — Blackwell (sm_100a) tensor-core primitives written as inline PTX: tcgen05.mma / TMEM / mbarrier /
+// bulk async copy.  No CUTLASS.  Bit layouts follow the PTX ISA "tcgen05" matrix/instruction descriptors.
+//
+// Operand format used everywhere ("split planes"): an FP32 matrix X[R, K] is pre-split into NS bf16 planes
+// x = x1 + x2 (+ x3) (each the round-to-nearest bf16 of the remaining residual) and stored as units of
+// 64 rows x 64 K-elements = 64 x 128 B, K-major, already in the 128-byte-swizzle pattern the MMA expects:
+//     unit(rt, ka, p) at ((rt * KA + ka) * NS + p) * 8192 bytes,
+//     element (r, c) of the unit at  r*128 + (((c>>3) ^ (r&7)) << 4) + (c&7)*2.
+// A unit is one contiguous 8 KB block, so staging a tile into shared memory is a plain bulk copy (UBLKCP),
+// and any 1024-byte aligned destination reproduces the swizzle phase.
+// FP32-accurate products: D = sum over plane pairs (i,j), i+j <= NS+1, of X_i * Y_j^T accumulated in TMEM (FP32):
+// NS=2 -> 3 MMAs (rel. error ~2^-17, used as a kNN *filter*), NS=3 -> 6 MMAs (rel. error ~2^-24, "FP32-accurate").
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace dg {
+namespace tc {
+
+constexpr int kUnitRows = 64;
+constexpr int kUnitK = 64;
+constexpr int kUnitBytes = kUnitRows * kUnitK * 2;  // 8192
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier -----------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// ---- bulk async copy global -> shared (TMA engine, 1-D) ---------------------------------------------
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// make generic-proxy shared-memory writes visible to the async proxy (tensor core / TMA)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMEM ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {  // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // same warp that allocated
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 lanes x 32 consecutive columns: thread t of the warp receives TMEM lane (lane_base + t), columns col..col+31.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- descriptors --------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);            // start address | LBO = 16 B (unused for SW128 K-major)
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);           // SBO = 1024 B | version 1 (sm_100) | SWIZZLE_128B
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+// Instruction descriptor: kind::f16, A/B = bf16, D = f32, both K-major, shape M x N (x K=16).
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
+__device__ __forceinline__ void mma_bf16(uint32_t taddr, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(taddr),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when all MMAs issued so far by this thread have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Issue the split-precision product of one 64-wide K atom: A planes at a_s (+ p*a_plane bytes), B likewise.
+// Pairs are issued smallest-magnitude first.  `first` = true overwrites the accumulator with the first MMA.
+template <int NS>
+__device__ __forceinline__ void mma_split_katom(uint32_t taddr, uint32_t a_s, uint32_t a_plane, uint32_t b_s,
+                                                uint32_t b_plane, uint32_t idesc, bool first) {
+  uint32_t acc = first ? 0u : 1u;
+#pragma unroll
+  for (int sum = NS + 1; sum >= 2; --sum) {
+#pragma unroll
+    for (int i = 1; i <= NS; ++i) {
+      const int j = sum - i;
+      if (j < 1 || j > NS) continue;
+      const uint32_t a0 = a_s + (i - 1) * a_plane, b0 = b_s + (j - 1) * b_plane;
+#pragma unroll
+      for (int k16 = 0; k16 < kUnitK / 16; ++k16) {
+        mma_bf16(taddr, smem_desc_sw128(a0 + k16 * 32), smem_desc_sw128(b0 + k16 * 32), idesc, acc);
+        acc = 1u;
+      }
+    }
+  }
+}
+
+// ---- split-plane element address (shared with the prep kernels) ------------------------------------------
+__host__ __device__ constexpr uint32_t unit_elem_offset(int r, int c) {
+  return static_cast<uint32_t>(r * 128 + ((((c >> 3) ^ (r & 7)) & 7) << 4) + (c & 7) * 2);
+}
+
+}  // namespace tc
+}  // namespace dg

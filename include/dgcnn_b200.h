@@ -127,6 +127,17 @@ int dgcnn_edgeconv_bwd_a(const dgcnn_edgeconv_args* a, const float* y_a, const f
                          const float* g, const uint8_t* arg, const float* coef_a,
                          float* s, float* r, void* stream);
 
+/* ---- FP32-accurate tensor-core GEMM (tcgen05, bf16 split planes):  D[M,N] = A[M,K] * B[N,K]^T ---------------
+ * A and B are FP32 with arbitrary element strides (row stride, column stride), so transposed operands need no
+ * copy.  nsplit = 3: six bf16 MMAs per product, relative error ~2^-24 ("FP32-accurate", the dense GEMMs of the
+ * shared MLP / head, model.py:167-193);  nsplit = 2: three MMAs, ~2^-17 (filter precision).
+ * workspace: dgcnn_tc_gemm_workspace_bytes(M,N,K,nsplit) bytes of device scratch.                          */
+size_t dgcnn_tc_gemm_workspace_bytes(int M, int N, int K, int nsplit);
+int dgcnn_tc_gemm_f32(const float* A, int64_t a_row_stride, int64_t a_col_stride,
+                      const float* B, int64_t b_row_stride, int64_t b_col_stride,
+                      float* D, int ldd, int M, int N, int K, int nsplit,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -295,9 +295,12 @@ def test_batch_independence_eval(pkg):
     x = common.points(71, B, Fd, N, "real").to(DEV)
     net = pkg.DGCNN(5, Fd, k, cuda=True)
     net.eval()
-    full = net(x)
+    full, full3 = net(x), net(x, depth=3)
     for b in range(B):
-        assert torch.equal(net(x[b:b + 1]), full[b:b + 1])
+        # our kernels are per-block deterministic: EdgeConv output is bit-identical for any batch composition
+        assert torch.equal(net(x[b:b + 1], depth=3), full3[b:b + 1])
+        # the head's library GEMMs may pick another tiling for another M: equal to FP32 rounding only
+        torch.testing.assert_close(net(x[b:b + 1]), full[b:b + 1], rtol=1e-4, atol=1e-5)
 
 
 def test_state_dict_roundtrip(pkg):
