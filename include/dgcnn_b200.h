@@ -51,6 +51,15 @@ int dgcnn_unpack_rows_f32(const float* rows, int ld, int B, int C, int N, float*
 int dgcnn_knn_f32(const float* rows, int ld, int B, int C, int N, int k,
                   int32_t* idx, float* norms, void* stream);
 
+/* ---- tensor-core kNN (model.py:25-40 for the 64-channel feature-space graphs) ---------------------------------
+ * Same result as dgcnn_knn_f32, bit for bit: tcgen05 Gram tiles on a 2-plane bf16 split act as a filter
+ * (64 candidates per query + a rigorous error bound), survivors are re-scored with the exact FP32 expression,
+ * rows that cannot be certified are redone by brute force.  Needs 16 < C <= 64, k <= 48, N >= 128.         */
+int dgcnn_knn_tc_supported(int C, int N, int k);
+size_t dgcnn_knn_tc_workspace_bytes(int B, int N);
+int dgcnn_knn_tc_f32(const float* rows, int ld, int B, int C, int N, int k, int32_t* idx,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- get_graph_feature (model.py:43-83), materialising form kept for API parity -------------------
  * out[B,N,k,2C] = cat(x_j - x_i, x_i); the reference returns permute(0,3,1,2) of this buffer.        */
 int dgcnn_graph_feature_f32(const float* rows, int ld, const int32_t* idx, int B, int C, int N, int k,
