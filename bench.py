@@ -148,8 +148,10 @@ def kernel_flops(name: str, calls_per_step: int, B: int):
     """Algorithmic FLOPs of ALL launches of one entry point in one step."""
     M = B * NPTS
     E = M * KNN
-    if name == "dgcnn_knn_f32":                       # 3 graphs: C=4, 64, 64 ; 2*B*N^2*C each
-        return 2.0 * B * NPTS * NPTS * (FEAT + 64 + 64)
+    if name == "dgcnn_knn_f32":                       # xyz/agl graph (C=4): 2*B*N^2*C
+        return 2.0 * B * NPTS * NPTS * FEAT
+    if name == "dgcnn_knn_tc_f32":                    # two feature-space graphs (C=64)
+        return 2.0 * B * NPTS * NPTS * (64 + 64)
     if name == "dgcnn_edgeconv_conv_a_train":         # conv1 (2F->64), conv3, conv5 (128->64)
         return 2.0 * E * 64 * (2 * FEAT + 128 + 128)
     if name == "dgcnn_edgeconv_conv_b_train":         # conv2, conv4 (64->64)

@@ -53,7 +53,7 @@ def test_tc_gemm_transposed_operands(pkg):
     Bt = torch.randn(192, 256, generator=g).to(DEV)      # B = Bt^T  (N=256)
     D = _gemm(pkg, At.t(), Bt.t(), 3)
     ref = (At.double().t() @ Bt.double())
-    assert ((D.double() - ref).abs().max() / ref.abs().max()).item() < 1e-6
+    assert ((D.double() - ref).abs().max() / ref.abs().max()).item() < 4e-6
 
 
 # ---------------------------------------------------------------------------------------------- tensor-core kNN
