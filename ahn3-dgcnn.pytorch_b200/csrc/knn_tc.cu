@@ -2,7 +2,8 @@
 //
 // Gram tiles are computed by tcgen05.mma on a 2-plane bf16 split of the features (3 MMAs per product,
 // |error| <= ~2e-5 * |x_i||x_j|) into TMEM; the approximate scores only act as a FILTER:
-//   * every query keeps its KP = 64 best approximate candidates (streaming, warp-cooperative sorted lists);
+//   * every query keeps its 64 best approximate candidates (streaming: per-row candidate buffers + warp-level
+//     bitonic merges, select.cuh);
 //   * with eps_i a rigorous bound on |approx - exact| for row i, every true top-k neighbour has
 //     approx >= t_k - 2 eps_i (t_k = k-th best approximate score), so if the 64-th candidate is below that
 //     cut the candidate list provably contains the exact top-k ("certificate");
@@ -13,12 +14,11 @@
 // The B x N x N matrix never leaves the SM: scores go TMEM -> registers -> shared memory -> selection.
 #include "common.cuh"
 #include "tc.cuh"
+#include "select.cuh"
 
 namespace dg {
 
-constexpr int kKP = 64;                 // candidates kept per query (2 per lane)
 constexpr int kTcKeyTile = 64;          // keys per MMA tile (UMMA N)
-constexpr int kTcSld = kTcKeyTile + 4;  // S row stride (floats): 16-byte stores from 32 rows are conflict-free
 constexpr uint32_t kTileBytes = 2 * tc::kUnitBytes + kTcKeyTile * 4;   // plane0 | plane1 | 64 key norms
 constexpr uint32_t kStageBytes = 17 * 1024;                             // smem slot (planes stay 1024-aligned)
 constexpr int kTcStages = 3;
@@ -93,28 +93,6 @@ __global__ void knn_norms_max_kernel(const float* __restrict__ rows, int ld, int
   if ((threadIdx.x & 31) == 0) atomicMax(maxnorm_bits + b, m);
 }
 
-// ---------------------------------------------------------------------------------------------
-// warp-cooperative sorted list with 2 entries per lane (position = r*32 + lane), see knn.cu
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long list2_at(const unsigned long long (&lst)[2], int pos) {
-  const unsigned long long w0 = __shfl_sync(0xffffffffu, lst[0], pos & 31);
-  const unsigned long long w1 = __shfl_sync(0xffffffffu, lst[1], pos & 31);
-  return (pos >> 5) ? w1 : w0;
-}
-__device__ __forceinline__ void list2_insert(unsigned long long (&lst)[2], unsigned long long c, int lane) {
-  const unsigned long long up0 = __shfl_up_sync(0xffffffffu, lst[0], 1);
-  const unsigned long long up1 = __shfl_up_sync(0xffffffffu, lst[1], 1);
-  const unsigned long long wrap = __shfl_sync(0xffffffffu, lst[0], 31);
-  const unsigned long long p0 = lane == 0 ? ~0ull : up0;
-  const unsigned long long p1 = lane == 0 ? wrap : up1;
-  lst[0] = lst[0] >= c ? lst[0] : (p0 >= c ? c : p0);
-  lst[1] = lst[1] >= c ? lst[1] : (p1 >= c ? c : p1);
-}
-__device__ __forceinline__ float key_score(unsigned long long key) {
-  const uint32_t u = static_cast<uint32_t>(key >> 32);
-  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
-}
-
 // exact reference score of (query row xi, key row xj): FMA chain over channels, then the two rounded subtractions
 __device__ __forceinline__ float exact_score(const float* __restrict__ xi, const float* __restrict__ xj, int C4,
                                              float norm_i, float norm_j) {
@@ -133,22 +111,22 @@ __device__ __forceinline__ float exact_score(const float* __restrict__ xi, const
 struct KnnTcSmem {
   static constexpr uint32_t a_bytes = 2 * 128 * 128;                        // two planes of 128 query rows
   static constexpr uint32_t b_off = a_bytes;
-  static constexpr uint32_t s_off = b_off + kTcStages * kStageBytes;
-  static constexpr uint32_t l_off = s_off + 128 * kTcSld * 4;
-  static constexpr uint32_t bar_off = l_off + 128 * kKP * 8;
+  static constexpr uint32_t sel_off = b_off + kTcStages * kStageBytes;
+  static constexpr uint32_t bar_off = sel_off + static_cast<uint32_t>(sel::kSmemBytes);
   static constexpr uint32_t bytes = bar_off + 128 + 1024;
 };
 
+// Thread mapping of the scan: warp w reads TMEM lane quarter (w & 3) and column half (w >> 2); thread = one query
+// row x 32 keys per tile, scores stay in registers.  Compaction: warp w owns rows 16w .. 16w+15.
 __global__ void __launch_bounds__(kThreads, 1)
 knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__ rows, int ld,
               const float* __restrict__ norms, const unsigned int* __restrict__ maxnorm_bits, int N, int C4, int T,
-              int k, int32_t* __restrict__ idx, int* __restrict__ fb_count, int* __restrict__ fb_rows) {
+              int k, int kp, int32_t* __restrict__ idx, int* __restrict__ fb_count, int* __restrict__ fb_rows) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* As = sm;
   unsigned char* Bs = sm + KnnTcSmem::b_off;
-  float* Ss = reinterpret_cast<float*>(sm + KnnTcSmem::s_off);
-  unsigned long long* Ls = reinterpret_cast<unsigned long long*>(sm + KnnTcSmem::l_off);
+  const sel::Smem S = sel::carve(sm + KnnTcSmem::sel_off);
   uint64_t* abar = reinterpret_cast<uint64_t*>(sm + KnnTcSmem::bar_off);
   uint64_t* full = abar + 1;               // [kTcStages]
   uint64_t* accfull = full + kTcStages;    // [2]
@@ -167,7 +145,7 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, 128);            // two 64-column accumulators
-  for (int i = tid; i < 128 * kKP; i += kThreads) Ls[i] = 0ull;
+  sel::init(S, tid, kThreads);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -195,8 +173,9 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
   }
   __syncwarp();
 
-  const int quarter = warp & 3, chalf = warp >> 2;          // TMEM lane quarter / column half read by this warp
-  const int erow = quarter * 32 + lane;                     // epilogue: this thread's query row
+  const int quarter = warp & 3, chalf = warp >> 2;
+  const int erow = quarter * 32 + lane;                     // scan: this thread's query row
+  const bool row_ok = q0 + erow < N;
 
   for (int t = 0; t < Tk; ++t) {
     if (tid == 0 && t + 1 < Tk) {                           // keep the tensor pipe one tile ahead of the selection
@@ -214,57 +193,25 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
       float v[32];
       tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + (t & 1) * kTcKeyTile + chalf * 32, v);
       const float* kn = reinterpret_cast<const float*>(Bs + (t % kTcStages) * kStageBytes + 2 * tc::kUnitBytes) + chalf * 32;
-      float* dst = Ss + erow * kTcSld + chalf * 32;
+      const float thr = S.thr[erow];
+      const int j0 = t * kTcKeyTile + chalf * 32;
+      const int jn = row_ok ? N - j0 : 0;                   // keys j0+i with i < jn exist
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float4 o;
-        o.x = __fmaf_rn(v[i + 0], 2.0f, -kn[i + 0]);
-        o.y = __fmaf_rn(v[i + 1], 2.0f, -kn[i + 1]);
-        o.z = __fmaf_rn(v[i + 2], 2.0f, -kn[i + 2]);
-        o.w = __fmaf_rn(v[i + 3], 2.0f, -kn[i + 3]);
-        *reinterpret_cast<float4*>(dst + i) = o;
+      for (int i = 0; i < 32; ++i) {
+        const float sc = __fmaf_rn(v[i], 2.0f, -kn[i]);     // approx of 2 x_i.x_j - |x_j|^2 (|x_i|^2 is constant per row)
+        if (sc > thr && i < jn) sel::push(S, erow, sc, j0 + i);
       }
     }
     tc::fence_before_sync();
-    __syncthreads();                                        // S complete; tile t's smem slot and accumulator are free
+    __syncthreads();                                        // pushes visible; tile t's smem slot and accumulator are free
     if (tid == 0 && t + kTcStages < Tk) {
       const int s = t % kTcStages;
       tc::mbar_arrive_expect_tx(full + s, kTileBytes);
       tc::bulk_g2s(Bs + s * kStageBytes, btiles + static_cast<size_t>(t + kTcStages) * kTileBytes, kTileBytes, full + s);
     }
     __syncwarp();
-    // fold the approximate score tile into the candidate lists (warp owns 16 query rows)
-    const int t0 = t * kTcKeyTile;
-    for (int rr = 0; rr < 16; ++rr) {
-      const int row = warp * 16 + rr;
-      if (q0 + row >= N) break;
-      unsigned long long lst[2];
-      lst[0] = Ls[(row * 2 + 0) * 32 + lane];
-      lst[1] = Ls[(row * 2 + 1) * 32 + lane];
-      unsigned long long thr = list2_at(lst, kKP - 1);
-      bool changed = false;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int col = lane + 32 * half, j = t0 + col;
-        const unsigned long long c = (j < N) ? make_key(Ss[row * kTcSld + col], j) : 0ull;
-        unsigned m = __ballot_sync(0xffffffffu, c > thr);
-        while (m) {
-          const int src = __ffs(m) - 1;
-          m &= m - 1;
-          const unsigned long long cc = __shfl_sync(0xffffffffu, c, src);
-          if (cc > thr) {
-            list2_insert(lst, cc, lane);
-            thr = list2_at(lst, kKP - 1);
-            changed = true;
-          }
-        }
-      }
-      if (changed) {
-        Ls[(row * 2 + 0) * 32 + lane] = lst[0];
-        Ls[(row * 2 + 1) * 32 + lane] = lst[1];
-      }
-    }
-    __syncthreads();                                        // S may be overwritten
+    sel::compact_rows(S, warp * 16, 16, lane, kp, t == Tk - 1 ? 1 : sel::kTrigger);
+    __syncthreads();                                        // thresholds / buffers consistent for the next scan
   }
 
   // ---- certificate + exact re-scoring + exact top-k (warp per query row) ---------------------------------
@@ -272,24 +219,26 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
   for (int rr = 0; rr < 16; ++rr) {
     const int row = warp * 16 + rr, q = q0 + row;
     if (q >= N) break;
-    unsigned long long lst[2];
-    lst[0] = Ls[(row * 2 + 0) * 32 + lane];
-    lst[1] = Ls[(row * 2 + 1) * 32 + lane];
+    const sel::u64 l0 = S.lists[(row * 2 + 0) * 32 + lane];
+    const sel::u64 l1 = S.lists[(row * 2 + 1) * 32 + lane];
     const size_t g = static_cast<size_t>(b) * N + q;
     const float norm_i = norms[g];
     const float ni = sqrtf(norm_i);
     const float eps = 1.01f * (kC1 * ni * rmax + kC2 * (ni + rmax) * (ni + rmax));
-    const float tk = key_score(list2_at(lst, k - 1));
+    const float tk = sel::key_score(sel::list_at(l0, l1, k - 1));
     const float cut = tk - 2.0f * eps;
-    const unsigned long long last = list2_at(lst, kKP - 1);
-    const bool overflow = last != 0ull && key_score(last) >= cut;
+    // every key whose approximate score exceeds the score at list position kp-1 is in the list; the list is
+    // complete above `cut` iff that position is empty or strictly below the cut
+    const sel::u64 last = sel::list_at(l0, l1, kp - 1);
+    const bool uncertified = (last != 0ull && sel::key_score(last) >= cut) || S.overflow[row] != 0;
     const float* xi = rows + g * ld;
-    unsigned long long ex[2];
+    sel::u64 ex[2];
+    const sel::u64 ls[2] = {l0, l1};
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       ex[r] = 0ull;
-      if (lst[r] != 0ull && key_score(lst[r]) >= cut) {
-        const int j = key_index(lst[r]);
+      if (ls[r] != 0ull && sel::key_score(ls[r]) >= cut) {
+        const int j = key_index(ls[r]);
         const size_t gj = static_cast<size_t>(b) * N + j;
         ex[r] = make_key(exact_score(xi, rows + gj * ld, C4, norm_i, norms[gj]), j);
       }
@@ -297,18 +246,32 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
     int rank0 = 0, rank1 = 0;
 #pragma unroll 4
     for (int s = 0; s < 32; ++s) {
-      const unsigned long long o0 = __shfl_sync(0xffffffffu, ex[0], s);
-      const unsigned long long o1 = __shfl_sync(0xffffffffu, ex[1], s);
+      const sel::u64 o0 = __shfl_sync(0xffffffffu, ex[0], s);
+      const sel::u64 o1 = __shfl_sync(0xffffffffu, ex[1], s);
       rank0 += (o0 > ex[0]) + (o1 > ex[0]);
       rank1 += (o0 > ex[1]) + (o1 > ex[1]);
     }
     if (ex[0] != 0ull && rank0 < k) idx[g * k + rank0] = key_index(ex[0]);
     if (ex[1] != 0ull && rank1 < k) idx[g * k + rank1] = key_index(ex[1]);
-    if (overflow && lane == 0) fb_rows[atomicAdd(fb_count, 1)] = static_cast<int>(g);
+    if (uncertified && lane == 0) fb_rows[atomicAdd(fb_count, 1)] = static_cast<int>(g);
   }
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(taddr, 128);
+}
+
+// warp-cooperative sorted insertion used by the brute-force fallback (2 keys per lane, position = r*32 + lane)
+__device__ __forceinline__ unsigned long long list2_at(const unsigned long long (&lst)[2], int pos) {
+  return sel::list_at(lst[0], lst[1], pos);
+}
+__device__ __forceinline__ void list2_insert(unsigned long long (&lst)[2], unsigned long long c, int lane) {
+  const unsigned long long up0 = __shfl_up_sync(0xffffffffu, lst[0], 1);
+  const unsigned long long up1 = __shfl_up_sync(0xffffffffu, lst[1], 1);
+  const unsigned long long wrap = __shfl_sync(0xffffffffu, lst[0], 31);
+  const unsigned long long p0 = lane == 0 ? ~0ull : up0;
+  const unsigned long long p1 = lane == 0 ? wrap : up1;
+  lst[0] = lst[0] >= c ? lst[0] : (p0 >= c ? c : p0);
+  lst[1] = lst[1] >= c ? lst[1] : (p1 >= c ? c : p1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -318,7 +281,7 @@ __global__ void __launch_bounds__(kThreads)
 knn_fallback_kernel(const float* __restrict__ rows, int ld, const float* __restrict__ norms, int N, int C4, int k,
                     int32_t* __restrict__ idx, const int* __restrict__ fb_count, const int* __restrict__ fb_rows) {
   __shared__ __align__(16) float xi[64];
-  __shared__ unsigned long long wl[8][kKP];
+  __shared__ unsigned long long wl[8][sel::kList];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int count = *fb_count;
   for (int f = blockIdx.x; f < count; f += gridDim.x) {
@@ -415,8 +378,9 @@ extern "C" int dgcnn_knn_tc_f32(const float* rows, int ld, int B, int C, int N, 
   knn_tc_prep_kernel<<<dim3(std::min((T * 512 + 255) / 256, 4096), B), 256, 0, st>>>(rows, ld, N, C4, T, norms, tiles);
   DG_CUDA(cudaGetLastError());
   DG_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(KnnTcSmem::bytes)));
-  knn_tc_kernel<<<dim3((N + 127) / 128, B), kThreads, KnnTcSmem::bytes, st>>>(tiles, rows, ld, norms, maxnorm, N, C4, T, k, idx,
-                                                                               fb_count, fb_rows);
+  const int kp = std::min(sel::kList, k + 16);     // list position that defines the pass threshold / certificate
+  knn_tc_kernel<<<dim3((N + 127) / 128, B), kThreads, KnnTcSmem::bytes, st>>>(tiles, rows, ld, norms, maxnorm, N, C4, T, k, kp,
+                                                                               idx, fb_count, fb_rows);
   DG_CUDA(cudaGetLastError());
   knn_fallback_kernel<<<64, kThreads, 0, st>>>(rows, ld, norms, N, C4, k, idx, fb_count, fb_rows);
   DG_CUDA(cudaGetLastError());

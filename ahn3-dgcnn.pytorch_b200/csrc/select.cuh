@@ -1,0 +1,147 @@
+// select.cuh — streaming top-K selection for 128 query rows of a CTA.
+//
+// Producers (one thread per query row, scores in registers) append every candidate that beats the row's current
+// threshold to a small per-row buffer in shared memory.  Between tiles, warps compact the rows whose buffer is
+// at least half full: bitonic sort of the buffered keys (shuffles), bitonic merge with the row's sorted list of 64
+// (2 keys per lane), new threshold = key at position kp-1.  Candidates are 64-bit keys (ordered score << 32 | ~idx),
+// so ties on the score prefer the lower index and all keys are distinct.
+#pragma once
+#include "common.cuh"
+
+namespace dg {
+namespace sel {
+
+constexpr int kRows = 128;
+constexpr int kList = 64;            // sorted list length per row (2 per lane)
+constexpr int kBufCap = 64;          // buffered candidates per row
+constexpr int kBufLd = kBufCap + 1;  // row stride of the buffer (u64): 2-way bank conflicts at most on producer stores
+constexpr int kTrigger = 32;         // compact when a buffer holds at least this many candidates
+
+typedef unsigned long long u64;
+
+struct Smem {
+  u64* lists;        // [kRows][2][32]
+  u64* buf;          // [kRows][kBufLd]
+  int* cnt;          // [kRows]
+  float* thr;        // [kRows]  current pass threshold (score of list position kp-1, or -inf)
+  int* overflow;     // [kRows]  a candidate was dropped because the buffer was full -> row needs the exact fallback
+};
+constexpr size_t kSmemBytes = static_cast<size_t>(kRows) * (kList * 8 + kBufLd * 8 + 4 + 4 + 4);
+
+__device__ __forceinline__ Smem carve(unsigned char* base) {   // base 8-byte aligned
+  Smem s;
+  s.lists = reinterpret_cast<u64*>(base);
+  s.buf = s.lists + kRows * kList;
+  s.cnt = reinterpret_cast<int*>(s.buf + kRows * kBufLd);
+  s.thr = reinterpret_cast<float*>(s.cnt + kRows);
+  s.overflow = reinterpret_cast<int*>(s.thr + kRows);
+  return s;
+}
+
+__device__ __forceinline__ void init(const Smem& s, int tid, int nthreads) {
+  for (int i = tid; i < kRows * kList; i += nthreads) s.lists[i] = 0ull;
+  for (int i = tid; i < kRows; i += nthreads) {
+    s.cnt[i] = 0;
+    s.thr[i] = -INFINITY;
+    s.overflow[i] = 0;
+  }
+}
+
+__device__ __forceinline__ float key_score(u64 key) {
+  const uint32_t u = static_cast<uint32_t>(key >> 32);
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+// producer side: called by the thread(s) that own `row`
+__device__ __forceinline__ void push(const Smem& s, int row, float score, int j) {
+  const int pos = atomicAdd(&s.cnt[row], 1);
+  if (pos < kBufCap) s.buf[row * kBufLd + pos] = make_key(score, j);
+  else s.overflow[row] = 1;
+}
+
+// ---- warp-level bitonic networks on keys distributed as element i = r*32 + lane ---------------------------
+__device__ __forceinline__ void cmpx(u64& v, u64 pv, bool keep_max) {
+  const bool gt = v > pv;
+  v = (gt == keep_max) ? v : pv;
+}
+__device__ __forceinline__ void sort32_desc(u64& a0, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int d = size >> 1; d >= 1; d >>= 1) {
+      const u64 p0 = __shfl_xor_sync(0xffffffffu, a0, d);
+      cmpx(a0, p0, ((lane & d) == 0) == ((lane & size) == 0));
+    }
+  }
+}
+__device__ __forceinline__ void merge64_desc(u64& a0, u64& a1, int lane) {   // input bitonic, output sorted descending
+  const u64 mx = a0 > a1 ? a0 : a1, mn = a0 > a1 ? a1 : a0;
+  a0 = mx;
+  a1 = mn;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    const u64 p0 = __shfl_xor_sync(0xffffffffu, a0, d), p1 = __shfl_xor_sync(0xffffffffu, a1, d);
+    const bool lower = (lane & d) == 0;
+    cmpx(a0, p0, lower);
+    cmpx(a1, p1, lower);
+  }
+}
+__device__ __forceinline__ void sort64_desc(u64& a0, u64& a1, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int d = size >> 1; d >= 1; d >>= 1) {
+      const u64 p0 = __shfl_xor_sync(0xffffffffu, a0, d), p1 = __shfl_xor_sync(0xffffffffu, a1, d);
+      const bool lower = (lane & d) == 0;
+      const bool desc0 = (lane & size) == 0;              // element lane
+      const bool desc1 = ((lane + 32) & size) == 0;       // element lane + 32 (ascending block when size == 32)
+      cmpx(a0, p0, lower == desc0);
+      cmpx(a1, p1, lower == desc1);
+    }
+  }
+  merge64_desc(a0, a1, lane);
+}
+
+__device__ __forceinline__ u64 list_at(u64 l0, u64 l1, int pos) {
+  const u64 w0 = __shfl_sync(0xffffffffu, l0, pos & 31);
+  const u64 w1 = __shfl_sync(0xffffffffu, l1, pos & 31);
+  return (pos >> 5) ? w1 : w0;
+}
+
+// consumer side: one warp merges the buffer of `row` into its list and refreshes the threshold.
+__device__ __forceinline__ void compact_row(const Smem& s, int row, int lane, int kp) {
+  const int c = min(s.cnt[row], kBufCap);
+  u64 e0 = lane < c ? s.buf[row * kBufLd + lane] : 0ull;
+  u64 e1 = lane + 32 < c ? s.buf[row * kBufLd + 32 + lane] : 0ull;
+  if (c > 32) {
+    sort64_desc(e0, e1, lane);
+  } else {
+    sort32_desc(e0, lane);
+  }
+  // top-64 of (list U buffer): m[i] = max(list[i], buffer_sorted[63 - i]) is bitonic and holds it
+  const u64 r0 = __shfl_sync(0xffffffffu, e1, 31 - lane);
+  const u64 r1 = __shfl_sync(0xffffffffu, e0, 31 - lane);
+  u64 l0 = s.lists[(row * 2 + 0) * 32 + lane];
+  u64 l1 = s.lists[(row * 2 + 1) * 32 + lane];
+  l0 = l0 > r0 ? l0 : r0;
+  l1 = l1 > r1 ? l1 : r1;
+  merge64_desc(l0, l1, lane);
+  s.lists[(row * 2 + 0) * 32 + lane] = l0;
+  s.lists[(row * 2 + 1) * 32 + lane] = l1;
+  const u64 kth = list_at(l0, l1, kp - 1);
+  if (lane == 0) {
+    s.thr[row] = kth != 0ull ? key_score(kth) : -INFINITY;
+    s.cnt[row] = 0;
+  }
+}
+
+// Compact every row of this warp's group [row0, row0+nrows) whose buffer reached `trigger` candidates.
+__device__ __forceinline__ void compact_rows(const Smem& s, int row0, int nrows, int lane, int kp, int trigger) {
+  for (int rr = 0; rr < nrows; ++rr) {
+    const int row = row0 + rr;
+    if (s.cnt[row] >= trigger) compact_row(s, row, lane, kp);
+  }
+}
+
+}  // namespace sel
+}  // namespace dg
