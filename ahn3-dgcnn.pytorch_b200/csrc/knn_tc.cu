@@ -116,9 +116,10 @@ struct KnnTcSmem {
   static constexpr uint32_t bytes = bar_off + 128 + 1024;
 };
 
-// Thread mapping of the scan: warp w reads TMEM lane quarter (w & 3) and column half (w >> 2); thread = one query
-// row x 32 keys per tile, scores stay in registers.  Compaction: warp w owns rows 16w .. 16w+15.
-__global__ void __launch_bounds__(kThreads, 1)
+// 512 threads.  Scan: warp w reads TMEM lane quarter (w & 3) and column quarter (w >> 2); a thread = one query row x
+// 16 keys per tile, scores stay in registers.  Compaction / finalisation: warp w owns rows 8w .. 8w+7.
+constexpr int kTcThreads = 512;
+__global__ void __launch_bounds__(kTcThreads, 1)
 knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__ rows, int ld,
               const float* __restrict__ norms, const unsigned int* __restrict__ maxnorm_bits, int N, int C4, int T,
               int k, int kp, int32_t* __restrict__ idx, int* __restrict__ fb_count, int* __restrict__ fb_rows) {
@@ -145,7 +146,7 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, 128);            // two 64-column accumulators
-  sel::init(S, tid, kThreads);
+  sel::init(S, tid, kTcThreads);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -173,7 +174,7 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
   }
   __syncwarp();
 
-  const int quarter = warp & 3, chalf = warp >> 2;
+  const int quarter = warp & 3, cq = warp >> 2;
   const int erow = quarter * 32 + lane;                     // scan: this thread's query row
   const bool row_ok = q0 + erow < N;
 
@@ -190,17 +191,19 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
     tc::mbar_wait(accfull + (t & 1), (t >> 1) & 1);
     tc::fence_after_sync();
     {
-      float v[32];
-      tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + (t & 1) * kTcKeyTile + chalf * 32, v);
-      const float* kn = reinterpret_cast<const float*>(Bs + (t % kTcStages) * kStageBytes + 2 * tc::kUnitBytes) + chalf * 32;
+      float v[16];
+      tc::tmem_ld16(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + (t & 1) * kTcKeyTile + cq * 16, v);
+      const float* kn = reinterpret_cast<const float*>(Bs + (t % kTcStages) * kStageBytes + 2 * tc::kUnitBytes) + cq * 16;
       const float thr = S.thr[erow];
-      const int j0 = t * kTcKeyTile + chalf * 32;
+      int n = S.cnt[erow * sel::kSub + cq];
+      const int j0 = t * kTcKeyTile + cq * 16;
       const int jn = row_ok ? N - j0 : 0;                   // keys j0+i with i < jn exist
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      for (int i = 0; i < 16; ++i) {
         const float sc = __fmaf_rn(v[i], 2.0f, -kn[i]);     // approx of 2 x_i.x_j - |x_j|^2 (|x_i|^2 is constant per row)
-        if (sc > thr && i < jn) sel::push(S, erow, sc, j0 + i);
+        if (sc > thr && i < jn) sel::push(S, erow, cq, n, sc, j0 + i);
       }
+      S.cnt[erow * sel::kSub + cq] = n;
     }
     tc::fence_before_sync();
     __syncthreads();                                        // pushes visible; tile t's smem slot and accumulator are free
@@ -210,14 +213,17 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
       tc::bulk_g2s(Bs + s * kStageBytes, btiles + static_cast<size_t>(t + kTcStages) * kTileBytes, kTileBytes, full + s);
     }
     __syncwarp();
-    sel::compact_rows(S, warp * 16, 16, lane, kp, t == Tk - 1 ? 1 : sel::kTrigger);
+    // A sub-buffer (16 slots) receives at most 16 keys per tile, with probability ~kp/(keys seen) each: compact early
+    // and often while that probability is high so that overflow (-> exact fallback for the row) stays a non-event.
+    const int trigger = t == Tk - 1 ? 1 : (t < 4 ? 1 : (t < 32 ? 4 : 8));
+    sel::compact_rows(S, warp * 8, 8, lane, kp, trigger);
     __syncthreads();                                        // thresholds / buffers consistent for the next scan
   }
 
   // ---- certificate + exact re-scoring + exact top-k (warp per query row) ---------------------------------
   const float rmax = sqrtf(__uint_as_float(maxnorm_bits[b]));
-  for (int rr = 0; rr < 16; ++rr) {
-    const int row = warp * 16 + rr, q = q0 + row;
+  for (int rr = 0; rr < 8; ++rr) {
+    const int row = warp * 8 + rr, q = q0 + row;
     if (q >= N) break;
     const sel::u64 l0 = S.lists[(row * 2 + 0) * 32 + lane];
     const sel::u64 l1 = S.lists[(row * 2 + 1) * 32 + lane];
@@ -378,8 +384,8 @@ extern "C" int dgcnn_knn_tc_f32(const float* rows, int ld, int B, int C, int N, 
   knn_tc_prep_kernel<<<dim3(std::min((T * 512 + 255) / 256, 4096), B), 256, 0, st>>>(rows, ld, N, C4, T, norms, tiles);
   DG_CUDA(cudaGetLastError());
   DG_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(KnnTcSmem::bytes)));
-  const int kp = std::min(sel::kList, k + 16);     // list position that defines the pass threshold / certificate
-  knn_tc_kernel<<<dim3((N + 127) / 128, B), kThreads, KnnTcSmem::bytes, st>>>(tiles, rows, ld, norms, maxnorm, N, C4, T, k, kp,
+  const int kp = std::min(sel::kList, k + 8);     // list position that defines the pass threshold / certificate
+  knn_tc_kernel<<<dim3((N + 127) / 128, B), kTcThreads, KnnTcSmem::bytes, st>>>(tiles, rows, ld, norms, maxnorm, N, C4, T, k, kp,
                                                                                idx, fb_count, fb_rows);
   DG_CUDA(cudaGetLastError());
   knn_fallback_kernel<<<64, kThreads, 0, st>>>(rows, ld, norms, N, C4, k, idx, fb_count, fb_rows);

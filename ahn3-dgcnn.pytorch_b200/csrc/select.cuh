@@ -1,8 +1,8 @@
 // select.cuh — streaming top-K selection for 128 query rows of a CTA.
 //
-// Producers (one thread per query row, scores in registers) append every candidate that beats the row's current
-// threshold to a small per-row buffer in shared memory.  Between tiles, warps compact the rows whose buffer is
-// at least half full: bitonic sort of the buffered keys (shuffles), bitonic merge with the row's sorted list of 64
+// Producers (four threads per query row, 16 keys of each tile each, scores in registers) append every candidate that
+// beats the row's current threshold to a private sub-buffer in shared memory (no atomics).  Between tiles, warps
+// compact the rows in which a sub-buffer is filling up: bitonic sort of the buffered keys (shuffles), bitonic merge with the row's sorted list of 64
 // (2 keys per lane), new threshold = key at position kp-1.  Candidates are 64-bit keys (ordered score << 32 | ~idx),
 // so ties on the score prefer the lower index and all keys are distinct.
 #pragma once
@@ -13,35 +13,36 @@ namespace sel {
 
 constexpr int kRows = 128;
 constexpr int kList = 64;            // sorted list length per row (2 per lane)
-constexpr int kBufCap = 64;          // buffered candidates per row
-constexpr int kBufLd = kBufCap + 1;  // row stride of the buffer (u64): 2-way bank conflicts at most on producer stores
-constexpr int kTrigger = 32;         // compact when a buffer holds at least this many candidates
+constexpr int kSub = 4;              // producers per row (each owns a private sub-buffer: no atomics)
+constexpr int kSubCap = 16;          // candidates per sub-buffer (= keys one producer sees per tile)
+constexpr int kBufCap = kSub * kSubCap;
+constexpr int kBufLd = kBufCap + 1;  // row stride of the buffer (u64): producer stores of a warp hit distinct banks
 
 typedef unsigned long long u64;
 
 struct Smem {
   u64* lists;        // [kRows][2][32]
   u64* buf;          // [kRows][kBufLd]
-  int* cnt;          // [kRows]
+  int* cnt;          // [kRows][kSub]
   float* thr;        // [kRows]  current pass threshold (score of list position kp-1, or -inf)
   int* overflow;     // [kRows]  a candidate was dropped because the buffer was full -> row needs the exact fallback
 };
-constexpr size_t kSmemBytes = static_cast<size_t>(kRows) * (kList * 8 + kBufLd * 8 + 4 + 4 + 4);
+constexpr size_t kSmemBytes = static_cast<size_t>(kRows) * (kList * 8 + kBufLd * 8 + 4 * kSub + 4 + 4);
 
 __device__ __forceinline__ Smem carve(unsigned char* base) {   // base 8-byte aligned
   Smem s;
   s.lists = reinterpret_cast<u64*>(base);
   s.buf = s.lists + kRows * kList;
   s.cnt = reinterpret_cast<int*>(s.buf + kRows * kBufLd);
-  s.thr = reinterpret_cast<float*>(s.cnt + kRows);
+  s.thr = reinterpret_cast<float*>(s.cnt + kRows * kSub);
   s.overflow = reinterpret_cast<int*>(s.thr + kRows);
   return s;
 }
 
 __device__ __forceinline__ void init(const Smem& s, int tid, int nthreads) {
   for (int i = tid; i < kRows * kList; i += nthreads) s.lists[i] = 0ull;
+  for (int i = tid; i < kRows * kSub; i += nthreads) s.cnt[i] = 0;
   for (int i = tid; i < kRows; i += nthreads) {
-    s.cnt[i] = 0;
     s.thr[i] = -INFINITY;
     s.overflow[i] = 0;
   }
@@ -52,11 +53,15 @@ __device__ __forceinline__ float key_score(u64 key) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
 }
 
-// producer side: called by the thread(s) that own `row`
-__device__ __forceinline__ void push(const Smem& s, int row, float score, int j) {
-  const int pos = atomicAdd(&s.cnt[row], 1);
-  if (pos < kBufCap) s.buf[row * kBufLd + pos] = make_key(score, j);
-  else s.overflow[row] = 1;
+// producer side: the thread owning (row, sub) appends to its private sub-buffer; `n` is its running count
+// (loaded from cnt[row][sub] before the tile, stored back after it).
+__device__ __forceinline__ void push(const Smem& s, int row, int sub, int& n, float score, int j) {
+  if (n < kSubCap) {
+    s.buf[row * kBufLd + sub * kSubCap + n] = make_key(score, j);
+    ++n;
+  } else {
+    s.overflow[row] = 1;
+  }
 }
 
 // ---- warp-level bitonic networks on keys distributed as element i = r*32 + lane ---------------------------
@@ -110,10 +115,12 @@ __device__ __forceinline__ u64 list_at(u64 l0, u64 l1, int pos) {
 
 // consumer side: one warp merges the buffer of `row` into its list and refreshes the threshold.
 __device__ __forceinline__ void compact_row(const Smem& s, int row, int lane, int kp) {
-  const int c = min(s.cnt[row], kBufCap);
-  u64 e0 = lane < c ? s.buf[row * kBufLd + lane] : 0ull;
-  u64 e1 = lane + 32 < c ? s.buf[row * kBufLd + 32 + lane] : 0ull;
-  if (c > 32) {
+  // element i = r*32 + lane of the unsorted candidate set: sub-buffer (2r + lane/16), slot lane%16
+  const int sl = lane & 15, sb = lane >> 4;
+  const int c_lo = s.cnt[row * kSub + sb], c_hi = s.cnt[row * kSub + 2 + sb];
+  u64 e0 = sl < c_lo ? s.buf[row * kBufLd + sb * kSubCap + sl] : 0ull;
+  u64 e1 = sl < c_hi ? s.buf[row * kBufLd + (2 + sb) * kSubCap + sl] : 0ull;
+  if (__any_sync(0xffffffffu, c_hi > 0)) {
     sort64_desc(e0, e1, lane);
   } else {
     sort32_desc(e0, lane);
@@ -131,15 +138,16 @@ __device__ __forceinline__ void compact_row(const Smem& s, int row, int lane, in
   const u64 kth = list_at(l0, l1, kp - 1);
   if (lane == 0) {
     s.thr[row] = kth != 0ull ? key_score(kth) : -INFINITY;
-    s.cnt[row] = 0;
   }
+  if (lane < kSub) s.cnt[row * kSub + lane] = 0;
 }
 
-// Compact every row of this warp's group [row0, row0+nrows) whose buffer reached `trigger` candidates.
+// Compact every row of this warp's group [row0, row0+nrows) in which some sub-buffer reached `trigger` entries.
 __device__ __forceinline__ void compact_rows(const Smem& s, int row0, int nrows, int lane, int kp, int trigger) {
   for (int rr = 0; rr < nrows; ++rr) {
     const int row = row0 + rr;
-    if (s.cnt[row] >= trigger) compact_row(s, row, lane, kp);
+    const int4 c = *reinterpret_cast<const int4*>(s.cnt + row * kSub);
+    if (max(max(c.x, c.y), max(c.z, c.w)) >= trigger) compact_row(s, row, lane, kp);
   }
 }
 
