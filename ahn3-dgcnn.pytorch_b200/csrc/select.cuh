@@ -2,8 +2,8 @@
 //
 // Producers (four threads per query row, 16 keys of each tile each, scores in registers) append every candidate that
 // beats the row's current threshold to a private sub-buffer in shared memory (no atomics).  Between tiles, warps
-// compact the rows in which a sub-buffer is filling up: rank-based merge of the buffered keys into the row's sorted
-// list of 64, new threshold = key at position kp-1.  Candidates are 64-bit keys (ordered score << 32 | ~idx),
+// compact the rows in which a sub-buffer is filling up: bitonic sort of the buffered keys (shuffles), bitonic merge with the row's sorted list of 64
+// (2 keys per lane), new threshold = key at position kp-1.  Candidates are 64-bit keys (ordered score << 32 | ~idx),
 // so ties on the score prefer the lower index and all keys are distinct.
 #pragma once
 #include "common.cuh"
@@ -113,63 +113,30 @@ __device__ __forceinline__ u64 list_at(u64 l0, u64 l1, int pos) {
   return (pos >> 5) ? w1 : w0;
 }
 
-// consumer side: one warp merges the buffered candidates of `row` into its sorted list and refreshes the threshold.
-// Rank-based merge (short dependency chains instead of a 27-stage shuffle network): every element of list U buffer
-// computes how many elements are larger and is scattered to that position.
-//   list element at position p :  rank = p + #{buffer > x}
-//   buffer element y           :  rank = #{list > y} (binary search, the list is sorted) + #{buffer > y}
-// Keys are distinct; empty list slots are 0 (smaller than any key) and keep their relative order.
+// consumer side: one warp merges the buffer of `row` into its list and refreshes the threshold.
 __device__ __forceinline__ void compact_row(const Smem& s, int row, int lane, int kp) {
-  u64* L = s.lists + row * kList;
-  const u64* Bf = s.buf + row * kBufLd;
-  const int4 c4 = *reinterpret_cast<const int4*>(s.cnt + row * kSub);
-  const int c0 = min(c4.x, kSubCap), c1 = min(c4.y, kSubCap), c2 = min(c4.z, kSubCap), c3 = min(c4.w, kSubCap);
-  const int n01 = c0 + c1, n012 = n01 + c2, nb = n012 + c3;
-  // this lane's elements: list positions lane, lane+32; buffer elements (flat index) lane, lane+32
-  const u64 x0 = L[lane], x1 = L[lane + 32];
-  u64 y[2];
-  int ry[2];
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int e = lane + 32 * r;
-    y[r] = 0ull;
-    ry[r] = kList;                                   // "discard"
-    if (e < nb) {
-      const int sub = e < c0 ? 0 : (e < n01 ? 1 : (e < n012 ? 2 : 3));
-      const int slot = e - (sub == 0 ? 0 : (sub == 1 ? c0 : (sub == 2 ? n01 : n012)));
-      y[r] = Bf[sub * kSubCap + slot];
-      // #{list > y}: first position whose key is < y in the descending list
-      int lo = 0, hi = kList;
-#pragma unroll
-      for (int it = 0; it < 7; ++it) {               // 65 possible answers -> 7 probes
-        const int mid = (lo + hi) >> 1;
-        if (lo < hi) {
-          if (L[mid] > y[r]) lo = mid + 1; else hi = mid;
-        }
-      }
-      ry[r] = lo;
-    }
+  // element i = r*32 + lane of the unsorted candidate set: sub-buffer (2r + lane/16), slot lane%16
+  const int sl = lane & 15, sb = lane >> 4;
+  const int c_lo = s.cnt[row * kSub + sb], c_hi = s.cnt[row * kSub + 2 + sb];
+  u64 e0 = sl < c_lo ? s.buf[row * kBufLd + sb * kSubCap + sl] : 0ull;
+  u64 e1 = sl < c_hi ? s.buf[row * kBufLd + (2 + sb) * kSubCap + sl] : 0ull;
+  if (__any_sync(0xffffffffu, c_hi > 0)) {
+    sort64_desc(e0, e1, lane);
+  } else {
+    sort32_desc(e0, lane);
   }
-  int g0 = 0, g1 = 0;                                // #{buffer > x0}, #{buffer > x1}
-  for (int sub = 0; sub < kSub; ++sub) {
-    const int cs = sub == 0 ? c0 : (sub == 1 ? c1 : (sub == 2 ? c2 : c3));
-    for (int sl = 0; sl < cs; ++sl) {
-      const u64 b = Bf[sub * kSubCap + sl];          // broadcast read
-      g0 += b > x0;
-      g1 += b > x1;
-      ry[0] += b > y[0];
-      ry[1] += b > y[1];
-    }
-  }
-  __syncwarp();                                       // all reads of the old list are done
-  const int p0 = lane + g0, p1 = lane + 32 + g1;
-  if (p0 < kList) L[p0] = x0;
-  if (p1 < kList) L[p1] = x1;
-  if (y[0] != 0ull && ry[0] < kList) L[ry[0]] = y[0];
-  if (y[1] != 0ull && ry[1] < kList) L[ry[1]] = y[1];
-  __syncwarp();
+  // top-64 of (list U buffer): m[i] = max(list[i], buffer_sorted[63 - i]) is bitonic and holds it
+  const u64 r0 = __shfl_sync(0xffffffffu, e1, 31 - lane);
+  const u64 r1 = __shfl_sync(0xffffffffu, e0, 31 - lane);
+  u64 l0 = s.lists[(row * 2 + 0) * 32 + lane];
+  u64 l1 = s.lists[(row * 2 + 1) * 32 + lane];
+  l0 = l0 > r0 ? l0 : r0;
+  l1 = l1 > r1 ? l1 : r1;
+  merge64_desc(l0, l1, lane);
+  s.lists[(row * 2 + 0) * 32 + lane] = l0;
+  s.lists[(row * 2 + 1) * 32 + lane] = l1;
+  const u64 kth = list_at(l0, l1, kp - 1);
   if (lane == 0) {
-    const u64 kth = L[kp - 1];
     s.thr[row] = kth != 0ull ? key_score(kth) : -INFINITY;
   }
   if (lane < kSub) s.cnt[row * kSub + lane] = 0;
