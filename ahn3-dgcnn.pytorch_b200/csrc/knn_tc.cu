@@ -197,11 +197,21 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
       const float thr = S.thr[erow];
       int n = S.cnt[erow * sel::kSub + cq];
       const int j0 = t * kTcKeyTile + cq * 16;
-      const int jn = row_ok ? N - j0 : 0;                   // keys j0+i with i < jn exist
+      if (t < Tk - 1) {                                     // every key of the tile exists
+        if (row_ok) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float sc = __fmaf_rn(v[i], 2.0f, -kn[i]);     // approx of 2 x_i.x_j - |x_j|^2 (|x_i|^2 is constant per row)
-        if (sc > thr && i < jn) sel::push(S, erow, cq, n, sc, j0 + i);
+          for (int i = 0; i < 16; ++i) {
+            const float sc = __fmaf_rn(v[i], 2.0f, -kn[i]); // approx of 2 x_i.x_j - |x_j|^2 (|x_i|^2 is constant per row)
+            if (sc > thr) sel::push(S, erow, cq, n, sc, j0 + i);
+          }
+        }
+      } else {
+        const int jn = row_ok ? N - j0 : 0;                 // keys j0+i with i < jn exist
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float sc = __fmaf_rn(v[i], 2.0f, -kn[i]);
+          if (sc > thr && i < jn) sel::push(S, erow, cq, n, sc, j0 + i);
+        }
       }
       S.cnt[erow * sel::kSub + cq] = n;
     }

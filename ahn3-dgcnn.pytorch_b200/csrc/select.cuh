@@ -115,15 +115,25 @@ __device__ __forceinline__ u64 list_at(u64 l0, u64 l1, int pos) {
 
 // consumer side: one warp merges the buffer of `row` into its list and refreshes the threshold.
 __device__ __forceinline__ void compact_row(const Smem& s, int row, int lane, int kp) {
-  // element i = r*32 + lane of the unsorted candidate set: sub-buffer (2r + lane/16), slot lane%16
-  const int sl = lane & 15, sb = lane >> 4;
-  const int c_lo = s.cnt[row * kSub + sb], c_hi = s.cnt[row * kSub + 2 + sb];
-  u64 e0 = sl < c_lo ? s.buf[row * kBufLd + sb * kSubCap + sl] : 0ull;
-  u64 e1 = sl < c_hi ? s.buf[row * kBufLd + (2 + sb) * kSubCap + sl] : 0ull;
-  if (__any_sync(0xffffffffu, c_hi > 0)) {
+  // flat index e = r*32 + lane over the valid entries of the four sub-buffers
+  const int4 c4 = *reinterpret_cast<const int4*>(s.cnt + row * kSub);
+  const int c0 = min(c4.x, kSubCap), c1 = min(c4.y, kSubCap), c2 = min(c4.z, kSubCap), c3 = min(c4.w, kSubCap);
+  const int n01 = c0 + c1, n012 = n01 + c2, nb = n012 + c3;
+  u64 e0 = 0ull, e1 = 0ull;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int e = lane + 32 * r;
+    if (e < nb) {
+      const int sub = e < c0 ? 0 : (e < n01 ? 1 : (e < n012 ? 2 : 3));
+      const int slot = e - (sub == 0 ? 0 : (sub == 1 ? c0 : (sub == 2 ? n01 : n012)));
+      const u64 v = s.buf[row * kBufLd + sub * kSubCap + slot];
+      if (r == 0) e0 = v; else e1 = v;
+    }
+  }
+  if (nb > 32) {
     sort64_desc(e0, e1, lane);
   } else {
-    sort32_desc(e0, lane);
+    sort32_desc(e0, lane);       // the common case: half the network
   }
   // top-64 of (list U buffer): m[i] = max(list[i], buffer_sorted[63 - i]) is bitonic and holds it
   const u64 r0 = __shfl_sync(0xffffffffu, e1, 31 - lane);
