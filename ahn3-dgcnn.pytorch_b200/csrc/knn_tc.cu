@@ -122,7 +122,7 @@ constexpr int kTcThreads = 512;
 __global__ void __launch_bounds__(kTcThreads, 1)
 knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__ rows, int ld,
               const float* __restrict__ norms, const unsigned int* __restrict__ maxnorm_bits, int N, int C4, int T,
-              int k, int kp, int32_t* __restrict__ idx, int* __restrict__ fb_count, int* __restrict__ fb_rows) {
+              int k, int kp, int kinit, int32_t* __restrict__ idx, int* __restrict__ fb_count, int* __restrict__ fb_rows) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* As = sm;
@@ -225,8 +225,11 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
     __syncwarp();
     // A sub-buffer (16 slots) receives at most 16 keys per tile, with probability ~kp/(keys seen) each: compact early
     // and often while that probability is high so that overflow (-> exact fallback for the row) stays a non-event.
-    const int trigger = t == Tk - 1 ? 1 : (t < 4 ? 1 : (t < 32 ? 4 : 8));
-    sel::compact_rows(S, warp * 8, 8, lane, kp, trigger);
+    // Tile 0 bootstraps the threshold: the kinit-th best of the first 64 keys has an expected global rank of
+    // ~kinit*N/65 >= 4*kp, which removes the initial flood of candidates; if it turns out tighter than the kp-th best
+    // overall the certificate below fails and the row goes to the exact fallback (probability < 1e-3).
+    const int trigger = (t == Tk - 1 || t == 0) ? 1 : (t < 32 ? 4 : 8);
+    sel::compact_rows(S, warp * 8, 8, lane, t == 0 ? kinit : kp, trigger);
     __syncthreads();                                        // thresholds / buffers consistent for the next scan
   }
 
@@ -243,10 +246,9 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
     const float eps = 1.01f * (kC1 * ni * rmax + kC2 * (ni + rmax) * (ni + rmax));
     const float tk = sel::key_score(sel::list_at(l0, l1, k - 1));
     const float cut = tk - 2.0f * eps;
-    // every key whose approximate score exceeds the score at list position kp-1 is in the list; the list is
-    // complete above `cut` iff that position is empty or strictly below the cut
-    const sel::u64 last = sel::list_at(l0, l1, kp - 1);
-    const bool uncertified = (last != 0ull && sel::key_score(last) >= cut) || S.overflow[row] != 0;
+    // every key whose approximate score exceeds the final pass threshold is in the list, so the list is complete
+    // above `cut` iff that threshold is strictly below the cut
+    const bool uncertified = !(S.thr[row] < cut) || S.overflow[row] != 0;
     const float* xi = rows + g * ld;
     sel::u64 ex[2];
     const sel::u64 ls[2] = {l0, l1};
@@ -395,8 +397,9 @@ extern "C" int dgcnn_knn_tc_f32(const float* rows, int ld, int B, int C, int N, 
   DG_CUDA(cudaGetLastError());
   DG_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(KnnTcSmem::bytes)));
   const int kp = std::min(sel::kList, k + 8);     // list position that defines the pass threshold / certificate
+  const int kinit = std::max(4, std::min(kp, (4 * kp * 65 + N - 1) / N));
   knn_tc_kernel<<<dim3((N + 127) / 128, B), kTcThreads, KnnTcSmem::bytes, st>>>(tiles, rows, ld, norms, maxnorm, N, C4, T, k, kp,
-                                                                               idx, fb_count, fb_rows);
+                                                                               kinit, idx, fb_count, fb_rows);
   DG_CUDA(cudaGetLastError());
   knn_fallback_kernel<<<64, kThreads, 0, st>>>(rows, ld, norms, N, C4, k, idx, fb_count, fb_rows);
   DG_CUDA(cudaGetLastError());

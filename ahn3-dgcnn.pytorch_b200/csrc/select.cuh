@@ -145,10 +145,9 @@ __device__ __forceinline__ void compact_row(const Smem& s, int row, int lane, in
   merge64_desc(l0, l1, lane);
   s.lists[(row * 2 + 0) * 32 + lane] = l0;
   s.lists[(row * 2 + 1) * 32 + lane] = l1;
+  // the pass threshold only ever tightens (kp may be a smaller "bootstrap" position on the first tile)
   const u64 kth = list_at(l0, l1, kp - 1);
-  if (lane == 0) {
-    s.thr[row] = kth != 0ull ? key_score(kth) : -INFINITY;
-  }
+  if (lane == 0 && kth != 0ull) s.thr[row] = fmaxf(s.thr[row], key_score(kth));
   if (lane < kSub) s.cnt[row * kSub + lane] = 0;
 }
 
