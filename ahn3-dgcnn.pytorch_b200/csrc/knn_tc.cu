@@ -113,7 +113,7 @@ struct KnnTcSmem {
   static constexpr uint32_t b_off = a_bytes;
   static constexpr uint32_t sel_off = b_off + kTcStages * kStageBytes;
   static constexpr uint32_t bar_off = sel_off + static_cast<uint32_t>(sel::kSmemBytes);
-  static constexpr uint32_t bytes = bar_off + 128 + 1024;
+  static constexpr uint32_t bytes = bar_off + 128;
 };
 
 // 512 threads.  Scan: warp w reads TMEM lane quarter (w & 3) and column quarter (w >> 2); a thread = one query row x
@@ -123,8 +123,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__ rows, int ld,
               const float* __restrict__ norms, const unsigned int* __restrict__ maxnorm_bits, int N, int C4, int T,
               int k, int kp, int kinit, int32_t* __restrict__ idx, int* __restrict__ fb_count, int* __restrict__ fb_rows) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (checked below), and plain
+  // pointer arithmetic on it keeps the shared address space visible to the compiler (LDS/STS instead of generic LD/ST)
+  extern __shared__ __align__(1024) unsigned char sm[];
   unsigned char* As = sm;
   unsigned char* Bs = sm + KnnTcSmem::b_off;
   const sel::Smem S = sel::carve(sm + KnnTcSmem::sel_off);
@@ -139,6 +140,7 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
   const unsigned char* btiles = tiles + static_cast<size_t>(b) * T * kTileBytes;
 
   if (tid == 0) {
+    if (tc::smem_u32(sm) & 1023u) __trap();
     tc::mbar_init(abar, 1);
     for (int s = 0; s < kTcStages; ++s) tc::mbar_init(full + s, 1);
     tc::mbar_init(accfull, 1);
@@ -214,6 +216,10 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
         }
       }
       S.cnt[erow * sel::kSub + cq] = n;
+      // A sub-buffer (16 slots) receives at most 16 keys per tile, each with probability ~kp/(keys seen): compact early
+      // and often while that probability is high so that overflow (-> exact fallback for the row) stays a non-event.
+      const int trigger = (t == Tk - 1 || t == 0) ? 1 : (t < 32 ? 4 : 8);
+      sel::request_compaction(S, erow, n, trigger, t & 1);
     }
     tc::fence_before_sync();
     __syncthreads();                                        // pushes visible; tile t's smem slot and accumulator are free
@@ -223,13 +229,11 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
       tc::bulk_g2s(Bs + s * kStageBytes, btiles + static_cast<size_t>(t + kTcStages) * kTileBytes, kTileBytes, full + s);
     }
     __syncwarp();
-    // A sub-buffer (16 slots) receives at most 16 keys per tile, with probability ~kp/(keys seen) each: compact early
-    // and often while that probability is high so that overflow (-> exact fallback for the row) stays a non-event.
     // Tile 0 bootstraps the threshold: the kinit-th best of the first 64 keys has an expected global rank of
     // ~kinit*N/65 >= 4*kp, which removes the initial flood of candidates; if it turns out tighter than the kp-th best
     // overall the certificate below fails and the row goes to the exact fallback (probability < 1e-3).
-    const int trigger = (t == Tk - 1 || t == 0) ? 1 : (t < 32 ? 4 : 8);
-    sel::compact_rows(S, warp * 8, 8, lane, t == 0 ? kinit : kp, trigger);
+    if (tid == 0) S.nwork[(t + 1) & 1] = 0;
+    sel::compact_queued(S, warp, kTcThreads / 32, lane, t == 0 ? kinit : kp, t & 1);
     __syncthreads();                                        // thresholds / buffers consistent for the next scan
   }
 

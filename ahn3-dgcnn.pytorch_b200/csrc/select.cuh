@@ -26,8 +26,11 @@ struct Smem {
   int* cnt;          // [kRows][kSub]
   float* thr;        // [kRows]  current pass threshold (score of list position kp-1, or -inf)
   int* overflow;     // [kRows]  a candidate was dropped because the buffer was full -> row needs the exact fallback
+  int* flag;         // [kRows]  row is queued for compaction
+  int* work;         // [2][kRows] double-buffered worklists of rows to compact
+  int* nwork;        // [2 (+2 pad)]
 };
-constexpr size_t kSmemBytes = static_cast<size_t>(kRows) * (kList * 8 + kBufLd * 8 + 4 * kSub + 4 + 4);
+constexpr size_t kSmemBytes = static_cast<size_t>(kRows) * (kList * 8 + kBufLd * 8 + 4 * kSub + 4 + 4 + 4 + 8) + 16;
 
 __device__ __forceinline__ Smem carve(unsigned char* base) {   // base 8-byte aligned
   Smem s;
@@ -36,6 +39,9 @@ __device__ __forceinline__ Smem carve(unsigned char* base) {   // base 8-byte al
   s.cnt = reinterpret_cast<int*>(s.buf + kRows * kBufLd);
   s.thr = reinterpret_cast<float*>(s.cnt + kRows * kSub);
   s.overflow = reinterpret_cast<int*>(s.thr + kRows);
+  s.flag = s.overflow + kRows;
+  s.work = s.flag + kRows;
+  s.nwork = s.work + 2 * kRows;
   return s;
 }
 
@@ -45,7 +51,9 @@ __device__ __forceinline__ void init(const Smem& s, int tid, int nthreads) {
   for (int i = tid; i < kRows; i += nthreads) {
     s.thr[i] = -INFINITY;
     s.overflow[i] = 0;
+    s.flag[i] = 0;
   }
+  if (tid < 4) s.nwork[tid] = 0;
 }
 
 __device__ __forceinline__ float key_score(u64 key) {
@@ -151,12 +159,17 @@ __device__ __forceinline__ void compact_row(const Smem& s, int row, int lane, in
   if (lane < kSub) s.cnt[row * kSub + lane] = 0;
 }
 
-// Compact every row of this warp's group [row0, row0+nrows) in which some sub-buffer reached `trigger` entries.
-__device__ __forceinline__ void compact_rows(const Smem& s, int row0, int nrows, int lane, int kp, int trigger) {
-  for (int rr = 0; rr < nrows; ++rr) {
-    const int row = row0 + rr;
-    const int4 c = *reinterpret_cast<const int4*>(s.cnt + row * kSub);
-    if (max(max(c.x, c.y), max(c.z, c.w)) >= trigger) compact_row(s, row, lane, kp);
+// producer side, after a tile: queue the row for compaction if this producer's sub-buffer reached `trigger`
+__device__ __forceinline__ void request_compaction(const Smem& s, int row, int n, int trigger, int parity) {
+  if (n >= trigger && atomicExch(&s.flag[row], 1) == 0) s.work[parity * kRows + atomicAdd(&s.nwork[parity], 1)] = row;
+}
+// consumer side: the queued rows are dealt round-robin to the CTA's warps (balanced, unlike static row ownership)
+__device__ __forceinline__ void compact_queued(const Smem& s, int warp, int nwarps, int lane, int kp, int parity) {
+  const int nw = s.nwork[parity];
+  for (int i = warp; i < nw; i += nwarps) {
+    const int row = s.work[parity * kRows + i];
+    compact_row(s, row, lane, kp);
+    if (lane == 0) s.flag[row] = 0;
   }
 }
 
