@@ -1,17 +1,22 @@
 // knn_tc.cu — feature-space kNN (16 < C <= 64) on the tensor cores, with EXACT results.
 //
 // Gram tiles are computed by tcgen05.mma on a 2-plane bf16 split of the features (3 MMAs per product,
-// |error| <= ~2e-5 * |x_i||x_j|) into TMEM; the approximate scores only act as a FILTER:
-//   * every query keeps its 64 best approximate candidates (streaming: per-row candidate buffers + warp-level
-//     bitonic merges, select.cuh);
-//   * with eps_i a rigorous bound on |approx - exact| for row i, every true top-k neighbour has
-//     approx >= t_k - 2 eps_i (t_k = k-th best approximate score), so if the 64-th candidate is below that
-//     cut the candidate list provably contains the exact top-k ("certificate");
-//   * the survivors are re-scored with the reference's exact FP32 arithmetic (FMA chain in channel order,
-//     two rounded subtractions, model.py:35-37) and the top-k of the exact scores is emitted;
-//   * rows whose certificate fails (more than 64-k near-ties, e.g. many duplicated points) are redone by an
-//     exact brute-force kernel.  The neighbour table is therefore identical to dgcnn_knn_f32's, bit for bit.
-// The B x N x N matrix never leaves the SM: scores go TMEM -> registers -> shared memory -> selection.
+// |error| <= ~2e-5 * |x_i||x_j|) into TMEM; the approximate scores only act as a FILTER ("threshold - collect -
+// re-score"), there are no running top-k lists and no CTA-wide barriers inside the key loop:
+//   pass 1  scan the first ~N/200 key tiles; each of the 4 threads that share a query row keeps the 8 best
+//           approximate scores of its 16 columns in registers; tau_i = mean of the four 8th-best values, an estimate
+//           of the row's ~100-th best score overall;
+//   pass 2  scan all keys; every key with approx > tau_i is appended to the row's candidate buffer (global memory,
+//           4 private sub-buffers of 64 per row, no atomics);
+//   pass 3  (warp per row) bisect the candidates' approximate scores to a value v exceeded by >= k+4 of them, keep the
+//           candidates above v - 2 eps_i (eps_i = rigorous bound on |approx - exact| for the row), re-score those with
+//           the reference's exact FP32 arithmetic (FMA chain in channel order, two rounded subtractions,
+//           model.py:35-37) and emit the exact top-k;
+//   certificate: every key outside the candidate set has exact score <= tau_i - |x_i|^2 + eps_i; if that is below the
+//           k-th exact score found, the result is provably the exact top-k.  Rows that fail it (tau too tight, buffer
+//           overflow, more than 64 near-ties) are redone by an exact brute-force kernel.
+// The neighbour table is therefore identical to dgcnn_knn_f32's, bit for bit, and the B x N x N matrix never leaves
+// the SM: scores go TMEM -> registers.
 #include "common.cuh"
 #include "tc.cuh"
 #include "select.cuh"
@@ -21,7 +26,7 @@ namespace dg {
 constexpr int kTcKeyTile = 64;          // keys per MMA tile (UMMA N)
 constexpr uint32_t kTileBytes = 2 * tc::kUnitBytes + kTcKeyTile * 4;   // plane0 | plane1 | 64 key norms
 constexpr uint32_t kStageBytes = 17 * 1024;                             // smem slot (planes stay 1024-aligned)
-constexpr int kTcStages = 3;
+constexpr int kTcStages = 6;
 // error model of the filter (see DESIGN.md "kNN filter bound")
 constexpr float kC1 = 2.0e-5f * 2.0f;   // 2 * (split + accumulation + chain error) on 2*dot, relative to |x_i||x_j|
 constexpr float kC2 = 4.8e-7f;          // final roundings, relative to (|x_i|+|x_j|)^2
@@ -108,178 +113,285 @@ __device__ __forceinline__ float exact_score(const float* __restrict__ xi, const
   return __fsub_rn(__fmaf_rn(d, 2.0f, -norm_j), norm_i);
 }
 
+constexpr int kAccs = 4;                 // TMEM accumulators (64 columns each)
+constexpr int kScanWarps = 16;
+constexpr int kTcThreads = (kScanWarps + 1) * 32;   // + 1 producer / MMA-issue warp
+constexpr int kSubCands = 64;            // candidate slots per (row, column quarter)
+constexpr int kSurvivors = 64;           // exact re-scores per row (2 per lane)
+
 struct KnnTcSmem {
   static constexpr uint32_t a_bytes = 2 * 128 * 128;                        // two planes of 128 query rows
   static constexpr uint32_t b_off = a_bytes;
-  static constexpr uint32_t sel_off = b_off + kTcStages * kStageBytes;
-  static constexpr uint32_t bar_off = sel_off + static_cast<uint32_t>(sel::kSmemBytes);
-  static constexpr uint32_t bytes = bar_off + 128;
+  static constexpr uint32_t misc_off = b_off + kTcStages * kStageBytes;     // per-row scalars
+  static constexpr uint32_t stage_off = misc_off + 128 * (4 * 4 + 4 * 4 + 4 + 4);   // tau4 | cnt4 | tau | flag
+  static constexpr uint32_t bar_off = stage_off + kScanWarps * kSurvivors * 8;      // per-warp survivor staging
+  static constexpr uint32_t bytes = bar_off + 256;
 };
 
-// 512 threads.  Scan: warp w reads TMEM lane quarter (w & 3) and column quarter (w >> 2); a thread = one query row x
-// 16 keys per tile, scores stay in registers.  Compaction / finalisation: warp w owns rows 8w .. 8w+7.
-constexpr int kTcThreads = 512;
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// insert v into the descending top-8 t[0..7] (registers)
+__device__ __forceinline__ void top8_insert(float (&t)[8], float v) {
+#pragma unroll
+  for (int i = 7; i >= 1; --i) t[i] = v > t[i - 1] ? t[i - 1] : fmaxf(v, t[i]);
+  t[0] = fmaxf(v, t[0]);
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1)
 knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__ rows, int ld,
               const float* __restrict__ norms, const unsigned int* __restrict__ maxnorm_bits, int N, int C4, int T,
-              int k, int kp, int kinit, int32_t* __restrict__ idx, int* __restrict__ fb_count, int* __restrict__ fb_rows) {
+              int k, int T1, unsigned long long* __restrict__ cand, int32_t* __restrict__ idx,
+              int* __restrict__ fb_count, int* __restrict__ fb_rows) {
   // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (checked below), and plain
-  // pointer arithmetic on it keeps the shared address space visible to the compiler (LDS/STS instead of generic LD/ST)
+  // pointer arithmetic on it keeps the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
   extern __shared__ __align__(1024) unsigned char sm[];
   unsigned char* As = sm;
   unsigned char* Bs = sm + KnnTcSmem::b_off;
-  const sel::Smem S = sel::carve(sm + KnnTcSmem::sel_off);
+  float* tau4 = reinterpret_cast<float*>(sm + KnnTcSmem::misc_off);      // [128][4]
+  int* cnt4 = reinterpret_cast<int*>(tau4 + 128 * 4);                    // [128][4]
+  float* tauS = reinterpret_cast<float*>(cnt4 + 128 * 4);                // [128]
+  int* flagS = reinterpret_cast<int*>(tauS + 128);                       // [128] overflow of a sub-buffer
+  unsigned long long* stageS = reinterpret_cast<unsigned long long*>(sm + KnnTcSmem::stage_off);
   uint64_t* abar = reinterpret_cast<uint64_t*>(sm + KnnTcSmem::bar_off);
-  uint64_t* full = abar + 1;               // [kTcStages]
-  uint64_t* accfull = full + kTcStages;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 2);
+  uint64_t* full = abar + 1;                 // [kTcStages]  tile landed in smem
+  uint64_t* sfree = full + kTcStages;        // [kTcStages]  all scan warps are done with the slot
+  uint64_t* accfull = sfree + kTcStages;     // [kAccs]      MMA of the tile finished
+  uint64_t* accfree = accfull + kAccs;       // [kAccs]      all scan warps have read the accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfree + kAccs);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y, qt = blockIdx.x, q0 = qt * 128;
-  const int Tk = (N + kTcKeyTile - 1) / kTcKeyTile;        // key tiles to visit
+  const int Tk = (N + kTcKeyTile - 1) / kTcKeyTile;        // key tiles of the block
+  const int TT = T1 + Tk;                                  // tiles streamed: pass 1 (first T1 tiles) then pass 2 (all)
   const unsigned char* btiles = tiles + static_cast<size_t>(b) * T * kTileBytes;
 
   if (tid == 0) {
     if (tc::smem_u32(sm) & 1023u) __trap();
     tc::mbar_init(abar, 1);
-    for (int s = 0; s < kTcStages; ++s) tc::mbar_init(full + s, 1);
-    tc::mbar_init(accfull, 1);
-    tc::mbar_init(accfull + 1, 1);
+    for (int s = 0; s < kTcStages; ++s) {
+      tc::mbar_init(full + s, 1);
+      tc::mbar_init(sfree + s, kScanWarps);
+    }
+    for (int a = 0; a < kAccs; ++a) {
+      tc::mbar_init(accfull + a, 1);
+      tc::mbar_init(accfree + a, kScanWarps);
+    }
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, 128);            // two 64-column accumulators
-  sel::init(S, tid, kTcThreads);
+  if (warp == kScanWarps) tc::tmem_alloc(tmem_slot, kAccs * kTcKeyTile);
+  if (tid < 128) flagS[tid] = 0;
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t taddr = *tmem_slot;
-  constexpr uint32_t idesc = tc::idesc_bf16(128, kTcKeyTile);
 
-  if (tid == 0) {
-    // queries: the two 64-row tiles 2*qt, 2*qt+1 -> planes of 128 rows
-    tc::mbar_arrive_expect_tx(abar, KnnTcSmem::a_bytes);
+  if (warp == kScanWarps) {
+    // ===== producer + MMA issuer (one thread) =================================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::idesc_bf16(128, kTcKeyTile);
+      tc::mbar_arrive_expect_tx(abar, KnnTcSmem::a_bytes);
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
+      for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int p = 0; p < 2; ++p)
-        tc::bulk_g2s(As + p * 16384 + h * tc::kUnitBytes, btiles + static_cast<size_t>(2 * qt + h) * kTileBytes + p * tc::kUnitBytes,
-                     tc::kUnitBytes, abar);
-    for (int t = 0; t < kTcStages && t < Tk; ++t) {
-      tc::mbar_arrive_expect_tx(full + t, kTileBytes);
-      tc::bulk_g2s(Bs + t * kStageBytes, btiles + static_cast<size_t>(t) * kTileBytes, kTileBytes, full + t);
+        for (int p = 0; p < 2; ++p)
+          tc::bulk_g2s(As + p * 16384 + h * tc::kUnitBytes,
+                       btiles + static_cast<size_t>(2 * qt + h) * kTileBytes + p * tc::kUnitBytes, tc::kUnitBytes, abar);
+      int loaded = 0;
+      auto issue_copy = [&](int l) {
+        const int s = l % kTcStages;
+        const int tile = l < T1 ? l : l - T1;
+        tc::mbar_arrive_expect_tx(full + s, kTileBytes);
+        tc::bulk_g2s(Bs + s * kStageBytes, btiles + static_cast<size_t>(tile) * kTileBytes, kTileBytes, full + s);
+      };
+      tc::mbar_wait(abar, 0);
+      for (int i = 0; i < TT; ++i) {
+        // tile i must be on its way; further tiles are prefetched only if their slot is already free (never block
+        // the MMA issue on a slot that the scan warps still hold)
+        while (loaded < TT && loaded < i + kTcStages) {
+          uint64_t* bar = sfree + loaded % kTcStages;
+          const uint32_t par = ((loaded / kTcStages) & 1) ^ 1;
+          if (loaded <= i) tc::mbar_wait(bar, par);
+          else if (!tc::mbar_try_wait(bar, par)) break;
+          issue_copy(loaded++);
+        }
+        const int s = i % kTcStages, a = i % kAccs;
+        tc::mbar_wait(full + s, (i / kTcStages) & 1);
+        tc::mbar_wait(accfree + a, ((i / kAccs) & 1) ^ 1);
+        tc::fence_after_sync();
+        tc::mma_split_katom<2>(taddr + a * kTcKeyTile, tc::smem_u32(As), 16384, tc::smem_u32(Bs + s * kStageBytes),
+                               tc::kUnitBytes, idesc, true);
+        tc::mma_commit(accfull + a);
+      }
     }
-    tc::mbar_wait(abar, 0);
-    tc::mbar_wait(full, 0);
-    tc::fence_after_sync();
-    tc::mma_split_katom<2>(taddr, tc::smem_u32(As), 16384, tc::smem_u32(Bs), tc::kUnitBytes, idesc, true);
-    tc::mma_commit(accfull);
-  }
-  __syncwarp();
+  } else {
+    // ===== scan warps: TMEM lane quarter (warp & 3), column quarter (warp >> 2); thread = 1 query row x 16 keys ====
+    const int quarter = warp & 3, cq = warp >> 2;
+    const int erow = quarter * 32 + lane;
+    const bool row_ok = q0 + erow < N;
+    const uint32_t tlane = static_cast<uint32_t>(quarter * 32) << 16;
+    float top[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) top[i] = -INFINITY;
 
-  const int quarter = warp & 3, cq = warp >> 2;
-  const int erow = quarter * 32 + lane;                     // scan: this thread's query row
-  const bool row_ok = q0 + erow < N;
-
-  for (int t = 0; t < Tk; ++t) {
-    if (tid == 0 && t + 1 < Tk) {                           // keep the tensor pipe one tile ahead of the selection
-      const int s1 = (t + 1) % kTcStages;
-      tc::mbar_wait(full + s1, ((t + 1) / kTcStages) & 1);
+    // ---- pass 1: threshold estimate from the first T1 tiles ------------------------------------------------------
+    for (int i = 0; i < T1; ++i) {
+      const int s = i % kTcStages, a = i % kAccs;
+      tc::mbar_wait(accfull + a, (i / kAccs) & 1);
       tc::fence_after_sync();
-      tc::mma_split_katom<2>(taddr + ((t + 1) & 1) * kTcKeyTile, tc::smem_u32(As), 16384, tc::smem_u32(Bs + s1 * kStageBytes),
-                             tc::kUnitBytes, idesc, true);
-      tc::mma_commit(accfull + ((t + 1) & 1));
-    }
-    __syncwarp();
-    tc::mbar_wait(accfull + (t & 1), (t >> 1) & 1);
-    tc::fence_after_sync();
-    {
       float v[16];
-      tc::tmem_ld16(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + (t & 1) * kTcKeyTile + cq * 16, v);
-      const float* kn = reinterpret_cast<const float*>(Bs + (t % kTcStages) * kStageBytes + 2 * tc::kUnitBytes) + cq * 16;
-      const float thr = S.thr[erow];
-      int n = S.cnt[erow * sel::kSub + cq];
-      const int j0 = t * kTcKeyTile + cq * 16;
-      if (t < Tk - 1) {                                     // every key of the tile exists
-        if (row_ok) {
+      tc::tmem_ld16(taddr + tlane + a * kTcKeyTile + cq * 16, v);
+      const float* kn = reinterpret_cast<const float*>(Bs + s * kStageBytes + 2 * tc::kUnitBytes) + cq * 16;
+      const int jn = N - (i * kTcKeyTile + cq * 16);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float sc = __fmaf_rn(v[i], 2.0f, -kn[i]); // approx of 2 x_i.x_j - |x_j|^2 (|x_i|^2 is constant per row)
-            if (sc > thr) sel::push(S, erow, cq, n, sc, j0 + i);
-          }
-        }
-      } else {
-        const int jn = row_ok ? N - j0 : 0;                 // keys j0+i with i < jn exist
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float sc = __fmaf_rn(v[i], 2.0f, -kn[i]);
-          if (sc > thr && i < jn) sel::push(S, erow, cq, n, sc, j0 + i);
-        }
+      for (int c = 0; c < 16; ++c) {
+        const float sc = __fmaf_rn(v[c], 2.0f, -kn[c]);
+        if (sc > top[7] && c < jn) top8_insert(top, sc);
       }
-      S.cnt[erow * sel::kSub + cq] = n;
-      // A sub-buffer (16 slots) receives at most 16 keys per tile, each with probability ~kp/(keys seen): compact early
-      // and often while that probability is high so that overflow (-> exact fallback for the row) stays a non-event.
-      const int trigger = (t == Tk - 1 || t == 0) ? 1 : (t < 32 ? 4 : 8);
-      sel::request_compaction(S, erow, n, trigger, t & 1);
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        tc::mbar_arrive(accfree + a);
+        tc::mbar_arrive(sfree + s);
+      }
     }
-    tc::fence_before_sync();
-    __syncthreads();                                        // pushes visible; tile t's smem slot and accumulator are free
-    if (tid == 0 && t + kTcStages < Tk) {
-      const int s = t % kTcStages;
-      tc::mbar_arrive_expect_tx(full + s, kTileBytes);
-      tc::bulk_g2s(Bs + s * kStageBytes, btiles + static_cast<size_t>(t + kTcStages) * kTileBytes, kTileBytes, full + s);
-    }
-    __syncwarp();
-    // Tile 0 bootstraps the threshold: the kinit-th best of the first 64 keys has an expected global rank of
-    // ~kinit*N/65 >= 4*kp, which removes the initial flood of candidates; if it turns out tighter than the kp-th best
-    // overall the certificate below fails and the row goes to the exact fallback (probability < 1e-3).
-    if (tid == 0) S.nwork[(t + 1) & 1] = 0;
-    sel::compact_queued(S, warp, kTcThreads / 32, lane, t == 0 ? kinit : kp, t & 1);
-    __syncthreads();                                        // thresholds / buffers consistent for the next scan
-  }
+    tau4[erow * 4 + cq] = top[7];
+    named_bar_sync(1, kScanWarps * 32);
+    const float4 t4 = *reinterpret_cast<const float4*>(tau4 + erow * 4);
+    const float tau = 0.25f * (t4.x + t4.y + t4.z + t4.w);     // -inf if a thread saw fewer than 8 keys: keep all
+    if (cq == 0) tauS[erow] = tau;
 
-  // ---- certificate + exact re-scoring + exact top-k (warp per query row) ---------------------------------
-  const float rmax = sqrtf(__uint_as_float(maxnorm_bits[b]));
-  for (int rr = 0; rr < 8; ++rr) {
-    const int row = warp * 8 + rr, q = q0 + row;
-    if (q >= N) break;
-    const sel::u64 l0 = S.lists[(row * 2 + 0) * 32 + lane];
-    const sel::u64 l1 = S.lists[(row * 2 + 1) * 32 + lane];
-    const size_t g = static_cast<size_t>(b) * N + q;
-    const float norm_i = norms[g];
-    const float ni = sqrtf(norm_i);
-    const float eps = 1.01f * (kC1 * ni * rmax + kC2 * (ni + rmax) * (ni + rmax));
-    const float tk = sel::key_score(sel::list_at(l0, l1, k - 1));
-    const float cut = tk - 2.0f * eps;
-    // every key whose approximate score exceeds the final pass threshold is in the list, so the list is complete
-    // above `cut` iff that threshold is strictly below the cut
-    const bool uncertified = !(S.thr[row] < cut) || S.overflow[row] != 0;
-    const float* xi = rows + g * ld;
-    sel::u64 ex[2];
-    const sel::u64 ls[2] = {l0, l1};
+    // ---- pass 2: collect every key above tau ------------------------------------------------------------------------
+    unsigned long long* mycand = cand + ((static_cast<size_t>(b) * N + q0 + erow) * 4 + cq) * kSubCands;
+    int n = 0;
+    for (int i = T1; i < TT; ++i) {
+      const int s = i % kTcStages, a = i % kAccs;
+      tc::mbar_wait(accfull + a, (i / kAccs) & 1);
+      tc::fence_after_sync();
+      float v[16];
+      tc::tmem_ld16(taddr + tlane + a * kTcKeyTile + cq * 16, v);
+      const float* kn = reinterpret_cast<const float*>(Bs + s * kStageBytes + 2 * tc::kUnitBytes) + cq * 16;
+      const int j0 = (i - T1) * kTcKeyTile + cq * 16;
+      const int jn = row_ok ? N - j0 : 0;
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      ex[r] = 0ull;
-      if (ls[r] != 0ull && sel::key_score(ls[r]) >= cut) {
-        const int j = key_index(ls[r]);
-        const size_t gj = static_cast<size_t>(b) * N + j;
-        ex[r] = make_key(exact_score(xi, rows + gj * ld, C4, norm_i, norms[gj]), j);
+      for (int c = 0; c < 16; ++c) {
+        const float sc = __fmaf_rn(v[c], 2.0f, -kn[c]);    // approx of 2 x_i.x_j - |x_j|^2 (|x_i|^2 is constant per row)
+        if (sc > tau && c < jn) {
+          if (n < kSubCands) mycand[n] = make_key(sc, j0 + c);
+          ++n;
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        tc::mbar_arrive(accfree + a);
+        tc::mbar_arrive(sfree + s);
       }
     }
-    int rank0 = 0, rank1 = 0;
+    cnt4[erow * 4 + cq] = n;
+    __threadfence_block();
+    named_bar_sync(1, kScanWarps * 32);
+
+    // ---- pass 3: bisect, re-score exactly, certify (warp per row, 8 rows per warp) ----------------------------------
+    const float rmax = sqrtf(__uint_as_float(maxnorm_bits[b]));
+    unsigned long long* stg = stageS + warp * kSurvivors;
+    for (int rr = 0; rr < 8; ++rr) {
+      const int row = warp * 8 + rr, q = q0 + row;
+      if (q >= N) break;
+      const size_t g = static_cast<size_t>(b) * N + q;
+      const int4 c4 = *reinterpret_cast<const int4*>(cnt4 + row * 4);
+      bool bad = max(max(c4.x, c4.y), max(c4.z, c4.w)) > kSubCands;          // a sub-buffer overflowed
+      const int cs[4] = {min(c4.x, kSubCands), min(c4.y, kSubCands), min(c4.z, kSubCands), min(c4.w, kSubCands)};
+      const int ntot = cs[0] + cs[1] + cs[2] + cs[3];
+      bad = bad || ntot < k;                                                  // tau was too tight
+      const unsigned long long* rc = cand + g * 4 * kSubCands;
+      unsigned long long key[8];
+      float ap[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int sub = r >> 1, slot = (r & 1) * 32 + lane;
+        key[r] = slot < cs[sub] ? rc[sub * kSubCands + slot] : 0ull;
+        ap[r] = key[r] != 0ull ? sel::key_score(key[r]) : -INFINITY;
+      }
+      const float tau_r = tauS[row];
+      // bisection: v with at least min(ntot, k+4) candidates strictly above it
+      float lo = tau_r, hi = ap[0];
+#pragma unroll
+      for (int r = 1; r < 8; ++r) hi = fmaxf(hi, ap[r]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      if (!(lo > -INFINITY)) {                       // tau = -inf (tiny blocks): start from the smallest candidate
+        float mn = INFINITY;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) mn = fminf(mn, key[r] != 0ull ? ap[r] : INFINITY);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        lo = mn - fabsf(mn) * 1e-6f - 1e-30f;
+      }
+      const int want = min(ntot, k + 4);
+      for (int it = 0; it < 10; ++it) {
+        const float mid = 0.5f * (lo + hi);
+        int c = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) c += ap[r] > mid;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (c >= want) lo = mid; else hi = mid;
+      }
+      const float norm_i = norms[g];
+      const float ni = sqrtf(norm_i);
+      const float eps = 1.01f * (kC1 * ni * rmax + kC2 * (ni + rmax) * (ni + rmax));
+      const float cut = lo - 2.0f * eps;
+      // compact the survivors (approx > cut) into the warp's staging area
+      int base = 0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const bool keep = ap[r] > cut;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        const int pos = base + __popc(m & ((1u << lane) - 1u));
+        if (keep && pos < kSurvivors) stg[pos] = key[r];
+        base += __popc(m);
+      }
+      bad = bad || base > kSurvivors;                                         // too many near-ties to re-score here
+      const int ns = min(base, kSurvivors);
+      __syncwarp();
+      const float* xi = rows + g * ld;
+      unsigned long long ex[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        ex[r] = 0ull;
+        const int e = lane + 32 * r;
+        if (e < ns) {
+          const int j = key_index(stg[e]);
+          const size_t gj = static_cast<size_t>(b) * N + j;
+          ex[r] = make_key(exact_score(xi, rows + gj * ld, C4, norm_i, norms[gj]), j);
+        }
+      }
+      __syncwarp();
+      int rank0 = 0, rank1 = 0;
 #pragma unroll 4
-    for (int s = 0; s < 32; ++s) {
-      const sel::u64 o0 = __shfl_sync(0xffffffffu, ex[0], s);
-      const sel::u64 o1 = __shfl_sync(0xffffffffu, ex[1], s);
-      rank0 += (o0 > ex[0]) + (o1 > ex[0]);
-      rank1 += (o0 > ex[1]) + (o1 > ex[1]);
+      for (int s2 = 0; s2 < 32; ++s2) {
+        const unsigned long long o0 = __shfl_sync(0xffffffffu, ex[0], s2);
+        const unsigned long long o1 = __shfl_sync(0xffffffffu, ex[1], s2);
+        rank0 += (o0 > ex[0]) + (o1 > ex[0]);
+        rank1 += (o0 > ex[1]) + (o1 > ex[1]);
+      }
+      if (ex[0] != 0ull && rank0 < k) idx[g * k + rank0] = key_index(ex[0]);
+      if (ex[1] != 0ull && rank1 < k) idx[g * k + rank1] = key_index(ex[1]);
+      // certificate: no key outside the candidate set can reach the k-th exact score found
+      float pdk = -INFINITY;
+      if (ex[0] != 0ull && rank0 == k - 1) pdk = sel::key_score(ex[0]);
+      if (ex[1] != 0ull && rank1 == k - 1) pdk = sel::key_score(ex[1]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) pdk = fmaxf(pdk, __shfl_xor_sync(0xffffffffu, pdk, o));
+      bad = bad || !((tau_r - norm_i) + eps < pdk);
+      if (bad && lane == 0) fb_rows[atomicAdd(fb_count, 1)] = static_cast<int>(g);
     }
-    if (ex[0] != 0ull && rank0 < k) idx[g * k + rank0] = key_index(ex[0]);
-    if (ex[1] != 0ull && rank1 < k) idx[g * k + rank1] = key_index(ex[1]);
-    if (uncertified && lane == 0) fb_rows[atomicAdd(fb_count, 1)] = static_cast<int>(g);
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(taddr, 128);
+  if (warp == kScanWarps) tc::tmem_dealloc(taddr, kAccs * kTcKeyTile);
 }
 
 // warp-cooperative sorted insertion used by the brute-force fallback (2 keys per lane, position = r*32 + lane)
@@ -303,7 +415,7 @@ __global__ void __launch_bounds__(kThreads)
 knn_fallback_kernel(const float* __restrict__ rows, int ld, const float* __restrict__ norms, int N, int C4, int k,
                     int32_t* __restrict__ idx, const int* __restrict__ fb_count, const int* __restrict__ fb_rows) {
   __shared__ __align__(16) float xi[64];
-  __shared__ unsigned long long wl[8][sel::kList];
+  __shared__ unsigned long long wl[8][64];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int count = *fb_count;
   for (int f = blockIdx.x; f < count; f += gridDim.x) {
@@ -352,7 +464,8 @@ knn_fallback_kernel(const float* __restrict__ rows, int ld, const float* __restr
 
 using namespace dg;
 
-static size_t knn_tc_layout(int B, int N, size_t* o_norms, size_t* o_max, size_t* o_cnt, size_t* o_rows, size_t* o_tiles) {
+static size_t knn_tc_layout(int B, int N, size_t* o_norms, size_t* o_max, size_t* o_cnt, size_t* o_rows, size_t* o_tiles,
+                            size_t* o_cand) {
   const int T = 2 * ((N + 127) / 128);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 1023) & ~size_t(1023); return o; };
@@ -361,16 +474,18 @@ static size_t knn_tc_layout(int B, int N, size_t* o_norms, size_t* o_max, size_t
   *o_cnt = take(4);
   *o_rows = take(static_cast<size_t>(B) * N * 4);
   *o_tiles = take(static_cast<size_t>(B) * T * kTileBytes);
+  // candidate buffers; query tiles are padded to 128 rows, so allow for the rows past the end of the last block
+  *o_cand = take((static_cast<size_t>(B) * N + 128) * 4 * kSubCands * 8);
   return off + 1024;
 }
 
 extern "C" size_t dgcnn_knn_tc_workspace_bytes(int B, int N) {
   if (B <= 0 || N <= 0) return 0;
-  size_t a, b, c, d, e;
-  return knn_tc_layout(B, N, &a, &b, &c, &d, &e);
+  size_t a, b, c, d, e, f;
+  return knn_tc_layout(B, N, &a, &b, &c, &d, &e, &f);
 }
 
-extern "C" int dgcnn_knn_tc_supported(int C, int N, int k) { return (C > 16 && C <= 64 && k <= 48 && N >= 128) ? 1 : 0; }
+extern "C" int dgcnn_knn_tc_supported(int C, int N, int k) { return (C > 16 && C <= 64 && k <= 48 && N >= 1024) ? 1 : 0; }
 
 extern "C" int dgcnn_knn_tc_f32(const float* rows, int ld, int B, int C, int N, int k, int32_t* idx, void* workspace,
                                 size_t workspace_bytes, void* stream) {
@@ -378,14 +493,14 @@ extern "C" int dgcnn_knn_tc_f32(const float* rows, int ld, int B, int C, int N, 
   DG_REQUIRE(B > 0 && N > 0 && C > 0 && B <= 65535, DGCNN_E_INVALID, "knn_tc: bad shape B=%d C=%d N=%d", B, C, N);
   DG_REQUIRE(k >= 1 && k <= N, DGCNN_E_INVALID, "knn_tc: selected index k out of range (k=%d, N=%d)", k, N);
   DG_REQUIRE(dgcnn_knn_tc_supported(C, N, k), DGCNN_E_UNSUPPORTED,
-             "knn_tc: needs 16 < C <= 64, k <= 48, N >= 128 (C=%d N=%d k=%d); use dgcnn_knn_f32", C, N, k);
+             "knn_tc: needs 16 < C <= 64, k <= 48, N >= 1024 (C=%d N=%d k=%d); use dgcnn_knn_f32", C, N, k);
   const int C4 = (C + 3) / 4 * 4;
   DG_REQUIRE(ld >= C4 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0, DGCNN_E_INVALID,
              "knn_tc: rows must be 16-byte aligned with ld %% 4 == 0 and ld >= round4(C)");
   DG_REQUIRE(workspace_bytes >= dgcnn_knn_tc_workspace_bytes(B, N), DGCNN_E_WORKSPACE, "knn_tc: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  size_t o_norms, o_max, o_cnt, o_rows, o_tiles;
-  knn_tc_layout(B, N, &o_norms, &o_max, &o_cnt, &o_rows, &o_tiles);
+  size_t o_norms, o_max, o_cnt, o_rows, o_tiles, o_cand;
+  knn_tc_layout(B, N, &o_norms, &o_max, &o_cnt, &o_rows, &o_tiles, &o_cand);
   unsigned char* ws = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
   float* norms = reinterpret_cast<float*>(ws + o_norms);
   unsigned int* maxnorm = reinterpret_cast<unsigned int*>(ws + o_max);
@@ -400,10 +515,13 @@ extern "C" int dgcnn_knn_tc_f32(const float* rows, int ld, int B, int C, int N, 
   knn_tc_prep_kernel<<<dim3(std::min((T * 512 + 255) / 256, 4096), B), 256, 0, st>>>(rows, ld, N, C4, T, norms, tiles);
   DG_CUDA(cudaGetLastError());
   DG_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(KnnTcSmem::bytes)));
-  const int kp = std::min(sel::kList, k + 8);     // list position that defines the pass threshold / certificate
-  const int kinit = std::max(4, std::min(kp, (4 * kp * 65 + N - 1) / N));
-  knn_tc_kernel<<<dim3((N + 127) / 128, B), kTcThreads, KnnTcSmem::bytes, st>>>(tiles, rows, ld, norms, maxnorm, N, C4, T, k, kp,
-                                                                               kinit, idx, fb_count, fb_rows);
+  // pass-1 sample: the 8th best of a thread's 16*T1 keys estimates global rank N/(2*T1); aim at ~max(100, 3k)
+  const int Tk = (N + kTcKeyTile - 1) / kTcKeyTile;
+  const int target = std::max(100, 3 * k);
+  const int T1 = std::max(1, std::min(Tk, (N + 2 * target - 1) / (2 * target)));
+  unsigned long long* cand = reinterpret_cast<unsigned long long*>(ws + o_cand);
+  knn_tc_kernel<<<dim3((N + 127) / 128, B), kTcThreads, KnnTcSmem::bytes, st>>>(tiles, rows, ld, norms, maxnorm, N, C4, T, k, T1,
+                                                                               cand, idx, fb_count, fb_rows);
   DG_CUDA(cudaGetLastError());
   knn_fallback_kernel<<<64, kThreads, 0, st>>>(rows, ld, norms, N, C4, k, idx, fb_count, fb_rows);
   DG_CUDA(cudaGetLastError());
