@@ -485,7 +485,7 @@ extern "C" size_t dgcnn_knn_tc_workspace_bytes(int B, int N) {
   return knn_tc_layout(B, N, &a, &b, &c, &d, &e, &f);
 }
 
-extern "C" int dgcnn_knn_tc_supported(int C, int N, int k) { return (C > 16 && C <= 64 && k <= 48 && N >= 1024) ? 1 : 0; }
+extern "C" int dgcnn_knn_tc_supported(int C, int N, int k) { return (C > 16 && C <= 64 && k <= 48 && N >= 128) ? 1 : 0; }
 
 extern "C" int dgcnn_knn_tc_f32(const float* rows, int ld, int B, int C, int N, int k, int32_t* idx, void* workspace,
                                 size_t workspace_bytes, void* stream) {
@@ -493,7 +493,7 @@ extern "C" int dgcnn_knn_tc_f32(const float* rows, int ld, int B, int C, int N, 
   DG_REQUIRE(B > 0 && N > 0 && C > 0 && B <= 65535, DGCNN_E_INVALID, "knn_tc: bad shape B=%d C=%d N=%d", B, C, N);
   DG_REQUIRE(k >= 1 && k <= N, DGCNN_E_INVALID, "knn_tc: selected index k out of range (k=%d, N=%d)", k, N);
   DG_REQUIRE(dgcnn_knn_tc_supported(C, N, k), DGCNN_E_UNSUPPORTED,
-             "knn_tc: needs 16 < C <= 64, k <= 48, N >= 1024 (C=%d N=%d k=%d); use dgcnn_knn_f32", C, N, k);
+             "knn_tc: needs 16 < C <= 64, k <= 48, N >= 128 (C=%d N=%d k=%d); use dgcnn_knn_f32", C, N, k);
   const int C4 = (C + 3) / 4 * 4;
   DG_REQUIRE(ld >= C4 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0, DGCNN_E_INVALID,
              "knn_tc: rows must be 16-byte aligned with ld %% 4 == 0 and ld >= round4(C)");

@@ -138,7 +138,8 @@ def knn_rows(rows: torch.Tensor, B: int, Cn: int, N: int, k: int, method: str = 
     rows, ld = _rows_view(rows)
     lib = _lib.load()
     idx = torch.empty(B * N, k, dtype=torch.int32, device=rows.device)
-    use_tc = method == "tc" or (method == "auto" and k <= N and lib.dgcnn_knn_tc_supported(Cn, N, k))
+    # small blocks: the pass-1 threshold needs a few thousand keys to pay off
+    use_tc = method == "tc" or (method == "auto" and k <= N and N >= 1024 and lib.dgcnn_knn_tc_supported(Cn, N, k))
     if use_tc:
         nbytes = lib.dgcnn_knn_tc_workspace_bytes(B, N)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=rows.device)
