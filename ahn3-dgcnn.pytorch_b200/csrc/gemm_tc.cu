@@ -49,6 +49,42 @@ __global__ void split_planes_kernel(const float* __restrict__ X, long long sr, l
   }
 }
 
+// Same output format for inputs whose contraction index is the SLOW memory dimension (sr == 1, e.g. A = dY^T for a
+// weight gradient): one CTA per 64x64 unit, coalesced loads along the rows, transposed through shared memory.
+template <int NS>
+__global__ void __launch_bounds__(256) split_planes_t_kernel(const float* __restrict__ X, long long sr, long long sc,
+                                                             int R, int K, int KA, unsigned char* __restrict__ out) {
+  __shared__ float tile[64][65];                 // [c][r]
+  const int u = blockIdx.x, ka = u % KA, rt = u / KA;
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int rl = tid & 63, cl = (tid >> 6) + 4 * i;
+    const int r = rt * 64 + rl, c = ka * 64 + cl;
+    tile[cl][rl] = (r < R && c < K) ? X[r * sr + c * sc] : 0.f;
+  }
+  __syncthreads();
+  unsigned char* unit = out + static_cast<size_t>(u) * NS * tc::kUnitBytes;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int rl = (tid >> 3) + 32 * h, ch = tid & 7;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = tile[ch * 8 + e][rl];
+    const uint32_t off = tc::unit_elem_offset(rl, ch * 8);
+#pragma unroll
+    for (int p = 0; p < NS; ++p) {
+      __nv_bfloat16 hv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        hv[e] = __float2bfloat16_rn(v[e]);
+        v[e] -= __bfloat162float(hv[e]);
+      }
+      *reinterpret_cast<uint4*>(unit + static_cast<size_t>(p) * tc::kUnitBytes + off) = *reinterpret_cast<const uint4*>(hv);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // GEMM kernel: one 128 x BN output tile per CTA, K streamed in 64-wide atoms through a STAGES-deep ring.
 // warp 0: bulk-copy producer | warp 1: TMEM owner + MMA issuer | warps 2-5: epilogue (one TMEM lane quarter each)
@@ -64,7 +100,7 @@ struct GemmSmem {
 template <int NS, int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __restrict__ Bp, float* __restrict__ D,
-               int ldd, int M, int N, int KA) {
+               int ldd, int M, int N, int KA, int ka_per_split, size_t split_stride) {
   using SM = GemmSmem<NS, BN, STAGES>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -75,6 +111,9 @@ tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __rest
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = blockIdx.x, mt = blockIdx.y;
+  // split-K: this CTA contracts k-atoms [ka_lo, ka_hi) and writes its partial tile to D + z * split_stride
+  const int ka_lo = blockIdx.z * ka_per_split, ka_hi = min(KA, ka_lo + ka_per_split);
+  D += static_cast<size_t>(blockIdx.z) * split_stride;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -92,9 +131,9 @@ tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __rest
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int ka = 0; ka < KA; ++ka) {
-        const int s = ka % STAGES;
-        tc::mbar_wait(empty + s, ((ka / STAGES) & 1) ^ 1);
+      for (int ka = ka_lo; ka < ka_hi; ++ka) {
+        const int it = ka - ka_lo, s = it % STAGES;
+        tc::mbar_wait(empty + s, ((it / STAGES) & 1) ^ 1);
         tc::mbar_arrive_expect_tx(full + s, SM::stage);
         unsigned char* a_s = tiles + s * SM::stage;
         unsigned char* b_s = a_s + NS * SM::a_plane;
@@ -117,12 +156,12 @@ tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __rest
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = tc::idesc_bf16(128, BN);
-      for (int ka = 0; ka < KA; ++ka) {
-        const int s = ka % STAGES;
-        tc::mbar_wait(full + s, (ka / STAGES) & 1);
+      for (int ka = ka_lo; ka < ka_hi; ++ka) {
+        const int it = ka - ka_lo, s = it % STAGES;
+        tc::mbar_wait(full + s, (it / STAGES) & 1);
         tc::fence_after_sync();
         const uint32_t a_s = tc::smem_u32(tiles + s * SM::stage);
-        tc::mma_split_katom<NS>(taddr, a_s, SM::a_plane, a_s + NS * SM::a_plane, SM::b_plane, idesc, ka == 0);
+        tc::mma_split_katom<NS>(taddr, a_s, SM::a_plane, a_s + NS * SM::a_plane, SM::b_plane, idesc, ka == ka_lo);
         tc::mma_commit(empty + s);       // frees the stage once these MMAs have read it
       }
       tc::mma_commit(accfull);
@@ -155,6 +194,19 @@ tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __rest
   if (warp == 1) tc::tmem_dealloc(taddr, BN);
 }
 
+// D[i] = sum_z P[z][i] in a fixed order (deterministic split-K reduction)
+__global__ void splitk_reduce_kernel(const float* __restrict__ P, size_t split_stride, int splits, float* __restrict__ D,
+                                     int ldd, int M, int N) {
+  const size_t total = static_cast<size_t>(M) * N;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t r = i / N, c = i % N;
+    float acc = 0.f;
+    for (int z = 0; z < splits; ++z) acc += P[z * split_stride + r * N + c];
+    D[r * ldd + c] = acc;
+  }
+}
+
 static size_t planes_bytes(int rows_pad, int KA, int NS) {
   return static_cast<size_t>(rows_pad / 64) * KA * NS * tc::kUnitBytes;
 }
@@ -162,6 +214,11 @@ static size_t planes_bytes(int rows_pad, int KA, int NS) {
 template <int NS>
 static int launch_split(const float* X, long long sr, long long sc, int R, int K, int R_pad, int KA, unsigned char* out,
                         cudaStream_t st) {
+  if (sr == 1 && sc != 1 && R_pad / 64 * KA < (1 << 30)) {       // contraction index is the slow dimension: transpose via smem
+    split_planes_t_kernel<NS><<<R_pad / 64 * KA, 256, 0, st>>>(X, sr, sc, R, K, KA, out);
+    DG_CUDA(cudaGetLastError());
+    return DGCNN_OK;
+  }
   const long long total = static_cast<long long>(R_pad) * KA * 8;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
   split_planes_kernel<NS><<<blocks, 256, 0, st>>>(X, sr, sc, R, K, R_pad, KA, out);
@@ -169,14 +226,33 @@ static int launch_split(const float* X, long long sr, long long sc, int R, int K
   return DGCNN_OK;
 }
 
+static int splitk_factor(int M, int N, int KA) {
+  const int tiles = ((N + 127) / 128) * ((M + 127) / 128);
+  if (tiles >= 148 || KA < 16) return 1;
+  return std::max(1, std::min(KA / 8, (2 * 148 + tiles - 1) / tiles));
+}
+
 template <int NS, int BN, int STAGES>
 static int launch_gemm(const unsigned char* Ap, const unsigned char* Bp, float* D, int ldd, int M, int N, int KA,
-                       cudaStream_t st) {
+                       float* partials, cudaStream_t st) {
   using SM = GemmSmem<NS, BN, STAGES>;
   auto kern = tc_gemm_kernel<NS, BN, STAGES>;
   DG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SM::bytes)));
-  dim3 grid((N + BN - 1) / BN, (M + 127) / 128);
-  kern<<<grid, 192, SM::bytes, st>>>(Ap, Bp, D, ldd, M, N, KA);
+  const int splits = splitk_factor(M, N, KA);
+  dim3 grid((N + BN - 1) / BN, (M + 127) / 128, splits);
+  if (splits == 1) {
+    kern<<<grid, 192, SM::bytes, st>>>(Ap, Bp, D, ldd, M, N, KA, KA, 0);
+    DG_CUDA(cudaGetLastError());
+    return DGCNN_OK;
+  }
+  const int per = (KA + splits - 1) / splits;
+  const size_t stride = static_cast<size_t>(M) * N;
+  grid.z = (KA + per - 1) / per;
+  kern<<<grid, 192, SM::bytes, st>>>(Ap, Bp, partials, N, M, N, KA, per, stride);
+  DG_CUDA(cudaGetLastError());
+  const size_t total = stride;
+  splitk_reduce_kernel<<<static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 8)), 256, 0, st>>>(partials, stride, grid.z, D,
+                                                                                                     ldd, M, N);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
 }
@@ -188,7 +264,9 @@ using namespace dg;
 extern "C" size_t dgcnn_tc_gemm_workspace_bytes(int M, int N, int K, int nsplit) {
   if (M <= 0 || N <= 0 || K <= 0 || nsplit < 2 || nsplit > 3) return 0;
   const int KA = (K + 63) / 64;
-  return planes_bytes((M + 127) / 128 * 128, KA, nsplit) + planes_bytes((N + 127) / 128 * 128, KA, nsplit) + 2048;
+  const size_t part = static_cast<size_t>(splitk_factor(M, N, KA)) * M * N * sizeof(float);
+  return planes_bytes((M + 127) / 128 * 128, KA, nsplit) + planes_bytes((N + 127) / 128 * 128, KA, nsplit) +
+         (splitk_factor(M, N, KA) > 1 ? part : 0) + 4096;
 }
 
 extern "C" int dgcnn_tc_gemm_f32(const float* A, int64_t a_sr, int64_t a_sc, const float* B, int64_t b_sr, int64_t b_sc,
@@ -202,13 +280,14 @@ extern "C" int dgcnn_tc_gemm_f32(const float* A, int64_t a_sr, int64_t a_sc, con
   const int KA = (K + 63) / 64, Mp = (M + 127) / 128 * 128, Np = (N + 127) / 128 * 128;
   unsigned char* Ap = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
   unsigned char* Bp = Ap + planes_bytes(Mp, KA, nsplit);
+  float* partials = reinterpret_cast<float*>(Bp + planes_bytes(Np, KA, nsplit));
   int rc;
   if (nsplit == 3) {
     if ((rc = launch_split<3>(A, a_sr, a_sc, M, K, Mp, KA, Ap, st))) return rc;
     if ((rc = launch_split<3>(B, b_sr, b_sc, N, K, Np, KA, Bp, st))) return rc;
-    return launch_gemm<3, 128, 2>(Ap, Bp, D, ldd, M, N, KA, st);
+    return launch_gemm<3, 128, 2>(Ap, Bp, D, ldd, M, N, KA, partials, st);
   }
   if ((rc = launch_split<2>(A, a_sr, a_sc, M, K, Mp, KA, Ap, st))) return rc;
   if ((rc = launch_split<2>(B, b_sr, b_sc, N, K, Np, KA, Bp, st))) return rc;
-  return launch_gemm<2, 128, 3>(Ap, Bp, D, ldd, M, N, KA, st);
+  return launch_gemm<2, 128, 3>(Ap, Bp, D, ldd, M, N, KA, partials, st);
 }

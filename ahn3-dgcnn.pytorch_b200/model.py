@@ -127,7 +127,7 @@ class DGCNN(nn.Module):
 
     def _dense(self, h: torch.Tensor, i: int) -> torch.Tensor:
         conv, bn = getattr(self, f"conv{i}")[0], getattr(self, f"bn{i}")
-        return F.leaky_relu(bn(h @ conv.weight.squeeze(-1).t()), LRELU_SLOPE)
+        return F.leaky_relu(bn(ops.linear(h, conv.weight.squeeze(-1))), LRELU_SLOPE)
 
     def forward(self, x, depth=10, *, forced_idx=None):
         if not x.is_cuda:
@@ -170,7 +170,7 @@ class DGCNN(nn.Module):
         if E + feat.size(1) != w7.size(1):
             raise RuntimeError(f"conv7 expects {w7.size(1)} input channels but emb_dims+192 = {E + feat.size(1)}")
         # conv7([g ; x1,x2,x3]) = W7[:, :E] g (once per block) + W7[:, E:] feat  — no repeat/cat of the global feature
-        y7 = (feat @ w7[:, E:].t()).view(B, N, -1) + (g @ w7[:, :E].t()).unsqueeze(1)
+        y7 = ops.linear(feat, w7[:, E:]).view(B, N, -1) + (g @ w7[:, :E].t()).unsqueeze(1)
         h7 = F.leaky_relu(self.bn7(y7.view(B * N, -1)), LRELU_SLOPE)
         if depth == 8:
             return self._bcn(h7, B, N)

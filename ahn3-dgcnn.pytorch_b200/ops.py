@@ -61,7 +61,7 @@ class KernelLog:
 LOG = KernelLog()
 
 # kernels launched by each entry point
-_LAUNCHES = {"dgcnn_knn_f32": 2, "dgcnn_knn_tc_f32": 4, "dgcnn_edgeconv_bwd_b": 2}
+_LAUNCHES = {"dgcnn_knn_f32": 2, "dgcnn_knn_tc_f32": 4, "dgcnn_edgeconv_bwd_b": 2, "dgcnn_tc_gemm_f32": 3}
 
 
 def _call(name: str, *args) -> None:
@@ -156,6 +156,57 @@ def graph_feature_rows(rows: torch.Tensor, idx: torch.Tensor, B: int, Cn: int, N
     out = torch.empty(B, N, k, 2 * Cn, dtype=torch.float32, device=rows.device)
     _call("dgcnn_graph_feature_f32", _ptr(rows), ld, _ptr(idx), B, Cn, N, k, _ptr(out), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# dense GEMMs of the shared MLP / head on the tensor cores (tcgen05, FP32-accurate bf16x3 split)
+# ------------------------------------------------------------------------------------------------
+_gemm_ws = {}
+
+
+def tc_gemm(a: torch.Tensor, b: torch.Tensor, nsplit: int = 3) -> torch.Tensor:
+    """D[M,N] = a[M,K] @ b[N,K]^T in FP32 via dgcnn_tc_gemm_f32; a and b may be arbitrary 2-D strided views."""
+    M, K = a.shape
+    N = b.shape[0]
+    lib = _lib.load()
+    nbytes = lib.dgcnn_tc_gemm_workspace_bytes(M, N, K, nsplit)
+    key = (a.device.index, nbytes)
+    ws = _gemm_ws.get(a.device.index)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.25), dtype=torch.uint8, device=a.device)
+        _gemm_ws[a.device.index] = ws
+    d = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    _call("dgcnn_tc_gemm_f32", _ptr(a), a.stride(0), a.stride(1), _ptr(b), b.stride(0), b.stride(1), _ptr(d), N, M, N, K,
+          nsplit, _ptr(ws), ws.numel(), _stream())
+    return d
+
+
+class TcLinear(torch.autograd.Function):
+    """y = x @ w^T (x [M,K], w [N,K]) with all three GEMMs (y, dx, dw) on the tensor cores."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return tc_gemm(x, w)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = tc_gemm(dy, w.t())                 # [M,K] = dy[M,N] @ w[N,K]
+        if ctx.needs_input_grad[1]:
+            dw = tc_gemm(dy.t(), x.t())             # [N,K] = dy^T[N,M] @ x[M,K]   (split-K over the points)
+        return dx, dw
+
+
+def linear(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """x @ w^T; tensor-core path for GEMMs big enough to fill the machine, library GEMM otherwise."""
+    M, K = x.shape
+    N = w.shape[0]
+    if x.is_cuda and x.dtype == torch.float32 and M >= 1024 and N >= 64 and K >= 64:
+        return TcLinear.apply(x, w)
+    return x @ w.t()
 
 
 # ------------------------------------------------------------------------------------------------
