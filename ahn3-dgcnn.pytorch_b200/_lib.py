@@ -30,6 +30,9 @@ SIGNATURES = {
     "dgcnn_knn_tc_supported": (c_int, [c_int, c_int, c_int]),
     "dgcnn_knn_tc_workspace_bytes": (c_size_t, [c_int, c_int]),
     "dgcnn_knn_tc_f32": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "dgcnn_knn_small_supported": (c_int, [c_int, c_int, c_int]),
+    "dgcnn_knn_small_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "dgcnn_knn_small_f32": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "dgcnn_graph_feature_f32": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "dgcnn_edgeconv_fwd_eval": (c_int, [_ARGS, _P, _P, _P]),
     "dgcnn_edgeconv_partials_bytes": (c_size_t, []),

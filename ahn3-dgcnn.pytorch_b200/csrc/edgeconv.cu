@@ -285,18 +285,33 @@ __global__ void __launch_bounds__(kThreads, 2) ec_fwd_kernel(const EcK p) {
 // ---------------------------------------------------------------------------------------------
 // small per-channel kernels
 // ---------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const double* __restrict__ partials, int C, double count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                   float momentum, float* running_mean, float* running_var, float* mean,
-                                   float* rstd, float* aff) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// Sum partials[part][2][C] over the parts with 4 thread groups (fixed order -> deterministic): thread (grp, c)
+// accumulates parts grp, grp+4, ... ; the four group sums are added in order.  Result valid for threadIdx.x < C.
+__device__ __forceinline__ void reduce_partials(const double* __restrict__ partials, int C, double& s, double& q) {
+  __shared__ double red[2][4][64];
+  const int c = threadIdx.x & 63, grp = threadIdx.x >> 6;
   const int nparts = static_cast<int>(partials[0]);
-  double s = 0.0, q = 0.0;
-  for (int i = 0; i < nparts; ++i) {
-    s += partials[128 + static_cast<size_t>(i) * 2 * C + c];
-    q += partials[128 + static_cast<size_t>(i) * 2 * C + C + c];
+  double a = 0.0, b = 0.0;
+#pragma unroll 4
+  for (int i = grp; i < nparts; i += 4) {
+    a += partials[128 + static_cast<size_t>(i) * 2 * C + c];
+    b += partials[128 + static_cast<size_t>(i) * 2 * C + C + c];
   }
+  red[0][grp][c] = a;
+  red[1][grp][c] = b;
+  __syncthreads();
+  s = ((red[0][0][c] + red[0][1][c]) + red[0][2][c]) + red[0][3][c];
+  q = ((red[1][0][c] + red[1][1][c]) + red[1][2][c]) + red[1][3][c];
+}
+
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restrict__ partials, int C, double count,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float eps, float momentum, float* running_mean,
+                                                          float* running_var, float* mean, float* rstd, float* aff) {
+  double s, q;
+  reduce_partials(partials, C, s, q);
+  const int c = threadIdx.x;
+  if (c >= C) return;
   const double m = s / count;
   double var = q / count - m * m;
   if (var < 0.0) var = 0.0;
@@ -361,17 +376,14 @@ __global__ void __launch_bounds__(kThreads) bwd_prep_kernel(int M, const float* 
 
 // From S1 = sum dz, S2 = sum dz*y:  dgamma = rstd (S2 - mean S1), dbeta = S1 and the coefficients of
 // dy = cA dz - cB - cC y  (BatchNorm backward with batch statistics).
-__global__ void bn_bwd_reduce_kernel(const double* __restrict__ partials, int C, double count,
-                                     const float* __restrict__ gamma, const float* __restrict__ mean,
-                                     const float* __restrict__ rstd, float* dgamma, float* dbeta, float* coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const double* __restrict__ partials, int C, double count,
+                                                            const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, float* dgamma, float* dbeta,
+                                                            float* coef) {
+  double s1, s2;
+  reduce_partials(partials, C, s1, s2);
+  const int c = threadIdx.x;
   if (c >= C) return;
-  const int nparts = static_cast<int>(partials[0]);
-  double s1 = 0.0, s2 = 0.0;
-  for (int i = 0; i < nparts; ++i) {
-    s1 += partials[128 + static_cast<size_t>(i) * 2 * C + c];
-    s2 += partials[128 + static_cast<size_t>(i) * 2 * C + C + c];
-  }
   const double m = mean[c], rs = rstd[c], ga = gamma[c];
   const double dg = rs * (s2 - m * s1);
   dgamma[c] = static_cast<float>(dg);
@@ -676,7 +688,7 @@ extern "C" int dgcnn_bn_finalize(const double* partials, int C, double count, co
   DG_REQUIRE(partials && gamma && beta && mean && rstd && aff, DGCNN_E_INVALID, "bn_finalize: null pointer");
   DG_REQUIRE(C == kCout, DGCNN_E_UNSUPPORTED, "bn_finalize: C must be 64");
   DG_REQUIRE(count >= 1.0 && (!running_mean == !running_var), DGCNN_E_INVALID, "bn_finalize: bad count / running stats");
-  bn_finalize_kernel<<<1, 64, 0, static_cast<cudaStream_t>(stream)>>>(partials, C, count, gamma, beta, eps, momentum,
+  bn_finalize_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, C, count, gamma, beta, eps, momentum,
                                                                     running_mean, running_var, mean, rstd, aff);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
@@ -708,7 +720,7 @@ extern "C" int dgcnn_bn_bwd_reduce(const double* partials, int C, double count, 
                                    const float* rstd, float* dgamma, float* dbeta, float* coef, void* stream) {
   DG_REQUIRE(partials && gamma && mean && rstd && dgamma && dbeta && coef, DGCNN_E_INVALID, "bn_bwd_reduce: null pointer");
   DG_REQUIRE(C == kCout && count >= 1.0, DGCNN_E_UNSUPPORTED, "bn_bwd_reduce: C must be 64");
-  bn_bwd_reduce_kernel<<<1, 64, 0, static_cast<cudaStream_t>(stream)>>>(partials, C, count, gamma, mean, rstd, dgamma, dbeta, coef);
+  bn_bwd_reduce_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, C, count, gamma, mean, rstd, dgamma, dbeta, coef);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
 }

@@ -460,6 +460,161 @@ knn_fallback_kernel(const float* __restrict__ rows, int ld, const float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// low-dimensional graphs (C <= 16: the xyz/agl input graph): same threshold - collect - select scheme with EXACT
+// scores from an FP32 FMA chain (thread per query, coordinates in registers, keys broadcast from shared memory).
+// No certificate is needed: every key above tau is a candidate, so the exact top-k is among them iff >= k were found.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSmallKeys = 512;        // keys per shared-memory tile
+constexpr int kSmallCap = 256;         // candidate slots per query row (global memory)
+
+template <int CP>
+__global__ void __launch_bounds__(kThreads)
+knn_small_kernel(const float* __restrict__ rows, int ld, const float* __restrict__ norms, int N, int k, int n_sample,
+                 unsigned long long* __restrict__ cand, int32_t* __restrict__ idx, int* __restrict__ fb_count,
+                 int* __restrict__ fb_rows) {
+  __shared__ __align__(16) float Ks[kSmallKeys * CP];
+  __shared__ float Kn[kSmallKeys];
+  __shared__ int cntS[kThreads];
+  __shared__ float tauS[kThreads];
+  __shared__ unsigned long long stageS[8][kSurvivors];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y, q0 = blockIdx.x * kThreads, q = q0 + tid;
+  const size_t base = static_cast<size_t>(b) * N;
+  const bool row_ok = q < N;
+  float xq[CP];
+#pragma unroll
+  for (int c = 0; c < CP; c += 4) {
+    const float4 v = row_ok ? *reinterpret_cast<const float4*>(rows + (base + q) * ld + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    xq[c] = v.x; xq[c + 1] = v.y; xq[c + 2] = v.z; xq[c + 3] = v.w;
+  }
+  const float nq = row_ok ? norms[base + q] : 0.f;
+  unsigned long long* mycand = cand + (base + q) * kSmallCap;
+
+  float top[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) top[i] = -INFINITY;
+  float tau = -INFINITY;
+  int n = 0;
+  // pass 0: the first n_sample keys give tau (8th best of the sample ~ global rank 8 N / n_sample); pass 1: all keys
+  for (int pass = 0; pass < 2; ++pass) {
+    const int nkeys = pass == 0 ? n_sample : N;
+    for (int t0 = 0; t0 < nkeys; t0 += kSmallKeys) {
+      __syncthreads();
+      for (int i = tid; i < kSmallKeys * (CP / 4); i += kThreads) {
+        const int r = i / (CP / 4), c4 = i % (CP / 4), j = t0 + r;
+        *reinterpret_cast<float4*>(Ks + r * CP + 4 * c4) =
+            j < nkeys ? *reinterpret_cast<const float4*>(rows + (base + j) * ld + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int r = tid; r < kSmallKeys; r += kThreads) Kn[r] = t0 + r < nkeys ? norms[base + t0 + r] : 0.f;
+      __syncthreads();
+      const int lim = min(kSmallKeys, nkeys - t0);
+#pragma unroll 4
+      for (int r = 0; r < lim; ++r) {
+        float d = 0.f;
+#pragma unroll
+        for (int c = 0; c < CP; c += 4) {
+          const float4 kv = *reinterpret_cast<const float4*>(Ks + r * CP + c);
+          d = __fmaf_rn(xq[c], kv.x, d);
+          d = __fmaf_rn(xq[c + 1], kv.y, d);
+          d = __fmaf_rn(xq[c + 2], kv.z, d);
+          d = __fmaf_rn(xq[c + 3], kv.w, d);
+        }
+        const float pd = __fsub_rn(__fmaf_rn(d, 2.0f, -Kn[r]), nq);      // model.py:37, one rounding per step
+        if (pass == 0) {
+          if (pd > top[7]) top8_insert(top, pd);
+        } else if (pd > tau && row_ok) {
+          if (n < kSmallCap) mycand[n] = make_key(pd, t0 + r);
+          ++n;
+        }
+      }
+    }
+    if (pass == 0) tau = top[7];          // -inf when fewer than 8 keys were sampled: keep everything
+  }
+  cntS[tid] = n;
+  tauS[tid] = tau;
+  __threadfence_block();
+  __syncthreads();
+
+  // selection: warp per query row (32 rows per warp)
+  unsigned long long* stg = stageS[warp];
+  for (int rr = 0; rr < 32; ++rr) {
+    const int row = warp * 32 + rr, qq = q0 + row;
+    if (qq >= N) break;
+    const size_t g = base + qq;
+    const int nc = cntS[row];
+    bool bad = nc > kSmallCap || nc < k;
+    const int ntot = min(nc, kSmallCap);
+    const unsigned long long* rc = cand + g * kSmallCap;
+    unsigned long long key[8];
+    float ap[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int slot = r * 32 + lane;
+      key[r] = slot < ntot ? rc[slot] : 0ull;
+      ap[r] = key[r] != 0ull ? sel::key_score(key[r]) : -INFINITY;
+    }
+    float lo = tauS[row], hi = ap[0];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) hi = fmaxf(hi, ap[r]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    if (!(lo > -INFINITY)) {
+      float mn = INFINITY;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) mn = fminf(mn, key[r] != 0ull ? ap[r] : INFINITY);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      lo = mn - fabsf(mn) * 1e-6f - 1e-30f;
+    }
+    const int want = min(ntot, k + 4);
+    for (int it = 0; it < 12; ++it) {            // v = lo: at least `want` candidates strictly above it
+      const float mid = 0.5f * (lo + hi);
+      int c = 0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) c += ap[r] > mid;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (c >= want) lo = mid; else hi = mid;
+    }
+    int nb = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const bool keep = ap[r] > lo;
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      const int pos = nb + __popc(m & ((1u << lane) - 1u));
+      if (keep && pos < kSurvivors) stg[pos] = key[r];
+      nb += __popc(m);
+    }
+    bad = bad || nb > kSurvivors;                 // > 64 exact ties around the k-th score
+    const int ns = min(nb, kSurvivors);
+    __syncwarp();
+    const unsigned long long e0 = lane < ns ? stg[lane] : 0ull;
+    const unsigned long long e1 = lane + 32 < ns ? stg[lane + 32] : 0ull;
+    __syncwarp();
+    int rank0 = 0, rank1 = 0;
+#pragma unroll 4
+    for (int s2 = 0; s2 < 32; ++s2) {
+      const unsigned long long o0 = __shfl_sync(0xffffffffu, e0, s2);
+      const unsigned long long o1 = __shfl_sync(0xffffffffu, e1, s2);
+      rank0 += (o0 > e0) + (o1 > e0);
+      rank1 += (o0 > e1) + (o1 > e1);
+    }
+    if (e0 != 0ull && rank0 < k) idx[g * k + rank0] = key_index(e0);
+    if (e1 != 0ull && rank1 < k) idx[g * k + rank1] = key_index(e1);
+    if (bad && lane == 0) fb_rows[atomicAdd(fb_count, 1)] = static_cast<int>(g);
+  }
+}
+
+template <int CP>
+static int launch_knn_small(const float* rows, int ld, const float* norms, int B, int N, int k, int n_sample,
+                            unsigned long long* cand, int32_t* idx, int* fb_count, int* fb_rows, cudaStream_t st) {
+  knn_small_kernel<CP><<<dim3((N + kThreads - 1) / kThreads, B), kThreads, 0, st>>>(rows, ld, norms, N, k, n_sample, cand, idx,
+                                                                                   fb_count, fb_rows);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}
+
 }  // namespace dg
 
 using namespace dg;
@@ -523,6 +678,62 @@ extern "C" int dgcnn_knn_tc_f32(const float* rows, int ld, int B, int C, int N, 
   knn_tc_kernel<<<dim3((N + 127) / 128, B), kTcThreads, KnnTcSmem::bytes, st>>>(tiles, rows, ld, norms, maxnorm, N, C4, T, k, T1,
                                                                                cand, idx, fb_count, fb_rows);
   DG_CUDA(cudaGetLastError());
+  knn_fallback_kernel<<<64, kThreads, 0, st>>>(rows, ld, norms, N, C4, k, idx, fb_count, fb_rows);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}
+
+
+// ---- low-dimensional exact kNN (C <= 16), threshold-collect-select ------------------------------------------------
+static size_t knn_small_layout(int B, int N, size_t* o_norms, size_t* o_cnt, size_t* o_rows, size_t* o_cand) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 1023) & ~size_t(1023); return o; };
+  *o_norms = take(static_cast<size_t>(B) * N * 4);
+  *o_cnt = take(4);
+  *o_rows = take(static_cast<size_t>(B) * N * 4);
+  *o_cand = take((static_cast<size_t>(B) * N + kThreads) * kSmallCap * 8);
+  return off + 1024;
+}
+
+extern "C" int dgcnn_knn_small_supported(int C, int N, int k) { return (C <= 16 && k <= 48 && N >= 512) ? 1 : 0; }
+
+extern "C" size_t dgcnn_knn_small_workspace_bytes(int B, int N) {
+  if (B <= 0 || N <= 0) return 0;
+  size_t a, b, c, d;
+  return knn_small_layout(B, N, &a, &b, &c, &d);
+}
+
+extern "C" int dgcnn_knn_small_f32(const float* rows, int ld, int B, int C, int N, int k, int32_t* idx, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  DG_REQUIRE(rows && idx && workspace, DGCNN_E_INVALID, "knn_small: null pointer");
+  DG_REQUIRE(B > 0 && N > 0 && C > 0 && B <= 65535, DGCNN_E_INVALID, "knn_small: bad shape B=%d C=%d N=%d", B, C, N);
+  DG_REQUIRE(k >= 1 && k <= N, DGCNN_E_INVALID, "knn_small: selected index k out of range (k=%d, N=%d)", k, N);
+  DG_REQUIRE(dgcnn_knn_small_supported(C, N, k), DGCNN_E_UNSUPPORTED,
+             "knn_small: needs C <= 16, k <= 48, N >= 512 (C=%d N=%d k=%d); use dgcnn_knn_f32", C, N, k);
+  const int C4 = (C + 3) / 4 * 4;
+  DG_REQUIRE(ld >= C4 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0, DGCNN_E_INVALID,
+             "knn_small: rows must be 16-byte aligned with ld %% 4 == 0 and ld >= round4(C)");
+  DG_REQUIRE(workspace_bytes >= dgcnn_knn_small_workspace_bytes(B, N), DGCNN_E_WORKSPACE, "knn_small: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  size_t o_norms, o_cnt, o_rows, o_cand;
+  knn_small_layout(B, N, &o_norms, &o_cnt, &o_rows, &o_cand);
+  unsigned char* ws = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  float* norms = reinterpret_cast<float*>(ws + o_norms);
+  int* fb_count = reinterpret_cast<int*>(ws + o_cnt);
+  int* fb_rows = reinterpret_cast<int*>(ws + o_rows);
+  unsigned long long* cand = reinterpret_cast<unsigned long long*>(ws + o_cand);
+  DG_CUDA(cudaMemsetAsync(fb_count, 0, 4, st));
+  // norms in torch.sum's order (rows beyond C are zero padded, so the padded chain is exact as well)
+  knn_norms_max_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(rows, ld, N, C, norms, reinterpret_cast<unsigned int*>(ws + o_rows));
+  DG_CUDA(cudaGetLastError());
+  // sample size: the 8th best of n_sample keys has expected global rank 8 N / n_sample; aim at max(100, 3k)
+  const int target = std::max(100, 3 * k);
+  const int n_sample = std::max(64, std::min(N, static_cast<int>(8LL * N / target)));
+  int rc;
+  if (C4 <= 4) rc = launch_knn_small<4>(rows, ld, norms, B, N, k, n_sample, cand, idx, fb_count, fb_rows, st);
+  else if (C4 <= 8) rc = launch_knn_small<8>(rows, ld, norms, B, N, k, n_sample, cand, idx, fb_count, fb_rows, st);
+  else rc = launch_knn_small<16>(rows, ld, norms, B, N, k, n_sample, cand, idx, fb_count, fb_rows, st);
+  if (rc) return rc;
   knn_fallback_kernel<<<64, kThreads, 0, st>>>(rows, ld, norms, N, C4, k, idx, fb_count, fb_rows);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;

@@ -61,7 +61,7 @@ class KernelLog:
 LOG = KernelLog()
 
 # kernels launched by each entry point
-_LAUNCHES = {"dgcnn_knn_f32": 2, "dgcnn_knn_tc_f32": 4, "dgcnn_edgeconv_bwd_b": 2, "dgcnn_tc_gemm_f32": 3}
+_LAUNCHES = {"dgcnn_knn_f32": 2, "dgcnn_knn_tc_f32": 4, "dgcnn_knn_small_f32": 3, "dgcnn_edgeconv_bwd_b": 2, "dgcnn_tc_gemm_f32": 3}
 
 
 def _call(name: str, *args) -> None:
@@ -132,18 +132,24 @@ def unpack_rows(rows: torch.Tensor, B: int, Cn: int, N: int) -> torch.Tensor:
 def knn_rows(rows: torch.Tensor, B: int, Cn: int, N: int, k: int, method: str = "auto") -> torch.Tensor:
     """Neighbour table int32 [B*N, k] of point-major rows (model.py:25-40).
 
-    method: "exact" = FP32-FMA kernel (any C <= 128); "tc" = tcgen05 filter + exact re-score (16 < C <= 64,
-    k <= 48), identical output; "auto" picks "tc" whenever it is supported."""
+    method: "exact" = FP32-FMA tile kernel (any C <= 128, any k <= 128); "tc" = tcgen05 filter + exact re-score
+    (16 < C <= 64, k <= 48); "small" = thread-per-query kernel (C <= 16, k <= 48, N >= 512); all three give the
+    identical table; "auto" picks the fastest supported one."""
     _need_cuda(rows, "knn")
     rows, ld = _rows_view(rows)
     lib = _lib.load()
     idx = torch.empty(B * N, k, dtype=torch.int32, device=rows.device)
-    # small blocks: the pass-1 threshold needs a few thousand keys to pay off
-    use_tc = method == "tc" or (method == "auto" and k <= N and N >= 1024 and lib.dgcnn_knn_tc_supported(Cn, N, k))
-    if use_tc:
-        nbytes = lib.dgcnn_knn_tc_workspace_bytes(B, N)
+    if method == "auto":
+        method = "exact"
+        if k <= N:
+            if N >= 1024 and lib.dgcnn_knn_tc_supported(Cn, N, k):       # small blocks: pass 1 does not pay off
+                method = "tc"
+            elif lib.dgcnn_knn_small_supported(Cn, N, k):
+                method = "small"
+    if method in ("tc", "small"):
+        nbytes = getattr(lib, f"dgcnn_knn_{method}_workspace_bytes")(B, N)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=rows.device)
-        _call("dgcnn_knn_tc_f32", _ptr(rows), ld, B, Cn, N, k, _ptr(idx), _ptr(ws), nbytes, _stream())
+        _call(f"dgcnn_knn_{method}_f32", _ptr(rows), ld, B, Cn, N, k, _ptr(idx), _ptr(ws), nbytes, _stream())
     else:
         norms = torch.empty(B * N, dtype=torch.float32, device=rows.device)
         _call("dgcnn_knn_f32", _ptr(rows), ld, B, Cn, N, k, _ptr(idx), _ptr(norms), _stream())

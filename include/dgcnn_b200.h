@@ -60,6 +60,14 @@ size_t dgcnn_knn_tc_workspace_bytes(int B, int N);
 int dgcnn_knn_tc_f32(const float* rows, int ld, int B, int C, int N, int k, int32_t* idx,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- low-dimensional kNN (C <= 16: the xyz/agl input graph), thread per query, exact FP32 scores, threshold-collect-
+ * select; same result as dgcnn_knn_f32 (rows that cannot be resolved in the fast path are redone by brute force).
+ * Needs C <= 16, k <= 48, N >= 512.                                                                       */
+int dgcnn_knn_small_supported(int C, int N, int k);
+size_t dgcnn_knn_small_workspace_bytes(int B, int N);
+int dgcnn_knn_small_f32(const float* rows, int ld, int B, int C, int N, int k, int32_t* idx,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- get_graph_feature (model.py:43-83), materialising form kept for API parity -------------------
  * out[B,N,k,2C] = cat(x_j - x_i, x_i); the reference returns permute(0,3,1,2) of this buffer.        */
 int dgcnn_graph_feature_f32(const float* rows, int ld, const int32_t* idx, int B, int C, int N, int k,

@@ -102,3 +102,22 @@ def test_knn_tc_on_model_features(pkg):
     tcv = pkg.ops.knn_rows(rows, B, 64, N, k, method="tc").view(B, N, k).cpu().long()
     rep = O.compare_neighbour_sets(x1, ora.trace["idx2"], tcv, tol_ulps=4.0)
     assert rep["hard"] == 0 and rep["identical"] >= 0.99 * rep["rows"], rep
+
+
+# ---------------------------------------------------------------------------------------------- low-dimensional kNN
+@pytest.mark.parametrize("B,C,N,k,kind", [(2, 4, 7000, 30, "real"), (1, 4, 3000, 20, "dup"), (3, 4, 513, 48, "unit"),
+                                          (1, 3, 2000, 16, "unit"), (1, 9, 1500, 33, "unit"), (1, 16, 1024, 5, "randn"),
+                                          (1, 4, 32768, 30, "real")])
+def test_knn_small_equals_exact_kernel(pkg, B, C, N, k, kind):
+    x = common.points(3000 + N + C, B, C, N, kind)
+    rows = pkg.ops.pack_rows(x.to(DEV))
+    a = pkg.ops.knn_rows(rows, B, C, N, k, method="exact")
+    b = pkg.ops.knn_rows(rows, B, C, N, k, method="small")
+    assert torch.equal(a, b)
+
+
+def test_knn_small_many_duplicates(pkg):
+    x = common.points(78, 1, 4, 2000, "unit")
+    x[0, :, 100:400] = x[0, :, 5:6]                    # 300 identical points: > 64 exact ties -> brute-force fallback
+    rows = pkg.ops.pack_rows(x.to(DEV))
+    assert torch.equal(pkg.ops.knn_rows(rows, 1, 4, 2000, 30, method="exact"), pkg.ops.knn_rows(rows, 1, 4, 2000, 30, method="small"))
