@@ -466,51 +466,55 @@ knn_fallback_kernel(const float* __restrict__ rows, int ld, const float* __restr
 // No certificate is needed: every key above tau is a candidate, so the exact top-k is among them iff >= k were found.
 // ---------------------------------------------------------------------------------------------
 constexpr int kSmallKeys = 512;        // keys per shared-memory tile
-constexpr int kSmallCap = 256;         // candidate slots per query row (global memory)
+constexpr int kSmallRows = 64;         // query rows per CTA; 4 threads per row, each scanning a quarter of every key tile
 
 template <int CP>
 __global__ void __launch_bounds__(kThreads)
-knn_small_kernel(const float* __restrict__ rows, int ld, const float* __restrict__ norms, int N, int k, int n_sample,
-                 unsigned long long* __restrict__ cand, int32_t* __restrict__ idx, int* __restrict__ fb_count,
-                 int* __restrict__ fb_rows) {
+knn_small_kernel(const float* __restrict__ rows, int ld, const float* __restrict__ norms, int N, int C4, int k,
+                 int n_sample, unsigned long long* __restrict__ cand, int32_t* __restrict__ idx,
+                 int* __restrict__ fb_count, int* __restrict__ fb_rows) {
   __shared__ __align__(16) float Ks[kSmallKeys * CP];
   __shared__ float Kn[kSmallKeys];
-  __shared__ int cntS[kThreads];
-  __shared__ float tauS[kThreads];
+  __shared__ __align__(16) int cntS[kSmallRows * 4];
+  __shared__ __align__(16) float tau4[kSmallRows * 4];
   __shared__ unsigned long long stageS[8][kSurvivors];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.y, q0 = blockIdx.x * kThreads, q = q0 + tid;
+  const int row = tid & (kSmallRows - 1), kq = tid >> 6;          // a warp = 32 rows of one key quarter
+  const int b = blockIdx.y, q0 = blockIdx.x * kSmallRows, q = q0 + row;
   const size_t base = static_cast<size_t>(b) * N;
   const bool row_ok = q < N;
   float xq[CP];
 #pragma unroll
   for (int c = 0; c < CP; c += 4) {
-    const float4 v = row_ok ? *reinterpret_cast<const float4*>(rows + (base + q) * ld + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 v = (row_ok && c < C4) ? *reinterpret_cast<const float4*>(rows + (base + q) * ld + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     xq[c] = v.x; xq[c + 1] = v.y; xq[c + 2] = v.z; xq[c + 3] = v.w;
   }
   const float nq = row_ok ? norms[base + q] : 0.f;
-  unsigned long long* mycand = cand + (base + q) * kSmallCap;
+  unsigned long long* mycand = cand + ((base + q) * 4 + kq) * kSubCands;
 
   float top[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) top[i] = -INFINITY;
   float tau = -INFINITY;
   int n = 0;
-  // pass 0: the first n_sample keys give tau (8th best of the sample ~ global rank 8 N / n_sample); pass 1: all keys
+  // pass 0: the first n_sample keys give tau (each thread's 8th best of its quarter ~ global rank 32 N / n_sample, the
+  // four estimates are averaged); pass 1: all keys, every key above tau becomes a candidate
   for (int pass = 0; pass < 2; ++pass) {
     const int nkeys = pass == 0 ? n_sample : N;
     for (int t0 = 0; t0 < nkeys; t0 += kSmallKeys) {
       __syncthreads();
       for (int i = tid; i < kSmallKeys * (CP / 4); i += kThreads) {
         const int r = i / (CP / 4), c4 = i % (CP / 4), j = t0 + r;
-        *reinterpret_cast<float4*>(Ks + r * CP + 4 * c4) =
-            j < nkeys ? *reinterpret_cast<const float4*>(rows + (base + j) * ld + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(Ks + r * CP + 4 * c4) = (j < nkeys && 4 * c4 < C4)
+            ? *reinterpret_cast<const float4*>(rows + (base + j) * ld + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       for (int r = tid; r < kSmallKeys; r += kThreads) Kn[r] = t0 + r < nkeys ? norms[base + t0 + r] : 0.f;
       __syncthreads();
-      const int lim = min(kSmallKeys, nkeys - t0);
+      const int r0 = kq * (kSmallKeys / 4);
+      const int lim = min(kSmallKeys / 4, nkeys - t0 - r0);
 #pragma unroll 4
-      for (int r = 0; r < lim; ++r) {
+      for (int i = 0; i < lim; ++i) {
+        const int r = r0 + i;
         float d = 0.f;
 #pragma unroll
         for (int c = 0; c < CP; c += 4) {
@@ -524,37 +528,45 @@ knn_small_kernel(const float* __restrict__ rows, int ld, const float* __restrict
         if (pass == 0) {
           if (pd > top[7]) top8_insert(top, pd);
         } else if (pd > tau && row_ok) {
-          if (n < kSmallCap) mycand[n] = make_key(pd, t0 + r);
+          if (n < kSubCands) mycand[n] = make_key(pd, t0 + r);
           ++n;
         }
       }
     }
-    if (pass == 0) tau = top[7];          // -inf when fewer than 8 keys were sampled: keep everything
+    if (pass == 0) {
+      tau4[row * 4 + kq] = top[7];
+      __syncthreads();
+      const float4 t4 = *reinterpret_cast<const float4*>(tau4 + row * 4);
+      tau = 0.25f * (t4.x + t4.y + t4.z + t4.w);        // -inf when a thread saw fewer than 8 keys: keep everything
+    }
   }
-  cntS[tid] = n;
-  tauS[tid] = tau;
+  cntS[row * 4 + kq] = n;
   __threadfence_block();
   __syncthreads();
 
-  // selection: warp per query row (32 rows per warp)
+  // selection: warp per query row (8 rows per warp); scores are exact, so the top-k of the candidates is the answer
+  // iff at least k candidates exist
   unsigned long long* stg = stageS[warp];
-  for (int rr = 0; rr < 32; ++rr) {
-    const int row = warp * 32 + rr, qq = q0 + row;
+  for (int rr = 0; rr < kSmallRows / 8; ++rr) {
+    const int srow = warp * (kSmallRows / 8) + rr, qq = q0 + srow;
     if (qq >= N) break;
     const size_t g = base + qq;
-    const int nc = cntS[row];
-    bool bad = nc > kSmallCap || nc < k;
-    const int ntot = min(nc, kSmallCap);
-    const unsigned long long* rc = cand + g * kSmallCap;
+    const int4 c4 = *reinterpret_cast<const int4*>(cntS + srow * 4);
+    bool bad = max(max(c4.x, c4.y), max(c4.z, c4.w)) > kSubCands;
+    const int cs[4] = {min(c4.x, kSubCands), min(c4.y, kSubCands), min(c4.z, kSubCands), min(c4.w, kSubCands)};
+    const int ntot = cs[0] + cs[1] + cs[2] + cs[3];
+    bad = bad || ntot < k;
+    const unsigned long long* rc = cand + g * 4 * kSubCands;
     unsigned long long key[8];
     float ap[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      const int slot = r * 32 + lane;
-      key[r] = slot < ntot ? rc[slot] : 0ull;
+      const int sub = r >> 1, slot = (r & 1) * 32 + lane;
+      key[r] = slot < cs[sub] ? rc[sub * kSubCands + slot] : 0ull;
       ap[r] = key[r] != 0ull ? sel::key_score(key[r]) : -INFINITY;
     }
-    float lo = tauS[row], hi = ap[0];
+    const float4 t4 = *reinterpret_cast<const float4*>(tau4 + srow * 4);
+    float lo = 0.25f * (t4.x + t4.y + t4.z + t4.w), hi = ap[0];
 #pragma unroll
     for (int r = 1; r < 8; ++r) hi = fmaxf(hi, ap[r]);
 #pragma unroll
@@ -607,10 +619,10 @@ knn_small_kernel(const float* __restrict__ rows, int ld, const float* __restrict
 }
 
 template <int CP>
-static int launch_knn_small(const float* rows, int ld, const float* norms, int B, int N, int k, int n_sample,
+static int launch_knn_small(const float* rows, int ld, const float* norms, int B, int N, int C4, int k, int n_sample,
                             unsigned long long* cand, int32_t* idx, int* fb_count, int* fb_rows, cudaStream_t st) {
-  knn_small_kernel<CP><<<dim3((N + kThreads - 1) / kThreads, B), kThreads, 0, st>>>(rows, ld, norms, N, k, n_sample, cand, idx,
-                                                                                   fb_count, fb_rows);
+  knn_small_kernel<CP><<<dim3((N + kSmallRows - 1) / kSmallRows, B), kThreads, 0, st>>>(rows, ld, norms, N, C4, k, n_sample, cand,
+                                                                                       idx, fb_count, fb_rows);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
 }
@@ -691,7 +703,7 @@ static size_t knn_small_layout(int B, int N, size_t* o_norms, size_t* o_cnt, siz
   *o_norms = take(static_cast<size_t>(B) * N * 4);
   *o_cnt = take(4);
   *o_rows = take(static_cast<size_t>(B) * N * 4);
-  *o_cand = take((static_cast<size_t>(B) * N + kThreads) * kSmallCap * 8);
+  *o_cand = take((static_cast<size_t>(B) * N + kSmallRows) * 4 * kSubCands * 8);
   return off + 1024;
 }
 
@@ -726,13 +738,13 @@ extern "C" int dgcnn_knn_small_f32(const float* rows, int ld, int B, int C, int 
   // norms in torch.sum's order (rows beyond C are zero padded, so the padded chain is exact as well)
   knn_norms_max_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(rows, ld, N, C, norms, reinterpret_cast<unsigned int*>(ws + o_rows));
   DG_CUDA(cudaGetLastError());
-  // sample size: the 8th best of n_sample keys has expected global rank 8 N / n_sample; aim at max(100, 3k)
+  // sample size: a thread's 8th best of its n_sample/4 keys has expected global rank 32 N / n_sample; aim at max(100, 3k)
   const int target = std::max(100, 3 * k);
-  const int n_sample = std::max(64, std::min(N, static_cast<int>(8LL * N / target)));
+  const int n_sample = std::max(256, std::min(N, static_cast<int>(32LL * N / target)));
   int rc;
-  if (C4 <= 4) rc = launch_knn_small<4>(rows, ld, norms, B, N, k, n_sample, cand, idx, fb_count, fb_rows, st);
-  else if (C4 <= 8) rc = launch_knn_small<8>(rows, ld, norms, B, N, k, n_sample, cand, idx, fb_count, fb_rows, st);
-  else rc = launch_knn_small<16>(rows, ld, norms, B, N, k, n_sample, cand, idx, fb_count, fb_rows, st);
+  if (C4 <= 4) rc = launch_knn_small<4>(rows, ld, norms, B, N, C4, k, n_sample, cand, idx, fb_count, fb_rows, st);
+  else if (C4 <= 8) rc = launch_knn_small<8>(rows, ld, norms, B, N, C4, k, n_sample, cand, idx, fb_count, fb_rows, st);
+  else rc = launch_knn_small<16>(rows, ld, norms, B, N, C4, k, n_sample, cand, idx, fb_count, fb_rows, st);
   if (rc) return rc;
   knn_fallback_kernel<<<64, kThreads, 0, st>>>(rows, ld, norms, N, C4, k, idx, fb_count, fb_rows);
   DG_CUDA(cudaGetLastError());
