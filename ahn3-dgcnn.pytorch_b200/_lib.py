@@ -40,6 +40,7 @@ SIGNATURES = {
     "dgcnn_edgeconv_conv_b_train": (c_int, [_ARGS, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dgcnn_bn_finalize": (c_int, [_P, c_int, c_double, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P]),
     "dgcnn_edgeconv_select": (c_int, [c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
+    "dgcnn_set_edgeconv_tc": (c_int, [c_int]),
     "dgcnn_edgeconv_bwd_prep": (c_int, [c_int, _P, c_int, _P, _P, _P, _P, _P]),
     "dgcnn_bn_bwd_reduce": (c_int, [_P, c_int, c_double, _P, _P, _P, _P, _P, _P, _P]),
     "dgcnn_edgeconv_dw_partials_bytes": (c_size_t, []),

@@ -6,30 +6,9 @@
 // Inference is a single kernel (gather -> conv_a -> BN -> LReLU -> conv_b -> BN -> LReLU -> max_k).
 // Training needs batch statistics before normalising, so the block is split at the BN boundaries; the
 // per-edge pre-BN conv_a output y_a is the only per-edge tensor that touches HBM (kept for backward).
-#include "common.cuh"
+#include "edgeconv.cuh"
 
 namespace dg {
-
-constexpr int kLdH = kCout + 4;          // smem row stride of 64-wide tiles
-constexpr int kMaxP = 16;                // points per tile cap (sizes the per-point smem arrays)
-
-enum { MODE_EVAL = 0, MODE_TRAIN_A = 1, MODE_TRAIN_B = 2 };
-
-struct EcK {
-  const float* rows; int ld;
-  const int32_t* idx;
-  int N, k, M, C, C4, P, num_tiles;
-  const float* w_a; const float* w_b; int two;
-  float* out; int ld_out;
-  const float* aff_a; const float* aff_b;     // float[192]: mean | scale | beta
-  float* y_a_out; const float* y_a_in;
-  double* partials;
-  float* ymax; float* ymin; uint8_t* amax; uint8_t* amin;
-};
-
-__device__ __forceinline__ float bn_apply(float y, float mean, float scale, float beta) {
-  return __fmaf_rn(y - mean, scale, beta);
-}
 
 // Per-CTA column statistics -> partials (double).  t1/t2 are per-thread partial sums for columns tx+16q.
 __device__ __forceinline__ void flush_stats(const float (&t1)[4], const float (&t2)[4], float* scratch,
@@ -666,6 +645,8 @@ extern "C" int dgcnn_edgeconv_conv_a_train(const dgcnn_edgeconv_args* a, float* 
              "edgeconv_conv_a_train: single-conv block needs the extrema outputs");
   p.y_a_out = y_a; p.partials = partials;
   p.ymax = ymax; p.ymin = ymin; p.amax = amax; p.amin = amin;
+  if (p.C == 64 && edgeconv_tc_enabled())
+    return launch_ec_tc_fwd(p, MODE_TRAIN_A, persistent_grid(p.num_tiles), static_cast<cudaStream_t>(stream));
   return dispatch_cp<MODE_TRAIN_A>(p, static_cast<cudaStream_t>(stream));
 }
 
@@ -679,6 +660,8 @@ extern "C" int dgcnn_edgeconv_conv_b_train(const dgcnn_edgeconv_args* a, const f
              "edgeconv_conv_b_train: null pointer");
   p.y_a_in = y_a; p.aff_a = aff_a; p.partials = partials;
   p.ymax = ymax; p.ymin = ymin; p.amax = amax; p.amin = amin;
+  if (edgeconv_tc_enabled())
+    return launch_ec_tc_fwd(p, MODE_TRAIN_B, persistent_grid(p.num_tiles), static_cast<cudaStream_t>(stream));
   return launch_fwd<64, MODE_TRAIN_B>(p, static_cast<cudaStream_t>(stream));
 }
 

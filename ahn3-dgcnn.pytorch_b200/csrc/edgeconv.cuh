@@ -1,0 +1,32 @@
+// edgeconv.cuh — declarations shared by the FP32-FMA (edgeconv.cu) and tensor-core (edgeconv_tc.cu) EdgeConv kernels.
+#pragma once
+#include "common.cuh"
+
+namespace dg {
+
+constexpr int kLdH = kCout + 4;          // smem row stride of 64-wide tiles
+constexpr int kMaxP = 16;                // points per tile cap (sizes the per-point smem arrays)
+
+enum { MODE_EVAL = 0, MODE_TRAIN_A = 1, MODE_TRAIN_B = 2 };
+
+struct EcK {
+  const float* rows; int ld;
+  const int32_t* idx;
+  int N, k, M, C, C4, P, num_tiles;
+  const float* w_a; const float* w_b; int two;
+  float* out; int ld_out;
+  const float* aff_a; const float* aff_b;     // float[192]: mean | scale | beta
+  float* y_a_out; const float* y_a_in;
+  double* partials;
+  float* ymax; float* ymin; uint8_t* amax; uint8_t* amin;
+};
+
+__device__ __forceinline__ float bn_apply(float y, float mean, float scale, float beta) {
+  return __fmaf_rn(y - mean, scale, beta);
+}
+
+// tensor-core training-forward kernels (edgeconv_tc.cu); mode = MODE_TRAIN_A (needs C == 64) or MODE_TRAIN_B
+int launch_ec_tc_fwd(const EcK& p, int mode, int grid, cudaStream_t st);
+bool edgeconv_tc_enabled();
+
+}  // namespace dg

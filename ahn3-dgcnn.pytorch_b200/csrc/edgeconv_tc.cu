@@ -1,0 +1,266 @@
+// edgeconv_tc.cu — EdgeConv training-forward passes on the 5th-gen tensor cores (C_in = 64 convolutions).
+//
+// Same tiles and outputs as edgeconv.cu (P*k <= 128 edge rows per tile, persistent CTAs, per-CTA statistics), but the
+// 128 x 64 x 64 tile GEMM is a tcgen05.mma with the accumulator in TMEM:
+//   * the A tile is produced in shared memory by the CTA itself (gathered x_j - x_i, or LReLU(BN(y_a))), split on the
+//     fly into three bf16 planes in the SWIZZLE_128B K-major layout (fence.proxy.async hands it to the tensor core);
+//   * the 64 x 64 weight is split once per CTA;
+//   * six kind::f16 MMAs per k16 step (bf16x3 split, FP32-accurate, see tc.cuh) — 24 MMAs per tile;
+//   * the epilogue reads TMEM (tcgen05.ld), adds the hoisted centre term, and parks the FP32 tile in shared memory
+//     (aliasing the A planes) for the column statistics, the coalesced y_a store and the max/min over k.
+// Two CTAs per SM overlap one CTA's gather/epilogue with the other's MMA.
+#include "edgeconv.cuh"
+#include "tc.cuh"
+
+namespace dg {
+
+static int g_edgeconv_tc = 1;
+bool edgeconv_tc_enabled() { return g_edgeconv_tc != 0; }
+
+constexpr uint32_t kPlA = 128 * 128;   // bytes of one A plane (128 rows x 64 bf16)
+constexpr uint32_t kPlW = 64 * 128;    // bytes of one weight plane
+constexpr int kYs = 65;                // row stride of the FP32 tile parked over the A planes
+
+struct EcTcSmem {
+  static constexpr uint32_t a_off = 0;                       // 3 A planes, later the FP32 Y tile
+  static constexpr uint32_t w_off = 3 * kPlA;                // 3 weight planes
+  static constexpr uint32_t v_off = w_off + 3 * kPlW;        // Vs [16][64]
+  static constexpr uint32_t xi_off = v_off + kMaxP * 64 * 4; // xis [16][64]
+  static constexpr uint32_t w2_off = xi_off + kMaxP * 64 * 4;   // Wa2 FP32 [64][68]
+  static constexpr uint32_t aff_off = w2_off + 64 * kLdH * 4;   // affine 192 floats
+  static constexpr uint32_t nbr_off = aff_off + 192 * 4;
+  static constexpr uint32_t red_off = nbr_off + 128 * 4;        // [2][4][64] floats for the final statistics flush
+  static constexpr uint32_t bar_off = red_off + 2 * 4 * 64 * 4;
+  static constexpr uint32_t bytes = bar_off + 64;
+};
+
+// 8 consecutive channels (chunk ch) of tile row r -> three bf16 planes, swizzled
+__device__ __forceinline__ void store_split3(unsigned char* planes, uint32_t plane_bytes, int r, int ch, float (&v)[8]) {
+  const uint32_t off = static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>((ch ^ (r & 7)) & 7) << 4);
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    __nv_bfloat16 h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      h[e] = __float2bfloat16_rn(v[e]);
+      v[e] -= __bfloat162float(h[e]);
+    }
+    *reinterpret_cast<uint4*>(planes + p * plane_bytes + off) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  unsigned char* Ap = sm + EcTcSmem::a_off;
+  float* Ys = reinterpret_cast<float*>(sm + EcTcSmem::a_off);
+  unsigned char* Wp = sm + EcTcSmem::w_off;
+  float* Vs = reinterpret_cast<float*>(sm + EcTcSmem::v_off);
+  float* xis = reinterpret_cast<float*>(sm + EcTcSmem::xi_off);
+  float* Wa2s = reinterpret_cast<float*>(sm + EcTcSmem::w2_off);
+  float* aff = reinterpret_cast<float*>(sm + EcTcSmem::aff_off);
+  int* nbr = reinterpret_cast<int*>(sm + EcTcSmem::nbr_off);
+  float* red = reinterpret_cast<float*>(sm + EcTcSmem::red_off);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + EcTcSmem::bar_off);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = p.k, P = p.P, M = p.M;
+
+  if (tid == 0) {
+    if (tc::smem_u32(sm) & 1023u) __trap();
+    tc::mbar_init(bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 64);
+  // weights: B operand rows = output channel, K = input channel.  conv_a uses Wa1 = w_a[:, 0:64]; conv_b uses w_b.
+  {
+    const float* W = MODE == MODE_TRAIN_A ? p.w_a : p.w_b;
+    const int ldw = MODE == MODE_TRAIN_A ? 128 : 64;
+    for (int i = tid; i < 64 * 8; i += kThreads) {
+      const int o = i >> 3, ch = i & 7;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = W[static_cast<size_t>(o) * ldw + ch * 8 + e];
+      store_split3(Wp, kPlW, o, ch, v);
+    }
+    if (MODE == MODE_TRAIN_A)
+      for (int i = tid; i < 64 * 64; i += kThreads) Wa2s[(i >> 6) * kLdH + (i & 63)] = p.w_a[static_cast<size_t>(i >> 6) * 128 + 64 + (i & 63)];
+    if (tid < 192) aff[tid] = p.aff_a ? p.aff_a[tid] : 0.f;
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t taddr = *tmem_slot;
+  constexpr uint32_t idesc = tc::idesc_bf16(128, 64);
+  uint32_t phase = 0;
+
+  // epilogue mapping: warp -> TMEM lane quarter (warp & 3) and column half (warp >> 2); thread = one tile row
+  const int quarter = warp & 3, half = warp >> 2;
+  const int erow = quarter * 32 + lane;
+  const int erp = min(erow / k, kMaxP - 1);
+  // statistics mapping: thread -> column (tid & 63), row group (tid >> 6) of 32 rows
+  const int sc = tid & 63, sg = tid >> 6;
+  float t1 = 0.f, t2 = 0.f;
+
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const int gp0 = tile * P;
+    const size_t e0 = static_cast<size_t>(gp0) * k;
+    const int nvalid = min(P, M - gp0) * k;
+    __syncthreads();  // S0: previous tile's Y tile / Vs / nbr fully consumed
+    if (MODE == MODE_TRAIN_A) {
+      if (tid < kTileRows) {
+        const int pp = tid / k, slot = tid - pp * k, gp = gp0 + pp;
+        nbr[tid] = (pp < P && gp < M) ? (gp / p.N) * p.N + p.idx[static_cast<size_t>(gp) * k + slot] : -1;
+      }
+      for (int i = tid; i < P * 16; i += kThreads) {
+        const int pp = i >> 4, c4 = i & 15, gp = gp0 + pp;
+        *reinterpret_cast<float4*>(xis + pp * 64 + 4 * c4) =
+            gp < M ? *reinterpret_cast<const float4*>(p.rows + static_cast<size_t>(gp) * p.ld + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncthreads();  // S1
+    }
+    // ---- produce the A planes -----------------------------------------------------------------------------------
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int i = tid + it * kThreads, row = i >> 3, ch = i & 7;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      if (MODE == MODE_TRAIN_A) {
+        const int j = nbr[row];
+        if (j >= 0) {
+          const float* src = p.rows + static_cast<size_t>(j) * p.ld + ch * 8;
+          const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+          const float* xi = xis + (row / k) * 64 + ch * 8;
+          const float4 c = *reinterpret_cast<const float4*>(xi), d = *reinterpret_cast<const float4*>(xi + 4);
+          v[0] = a.x - c.x; v[1] = a.y - c.y; v[2] = a.z - c.z; v[3] = a.w - c.w;       // x_j - x_i (model.py:81)
+          v[4] = b.x - d.x; v[5] = b.y - d.y; v[6] = b.z - d.z; v[7] = b.w - d.w;
+        }
+      } else if (row < nvalid) {
+        const float* src = p.y_a_in + (e0 + row) * kCout + ch * 8;
+        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+        const float y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = ch * 8 + e;
+          v[e] = lrelu(bn_apply(y[e], aff[c], aff[64 + c], aff[128 + c]));               // h = LReLU(BN_a(y_a))
+        }
+      }
+      store_split3(Ap, kPlA, row, ch, v);
+    }
+    if (MODE == MODE_TRAIN_A) {
+      // hoisted centre term V[p] = Wa2 x_i
+      for (int i = tid; i < P * kCout; i += kThreads) {
+        const int pp = i >> 6, o = i & 63;
+        float a = 0.f;
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) {
+          const float4 w = *reinterpret_cast<const float4*>(Wa2s + o * kLdH + 4 * c4);
+          const float4 x = *reinterpret_cast<const float4*>(xis + pp * 64 + 4 * c4);
+          a = __fmaf_rn(w.x, x.x, a);
+          a = __fmaf_rn(w.y, x.y, a);
+          a = __fmaf_rn(w.z, x.z, a);
+          a = __fmaf_rn(w.w, x.w, a);
+        }
+        Vs[i] = a;
+      }
+    }
+    tc::fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core
+    __syncthreads();                   // S2
+    if (tid == 0) {
+      tc::fence_after_sync();
+      tc::mma_split_katom<3>(taddr, tc::smem_u32(Ap), kPlA, tc::smem_u32(Wp), kPlW, idesc, true);
+      tc::mma_commit(bar);
+    }
+    __syncwarp();
+    tc::mbar_wait(bar, phase);
+    phase ^= 1;
+    tc::fence_after_sync();
+    // ---- epilogue: TMEM -> FP32 tile in smem (over the A planes, which the MMA has finished reading) ------------
+    {
+      float v[32];
+      tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + half * 32, v);
+      float* dst = Ys + erow * kYs + half * 32;
+      if (MODE == MODE_TRAIN_A) {
+        const float* vr = Vs + erp * kCout + half * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dst[i] = v[i] + vr[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dst[i] = v[i];
+      }
+    }
+    tc::fence_before_sync();
+    __syncthreads();                   // S3: Y tile complete
+    // ---- batch statistics of the raw conv output (valid rows only) ----------------------------------------------
+    {
+      const int r_lo = sg * 32, r_hi = min(r_lo + 32, nvalid);
+      for (int r = r_lo; r < r_hi; ++r) {
+        const float y = Ys[r * kYs + sc];
+        t1 += y;
+        t2 = __fmaf_rn(y, y, t2);
+      }
+    }
+    if (MODE == MODE_TRAIN_A) {
+      for (int i = tid; i < nvalid * 16; i += kThreads) {
+        const int row = i >> 4, c4 = i & 15;
+        const float* s = Ys + row * kYs + 4 * c4;
+        *reinterpret_cast<float4*>(p.y_a_out + (e0 + row) * kCout + 4 * c4) = make_float4(s[0], s[1], s[2], s[3]);
+      }
+    }
+    if (MODE == MODE_TRAIN_B || !p.two) {
+      for (int i = tid; i < P * kCout; i += kThreads) {
+        const int pp = i >> 6, c = i & 63, gp = gp0 + pp;
+        if (gp < M) {
+          float mx = Ys[(pp * k) * kYs + c], mn = mx;
+          int ax = 0, an = 0;
+          for (int s = 1; s < k; ++s) {
+            const float v = Ys[(pp * k + s) * kYs + c];
+            if (v > mx) { mx = v; ax = s; }
+            if (v < mn) { mn = v; an = s; }
+          }
+          const size_t o = static_cast<size_t>(gp) * kCout + c;
+          p.ymax[o] = mx; p.ymin[o] = mn;
+          p.amax[o] = static_cast<uint8_t>(ax); p.amin[o] = static_cast<uint8_t>(an);
+        }
+      }
+    }
+  }
+  // ---- per-CTA statistics -> partials ---------------------------------------------------------------------------------
+  __syncthreads();
+  red[(0 * 4 + sg) * 64 + sc] = t1;
+  red[(1 * 4 + sg) * 64 + sc] = t2;
+  __syncthreads();
+  if (tid < 128) {
+    const int w = tid >> 6, c = tid & 63;
+    const double s = ((static_cast<double>(red[(w * 4 + 0) * 64 + c]) + red[(w * 4 + 1) * 64 + c]) + red[(w * 4 + 2) * 64 + c]) +
+                     red[(w * 4 + 3) * 64 + c];
+    p.partials[128 + static_cast<size_t>(blockIdx.x) * 128 + tid] = s;
+  }
+  if (blockIdx.x == 0 && tid == 0) p.partials[0] = static_cast<double>(gridDim.x);
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(taddr, 64);
+}
+
+int launch_ec_tc_fwd(const EcK& p, int mode, int grid, cudaStream_t st) {
+  if (mode == MODE_TRAIN_A) {
+    DG_CUDA(cudaFuncSetAttribute(ec_tc_fwd_kernel<MODE_TRAIN_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcTcSmem::bytes)));
+    ec_tc_fwd_kernel<MODE_TRAIN_A><<<grid, kThreads, EcTcSmem::bytes, st>>>(p);
+  } else {
+    DG_CUDA(cudaFuncSetAttribute(ec_tc_fwd_kernel<MODE_TRAIN_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcTcSmem::bytes)));
+    ec_tc_fwd_kernel<MODE_TRAIN_B><<<grid, kThreads, EcTcSmem::bytes, st>>>(p);
+  }
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}
+
+}  // namespace dg
+
+extern "C" int dgcnn_set_edgeconv_tc(int enabled) {
+  const int old = dg::g_edgeconv_tc;
+  dg::g_edgeconv_tc = enabled;
+  return old;
+}

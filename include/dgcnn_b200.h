@@ -120,6 +120,10 @@ int dgcnn_bn_finalize(const double* partials, int C, double count, const float* 
 int dgcnn_edgeconv_select(int M, const float* ymax, const float* ymin, const uint8_t* amax, const uint8_t* amin,
                           const float* affine, float* out, int ld_out, float* ysel, uint8_t* arg, void* stream);
 
+/* Select the implementation of the 64-channel EdgeConv training passes: 1 (default) = tcgen05 tensor cores with the
+ * FP32-accurate bf16x3 split, 0 = FP32 FMA.  Returns the previous setting.  Process-wide; for A/B checks.   */
+int dgcnn_set_edgeconv_tc(int enabled);
+
 /* Training backward (dense because of batch-stat BN; SURVEY.md §7 hard part 3).  Sequence:
  *   bwd_prep -> bn_bwd_reduce(last BN) -> [bwd_b -> bn_bwd_reduce(BN a)] -> bwd_a
  * then dX = r*Wa1 + s*(Wa2-Wa1), dWa = [(r-s)^T X, s^T X] are small point-level GEMMs done by the host.  */

@@ -121,3 +121,34 @@ def test_knn_small_many_duplicates(pkg):
     x[0, :, 100:400] = x[0, :, 5:6]                    # 300 identical points: > 64 exact ties -> brute-force fallback
     rows = pkg.ops.pack_rows(x.to(DEV))
     assert torch.equal(pkg.ops.knn_rows(rows, 1, 4, 2000, 30, method="exact"), pkg.ops.knn_rows(rows, 1, 4, 2000, 30, method="small"))
+
+
+# ---------------------------------------------------------------------------------------------- tensor-core EdgeConv
+def test_edgeconv_tc_matches_ffma_path(pkg):
+    """Train-mode forward/backward with the tcgen05 EdgeConv passes vs the FP32-FMA passes (same graphs)."""
+    lib = pkg._lib.load()
+    B, Fd, N, k = 2, 4, 1003, 30
+    x = common.points(51, B, Fd, N, "real").to(DEV)
+    w = common.weights(52, 5, Fd, 1024)
+    outs = {}
+    for tcflag in (0, 1):
+        old = lib.dgcnn_set_edgeconv_tc(tcflag)
+        try:
+            net = pkg.DGCNN(5, Fd, k, dropout=0.0, cuda=True)
+            net.load_state_dict(w, strict=False)
+            net.train()
+            forced = outs.get("idx")
+            y = net(x, forced_idx=forced)
+            y.square().mean().backward()
+            outs.setdefault("idx", [i.view(B, N, k).long() for i in net.last_idx])
+            outs[tcflag] = (y.detach(), [p.grad.clone() for p in net.parameters()],
+                            [getattr(net, f"bn{i}").running_var.clone() for i in range(1, 6)])
+        finally:
+            lib.dgcnn_set_edgeconv_tc(old)
+    y0, g0, rv0 = outs[0]
+    y1, g1, rv1 = outs[1]
+    assert ((y0 - y1).abs().max() / y0.abs().max()).item() < 2e-5
+    for a, b in zip(rv0, rv1):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
+    for a, b in zip(g0, g1):
+        assert ((a - b).norm() / (a.norm() + 1e-30)).item() < 5e-3      # gradient noise floor, see test_gpu_parity
