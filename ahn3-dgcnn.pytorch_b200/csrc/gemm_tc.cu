@@ -291,3 +291,71 @@ extern "C" int dgcnn_tc_gemm_f32(const float* A, int64_t a_sr, int64_t a_sc, con
   if ((rc = launch_split<2>(B, b_sr, b_sc, N, K, Np, KA, Bp, st))) return rc;
   return launch_gemm<2, 128, 3>(Ap, Bp, D, ldd, M, N, KA, partials, st);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Descriptor lab (debug): D[128 x 64] = [X | Y]^T-contraction over the 128 tile rows using MN-major operand
+// descriptors on K-major-stored tiles: D[m][n] = sum_r S[r][m] * Y[r][n], S = X for m < 64, Y for m >= 64.
+// The descriptor fields are runtime parameters so that one run can scan the candidate encodings.
+// ---------------------------------------------------------------------------------------------
+namespace dg {
+__global__ void __launch_bounds__(128, 1)
+tc_mn_lab_kernel(const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ D, uint32_t lbo_a,
+                 uint32_t sbo_a, uint32_t lbo_b, uint32_t sbo_b, uint32_t kstep, int a_major, int b_major) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  unsigned char* Xs = sm;            // [128 rows][128 B] bf16, swizzled like every other tile
+  unsigned char* Ys = sm + 16384;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 32768);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_barrier_init(); }
+  if (warp == 0) tc::tmem_alloc(slot, 64);
+  for (int i = tid; i < 128 * 8; i += 128) {
+    const int r = i >> 3, ch = i & 7;
+    __nv_bfloat16 hx[8], hy[8];
+    for (int e = 0; e < 8; ++e) {
+      hx[e] = __float2bfloat16_rn(X[r * 64 + ch * 8 + e]);
+      hy[e] = __float2bfloat16_rn(Y[r * 64 + ch * 8 + e]);
+    }
+    const uint32_t off = r * 128 + (((ch ^ (r & 7)) & 7) << 4);
+    *reinterpret_cast<uint4*>(Xs + off) = *reinterpret_cast<const uint4*>(hx);
+    *reinterpret_cast<uint4*>(Ys + off) = *reinterpret_cast<const uint4*>(hy);
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t taddr = *slot;
+  if (tid == 0) {
+    const uint32_t idesc = tc::idesc_bf16(128, 64) | (static_cast<uint32_t>(a_major) << 15) | (static_cast<uint32_t>(b_major) << 16);
+    auto desc = [](uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+      const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16);
+      const uint32_t hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+      return (static_cast<uint64_t>(hi) << 32) | lo;
+    };
+    for (int k16 = 0; k16 < 8; ++k16)
+      tc::mma_bf16(taddr, desc(tc::smem_u32(Xs) + k16 * kstep, lbo_a, sbo_a), desc(tc::smem_u32(Ys) + k16 * kstep, lbo_b, sbo_b),
+                   idesc, k16 > 0);
+    tc::mma_commit(bar);
+  }
+  __syncwarp();
+  tc::mbar_wait(bar, 0);
+  tc::fence_after_sync();
+  for (int c0 = 0; c0 < 64; c0 += 32) {
+    float v[32];
+    tc::tmem_ld32(taddr + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+    for (int i = 0; i < 32; ++i) D[(warp * 32 + lane) * 64 + c0 + i] = v[i];
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(taddr, 64);
+}
+}  // namespace dg
+
+extern "C" int dgcnn_debug_mn_lab(const float* X, const float* Y, float* D, int lbo_a, int sbo_a, int lbo_b, int sbo_b,
+                                  int kstep, int a_major, int b_major, void* stream) {
+  DG_CUDA(cudaFuncSetAttribute(dg::tc_mn_lab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 64));
+  dg::tc_mn_lab_kernel<<<1, 128, 32768 + 64, static_cast<cudaStream_t>(stream)>>>(X, Y, D, lbo_a, sbo_a, lbo_b, sbo_b, kstep, a_major,
+                                                                               b_major);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}
