@@ -159,6 +159,10 @@ int dgcnn_tc_gemm_f32(const float* A, int64_t a_row_stride, int64_t a_col_stride
                       float* D, int ldd, int M, int N, int K, int nsplit,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* debug: exercises MN-major tcgen05 operand descriptors on one 128x64 tile pair (tests only) */
+int dgcnn_debug_mn_lab(const float* X, const float* Y, float* D, int lbo_a, int sbo_a, int lbo_b, int sbo_b,
+                       int kstep, int a_major, int b_major, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
