@@ -718,9 +718,15 @@ extern "C" int dgcnn_edgeconv_bwd_b(const dgcnn_edgeconv_args* a, const float* y
              "edgeconv_bwd_b: null pointer");
   p.y_a_in = y_a; p.aff_a = aff_a; p.partials = partials;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  DG_CUDA(cudaFuncSetAttribute(ec_bwd_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcBwdSmem::bytes)));
-  ec_bwd_b_kernel<<<persistent_grid(p.num_tiles), kThreads, EcBwdSmem::bytes, st>>>(p, g, arg, coef_b, dz_a, dw_partials);
-  DG_CUDA(cudaGetLastError());
+  if (edgeconv_tc_enabled()) {
+    // one CTA per SM (150 KB of operand planes each); every CTA gets at least one tile so that its dW partial is defined
+    const int grid = std::max(1, std::min(p.num_tiles, std::max(1, num_sms())));
+    if ((rc = launch_ec_tc_bwd_b(p, g, arg, coef_b, dz_a, dw_partials, grid, st))) return rc;
+  } else {
+    DG_CUDA(cudaFuncSetAttribute(ec_bwd_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcBwdSmem::bytes)));
+    ec_bwd_b_kernel<<<persistent_grid(p.num_tiles), kThreads, EcBwdSmem::bytes, st>>>(p, g, arg, coef_b, dz_a, dw_partials);
+    DG_CUDA(cudaGetLastError());
+  }
   dw_reduce_kernel<<<(kCout * kCout + 255) / 256, 256, 0, st>>>(dw_partials, partials, dw_b);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;

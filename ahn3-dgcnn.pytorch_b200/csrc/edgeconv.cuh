@@ -27,6 +27,8 @@ __device__ __forceinline__ float bn_apply(float y, float mean, float scale, floa
 
 // tensor-core training-forward kernels (edgeconv_tc.cu); mode = MODE_TRAIN_A (needs C == 64) or MODE_TRAIN_B
 int launch_ec_tc_fwd(const EcK& p, int mode, int grid, cudaStream_t st);
+int launch_ec_tc_bwd_b(const EcK& p, const float* g, const uint8_t* arg, const float* coef_b, float* dz_a,
+                       float* dw_partials, int grid, cudaStream_t st);
 bool edgeconv_tc_enabled();
 
 }  // namespace dg

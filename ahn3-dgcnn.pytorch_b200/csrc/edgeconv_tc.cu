@@ -245,6 +245,275 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
   if (warp == 0) tc::tmem_dealloc(taddr, 64);
 }
 
+// ---------------------------------------------------------------------------------------------
+// backward edge pass through conv_b on the tensor cores (same contract as ec_bwd_b_kernel in edgeconv.cu)
+//   MMA1  y_b  = H W_b^T            K-major, bf16x3 (recomputed pre-BN output, needed by the dense BN backward)
+//   MMA3  dh   = DY W_b             K-major, bf16x2 (gradient path: 2^-17 relative is far below the 1e-3 noise floor)
+//   MMA2  dW_b += DY^T H            MN-major views of the same tiles (contraction over the 128 tile rows), bf16x2;
+//                                   A = [DY ; H] stacked to M = 128 through the descriptor's leading-dimension offset,
+//                                   accumulated in TMEM across all tiles of the CTA
+// ---------------------------------------------------------------------------------------------
+struct EcTcBwdSmem {
+  static constexpr uint32_t dy_off = 0;                         // DY planes (2 used), 3 planes reserved
+  static constexpr uint32_t h_off = 3 * kPlA;                   // H planes (3)
+  static constexpr uint32_t w_off = h_off + 3 * kPlA;           // W_b planes (3): rows = c (out), K = c'' (in)
+  static constexpr uint32_t wt_off = w_off + 3 * kPlW;          // W_b^T planes (2): rows = c'', K = c
+  static constexpr uint32_t g_off = wt_off + 2 * kPlW;          // gs [16][64]
+  static constexpr uint32_t aff_off = g_off + kMaxP * 64 * 4;   // affine of BN_a (192) + coefficients of BN_b (192)
+  static constexpr uint32_t arg_off = aff_off + 2 * 192 * 4;    // args [16][64] u8
+  static constexpr uint32_t red_off = arg_off + kMaxP * 64;     // [2][4][64] floats
+  static constexpr uint32_t bar_off = red_off + 2 * 4 * 64 * 4;
+  static constexpr uint32_t bytes = bar_off + 64;
+};
+
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t saddr, uint32_t lbo) {
+  const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16);
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// column sums over the 32 lanes of a warp for 32 per-lane values: afterwards v[0] of lane l is the sum of column l
+__device__ __forceinline__ void warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __restrict__ arg,
+                   const float* __restrict__ coef_b, float* __restrict__ dz_a, float* __restrict__ dw_partials) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  unsigned char* DYp = sm + EcTcBwdSmem::dy_off;
+  unsigned char* Hp = sm + EcTcBwdSmem::h_off;
+  unsigned char* Wp = sm + EcTcBwdSmem::w_off;
+  unsigned char* WTp = sm + EcTcBwdSmem::wt_off;
+  float* gs = reinterpret_cast<float*>(sm + EcTcBwdSmem::g_off);
+  float* aff = reinterpret_cast<float*>(sm + EcTcBwdSmem::aff_off);
+  float* cb = aff + 192;
+  uint8_t* args = sm + EcTcBwdSmem::arg_off;
+  float* red = reinterpret_cast<float*>(sm + EcTcBwdSmem::red_off);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + EcTcBwdSmem::bar_off);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = p.k, P = p.P, M = p.M;
+
+  if (tid == 0) {
+    if (tc::smem_u32(sm) & 1023u) __trap();
+    tc::mbar_init(bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 128);     // columns 0-63: y_b / dh, columns 64-127: dW_b accumulator
+  for (int i = tid; i < 64 * 8; i += kThreads) {
+    const int o = i >> 3, ch = i & 7;
+    float v[8], vt[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = p.w_b[static_cast<size_t>(o) * 64 + ch * 8 + e];           // row o = out channel c, K = c''
+      vt[e] = p.w_b[static_cast<size_t>(ch * 8 + e) * 64 + o];          // row o = c'', K = c
+    }
+    store_split3(Wp, kPlW, o, ch, v);
+    // two planes of the transpose
+    const uint32_t off = static_cast<uint32_t>(o) * 128u + (static_cast<uint32_t>((ch ^ (o & 7)) & 7) << 4);
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
+      __nv_bfloat16 h[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        h[e] = __float2bfloat16_rn(vt[e]);
+        vt[e] -= __bfloat162float(h[e]);
+      }
+      *reinterpret_cast<uint4*>(WTp + pl * kPlW + off) = *reinterpret_cast<const uint4*>(h);
+    }
+  }
+  if (tid < 192) {
+    aff[tid] = p.aff_a[tid];
+    cb[tid] = coef_b[tid];
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t taddr = *tmem_slot;
+  constexpr uint32_t idesc_k = tc::idesc_bf16(128, 64);
+  constexpr uint32_t idesc_mn = tc::idesc_bf16(128, 64) | (1u << 15) | (1u << 16);
+  uint32_t phase = 0;
+  bool first_tile = true;
+
+  const int quarter = warp & 3, half = warp >> 2;
+  const int erow = quarter * 32 + lane;
+  const int erp = min(erow / k, kMaxP - 1), ers = erow - (erow / k) * k;
+  float t1 = 0.f, t2 = 0.f;     // sums of dz_a and dz_a*y_a for column half*32+lane over this warp's rows
+
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const int gp0 = tile * P;
+    const size_t e0 = static_cast<size_t>(gp0) * k;
+    const int nvalid = min(P, M - gp0) * k;
+    __syncthreads();  // S0
+    for (int i = tid; i < P * kCout; i += kThreads) {
+      const int gp = gp0 + (i >> 6);
+      const bool ok = gp < M;
+      gs[i] = ok ? g[static_cast<size_t>(gp) * kCout + (i & 63)] : 0.f;
+      args[i] = ok ? arg[static_cast<size_t>(gp) * kCout + (i & 63)] : 255;
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int i = tid + it * kThreads, row = i >> 3, ch = i & 7;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      if (row < nvalid) {
+        const float* src = p.y_a_in + (e0 + row) * kCout + ch * 8;
+        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+        const float y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = ch * 8 + e;
+          v[e] = lrelu(bn_apply(y[e], aff[c], aff[64 + c], aff[128 + c]));
+        }
+      }
+      store_split3(Hp, kPlA, row, ch, v);
+    }
+    tc::fence_proxy_async();
+    __syncthreads();  // S1
+    if (tid == 0) {
+      tc::fence_after_sync();
+      tc::mma_split_katom<3>(taddr, tc::smem_u32(Hp), kPlA, tc::smem_u32(Wp), kPlW, idesc_k, true);   // y_b
+      tc::mma_commit(bar);
+    }
+    __syncwarp();
+    tc::mbar_wait(bar, phase);
+    phase ^= 1;
+    tc::fence_after_sync();
+    // ---- epilogue 1: dy_b = cA dz - cB - cC y_b  -> two bf16 planes -----------------------------------------------
+    {
+      float v[32];
+      tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + half * 32, v);
+      const bool valid = erow < nvalid;
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        float d[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int col = half * 32 + c8 * 8 + e;
+          const float dz = (args[erp * kCout + col] == ers) ? gs[erp * kCout + col] : 0.f;
+          d[e] = valid ? cb[col] * dz - cb[64 + col] - cb[128 + col] * v[c8 * 8 + e] : 0.f;
+        }
+        const int ch = half * 4 + c8;
+        const uint32_t off = static_cast<uint32_t>(erow) * 128u + (static_cast<uint32_t>((ch ^ (erow & 7)) & 7) << 4);
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+          __nv_bfloat16 h[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            h[e] = __float2bfloat16_rn(d[e]);
+            d[e] -= __bfloat162float(h[e]);
+          }
+          *reinterpret_cast<uint4*>(DYp + pl * kPlA + off) = *reinterpret_cast<const uint4*>(h);
+        }
+      }
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();  // S2: DY planes complete, accumulator 0 drained
+    if (tid == 0) {
+      tc::fence_after_sync();
+      tc::mma_split_katom<2>(taddr, tc::smem_u32(DYp), kPlA, tc::smem_u32(WTp), kPlW, idesc_k, true);   // dh = DY W_b
+      // dW_b += DY^T H over the 128 tile rows: pairs (DY plane i, H plane j), i + j <= 3, smallest first
+      const uint32_t lbo = tc::smem_u32(Hp) - tc::smem_u32(DYp);
+      uint32_t acc = first_tile ? 0u : 1u;
+      const int pi[3] = {0, 1, 0}, pj[3] = {1, 0, 0};
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int k16 = 0; k16 < 8; ++k16) {
+          tc::mma_bf16(taddr + 64, smem_desc_mn(tc::smem_u32(DYp) + pi[q] * kPlA + k16 * 2048, lbo),
+                       smem_desc_mn(tc::smem_u32(Hp) + pj[q] * kPlA + k16 * 2048, 1024), idesc_mn, acc);
+          acc = 1u;
+        }
+      tc::mma_commit(bar);
+    }
+    first_tile = false;
+    __syncwarp();
+    tc::mbar_wait(bar, phase);
+    phase ^= 1;
+    tc::fence_after_sync();
+    // ---- epilogue 2: dz_a = dh * LReLU'(BN_a(y_a)); store; column sums of dz_a and dz_a*y_a ------------------------
+    {
+      float v[32], w[32];
+      tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + half * 32, v);
+      const bool valid = erow < nvalid;
+      if (valid) {
+        const float* src = p.y_a_in + (e0 + erow) * kCout + half * 32;
+        float* dst = dz_a + (e0 + erow) * kCout + half * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 y = *reinterpret_cast<const float4*>(src + i);
+          const float ya[4] = {y.x, y.y, y.z, y.w};
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = half * 32 + i + e;
+            const float z = bn_apply(ya[e], aff[col], aff[64 + col], aff[128 + col]);
+            o[e] = v[i + e] * (z > 0.f ? 1.f : kSlope);
+            v[i + e] = o[e];
+            w[i + e] = o[e] * ya[e];
+          }
+          *reinterpret_cast<float4*>(dst + i) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { v[i] = 0.f; w[i] = 0.f; }
+      }
+      warp_transpose_reduce(v, lane);
+      warp_transpose_reduce(w, lane);
+      t1 += v[0];
+      t2 += w[0];
+    }
+    tc::fence_before_sync();
+  }
+  // ---- dW_b partial of this CTA (TMEM lanes 0-63, columns 64-127) and the BN_a statistics -----------------------------
+  __syncthreads();
+  if (warp < 2 && !first_tile) {
+    float* dst = dw_partials + static_cast<size_t>(blockIdx.x) * kCout * kCout + static_cast<size_t>(warp * 32 + lane) * kCout;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      float v[32];
+      tc::tmem_ld32(taddr + (static_cast<uint32_t>(warp * 32) << 16) + 64 + c0, v);
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+  }
+  red[(0 * 4 + quarter) * 64 + half * 32 + lane] = t1;
+  red[(1 * 4 + quarter) * 64 + half * 32 + lane] = t2;
+  __syncthreads();
+  if (tid < 128) {
+    const int w = tid >> 6, c = tid & 63;
+    const double s = ((static_cast<double>(red[(w * 4 + 0) * 64 + c]) + red[(w * 4 + 1) * 64 + c]) + red[(w * 4 + 2) * 64 + c]) +
+                     red[(w * 4 + 3) * 64 + c];
+    p.partials[128 + static_cast<size_t>(blockIdx.x) * 128 + tid] = s;
+  }
+  if (blockIdx.x == 0 && tid == 0) p.partials[0] = static_cast<double>(gridDim.x);
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(taddr, 128);
+}
+
+int launch_ec_tc_bwd_b(const EcK& p, const float* g, const uint8_t* arg, const float* coef_b, float* dz_a,
+                       float* dw_partials, int grid, cudaStream_t st) {
+  DG_CUDA(cudaFuncSetAttribute(ec_tc_bwd_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcTcBwdSmem::bytes)));
+  ec_tc_bwd_b_kernel<<<grid, kThreads, EcTcBwdSmem::bytes, st>>>(p, g, arg, coef_b, dz_a, dw_partials);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}
+
 int launch_ec_tc_fwd(const EcK& p, int mode, int grid, cudaStream_t st) {
   if (mode == MODE_TRAIN_A) {
     DG_CUDA(cudaFuncSetAttribute(ec_tc_fwd_kernel<MODE_TRAIN_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcTcSmem::bytes)));

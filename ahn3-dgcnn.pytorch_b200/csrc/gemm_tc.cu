@@ -304,7 +304,7 @@ tc_mn_lab_kernel(const float* __restrict__ X, const float* __restrict__ Y, float
   extern __shared__ __align__(1024) unsigned char sm[];
   unsigned char* Xs = sm;            // [128 rows][128 B] bf16, swizzled like every other tile
   unsigned char* Ys = sm + 16384;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 32768);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 98304 - 64);   // operands may be addressed up to ~64 KB by bad encodings
   uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_barrier_init(); }
@@ -353,8 +353,8 @@ tc_mn_lab_kernel(const float* __restrict__ X, const float* __restrict__ Y, float
 
 extern "C" int dgcnn_debug_mn_lab(const float* X, const float* Y, float* D, int lbo_a, int sbo_a, int lbo_b, int sbo_b,
                                   int kstep, int a_major, int b_major, void* stream) {
-  DG_CUDA(cudaFuncSetAttribute(dg::tc_mn_lab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 64));
-  dg::tc_mn_lab_kernel<<<1, 128, 32768 + 64, static_cast<cudaStream_t>(stream)>>>(X, Y, D, lbo_a, sbo_a, lbo_b, sbo_b, kstep, a_major,
+  DG_CUDA(cudaFuncSetAttribute(dg::tc_mn_lab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+  dg::tc_mn_lab_kernel<<<1, 128, 98304, static_cast<cudaStream_t>(stream)>>>(X, Y, D, lbo_a, sbo_a, lbo_b, sbo_b, kstep, a_major,
                                                                                b_major);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
