@@ -525,7 +525,7 @@ __global__ void dw_reduce_kernel(const float* __restrict__ dw_partials, const do
 __global__ void __launch_bounds__(kThreads)
 ec_bwd_a_kernel(const EcK p, const float* __restrict__ dz_a, const float* __restrict__ g,
                 const uint8_t* __restrict__ arg, const float* __restrict__ coef_a, float* __restrict__ s_out,
-                float* __restrict__ r_out) {
+                float* __restrict__ r_out, int ld_rs) {
   const int c4 = threadIdx.x & 15, pl = threadIdx.x >> 4;
   const int c = 4 * c4;
   const float4 cA = *reinterpret_cast<const float4*>(coef_a + c);
@@ -560,9 +560,9 @@ ec_bwd_a_kernel(const EcK p, const float* __restrict__ dz_a, const float* __rest
       dy.w = cA.w * dz.w - cB.w - cC.w * y.w;
       s.x += dy.x; s.y += dy.y; s.z += dy.z; s.w += dy.w;
       const size_t j = base + p.idx[e];
-      atomicAdd(reinterpret_cast<float4*>(r_out + j * kCout + c), dy);
+      atomicAdd(reinterpret_cast<float4*>(r_out + j * ld_rs + c), dy);
     }
-    *reinterpret_cast<float4*>(s_out + static_cast<size_t>(gp) * kCout + c) = s;
+    *reinterpret_cast<float4*>(s_out + static_cast<size_t>(gp) * ld_rs + c) = s;
   }
 }
 
@@ -719,8 +719,8 @@ extern "C" int dgcnn_edgeconv_bwd_b(const dgcnn_edgeconv_args* a, const float* y
   p.y_a_in = y_a; p.aff_a = aff_a; p.partials = partials;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (edgeconv_tc_enabled()) {
-    // one CTA per SM (150 KB of operand planes each); every CTA gets at least one tile so that its dW partial is defined
-    const int grid = std::max(1, std::min(p.num_tiles, std::max(1, num_sms())));
+    // two CTAs per SM; every CTA gets at least one tile so that its dW partial is defined
+    const int grid = std::max(1, std::min(p.num_tiles, 2 * std::max(1, num_sms())));
     if ((rc = launch_ec_tc_bwd_b(p, g, arg, coef_b, dz_a, dw_partials, grid, st))) return rc;
   } else {
     DG_CUDA(cudaFuncSetAttribute(ec_bwd_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcBwdSmem::bytes)));
@@ -733,14 +733,16 @@ extern "C" int dgcnn_edgeconv_bwd_b(const dgcnn_edgeconv_args* a, const float* y
 }
 
 extern "C" int dgcnn_edgeconv_bwd_a(const dgcnn_edgeconv_args* a, const float* y_a, const float* dz_a, const float* g,
-                                    const uint8_t* arg, const float* coef_a, float* s, float* r, void* stream) {
+                                    const uint8_t* arg, const float* coef_a, float* s, float* r, int ld_rs, void* stream) {
   EcK p;
   int rc = fill_common(a, p, "edgeconv_bwd_a");
   if (rc) return rc;
   DG_REQUIRE(a->idx && y_a && coef_a && s && r && (dz_a || (g && arg)), DGCNN_E_INVALID, "edgeconv_bwd_a: null pointer");
+  DG_REQUIRE(ld_rs >= kCout && ld_rs % 4 == 0 && ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(r)) & 15) == 0,
+             DGCNN_E_INVALID, "edgeconv_bwd_a: s/r need 16-byte alignment and ld_rs %% 4 == 0, ld_rs >= 64");
   p.y_a_in = y_a;
   const int blocks = std::max(1, std::min((p.M + 15) / 16, 8 * 148));
-  ec_bwd_a_kernel<<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, dz_a, g, arg, coef_a, s, r);
+  ec_bwd_a_kernel<<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, dz_a, g, arg, coef_a, s, r, ld_rs);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
 }

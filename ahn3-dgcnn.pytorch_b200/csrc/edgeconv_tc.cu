@@ -34,19 +34,28 @@ struct EcTcSmem {
   static constexpr uint32_t bytes = bar_off + 64;
 };
 
-// 8 consecutive channels (chunk ch) of tile row r -> three bf16 planes, swizzled
-__device__ __forceinline__ void store_split3(unsigned char* planes, uint32_t plane_bytes, int r, int ch, float (&v)[8]) {
+// 8 consecutive channels (chunk ch) of tile row r -> NP bf16 planes (x = x1 + x2 (+ x3)), swizzled.
+// Packed conversions: one cvt.rn.bf16x2 per pair and plane; the residual is exact in FP32.
+template <int NP>
+__device__ __forceinline__ void store_split(unsigned char* planes, uint32_t plane_bytes, int r, int ch, float (&v)[8]) {
   const uint32_t off = static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>((ch ^ (r & 7)) & 7) << 4);
 #pragma unroll
-  for (int p = 0; p < 3; ++p) {
-    __nv_bfloat16 h[8];
+  for (int p = 0; p < NP; ++p) {
+    __nv_bfloat162 h[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      h[e] = __float2bfloat16_rn(v[e]);
-      v[e] -= __bfloat162float(h[e]);
+    for (int e = 0; e < 4; ++e) {
+      h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+      if (p + 1 < NP) {
+        const float2 f = __bfloat1622float2(h[e]);
+        v[2 * e] -= f.x;
+        v[2 * e + 1] -= f.y;
+      }
     }
     *reinterpret_cast<uint4*>(planes + p * plane_bytes + off) = *reinterpret_cast<const uint4*>(h);
   }
+}
+__device__ __forceinline__ void store_split3(unsigned char* planes, uint32_t plane_bytes, int r, int ch, float (&v)[8]) {
+  store_split<3>(planes, plane_bytes, r, ch, v);
 }
 
 template <int MODE>
@@ -247,17 +256,19 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
 
 // ---------------------------------------------------------------------------------------------
 // backward edge pass through conv_b on the tensor cores (same contract as ec_bwd_b_kernel in edgeconv.cu)
-//   MMA1  y_b  = H W_b^T            K-major, bf16x3 (recomputed pre-BN output, needed by the dense BN backward)
-//   MMA3  dh   = DY W_b             K-major, bf16x2 (gradient path: 2^-17 relative is far below the 1e-3 noise floor)
+//   MMA1  y_b  = H W_b^T            K-major (recomputed pre-BN output, needed by the dense BN backward)
+//   MMA3  dh   = DY W_b             K-major
+//   all three with the 2-plane bf16 split: this is the gradient path, 2^-17 relative error is far below its 1e-3 noise
+//   floor (tests/test_gpu_parity.py), and two planes per operand let two CTAs share an SM
 //   MMA2  dW_b += DY^T H            MN-major views of the same tiles (contraction over the 128 tile rows), bf16x2;
 //                                   A = [DY ; H] stacked to M = 128 through the descriptor's leading-dimension offset,
 //                                   accumulated in TMEM across all tiles of the CTA
 // ---------------------------------------------------------------------------------------------
 struct EcTcBwdSmem {
-  static constexpr uint32_t dy_off = 0;                         // DY planes (2 used), 3 planes reserved
-  static constexpr uint32_t h_off = 3 * kPlA;                   // H planes (3)
-  static constexpr uint32_t w_off = h_off + 3 * kPlA;           // W_b planes (3): rows = c (out), K = c'' (in)
-  static constexpr uint32_t wt_off = w_off + 3 * kPlW;          // W_b^T planes (2): rows = c'', K = c
+  static constexpr uint32_t dy_off = 0;                         // DY planes (2)
+  static constexpr uint32_t h_off = 2 * kPlA;                   // H planes (2)
+  static constexpr uint32_t w_off = h_off + 2 * kPlA;           // W_b planes (2): rows = c (out), K = c'' (in)
+  static constexpr uint32_t wt_off = w_off + 2 * kPlW;          // W_b^T planes (2): rows = c'', K = c
   static constexpr uint32_t g_off = wt_off + 2 * kPlW;          // gs [16][64]
   static constexpr uint32_t aff_off = g_off + kMaxP * 64 * 4;   // affine of BN_a (192) + coefficients of BN_b (192)
   static constexpr uint32_t arg_off = aff_off + 2 * 192 * 4;    // args [16][64] u8
@@ -286,7 +297,7 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&v)[32], int lane) 
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __restrict__ arg,
                    const float* __restrict__ coef_b, float* __restrict__ dz_a, float* __restrict__ dw_partials) {
   extern __shared__ __align__(1024) unsigned char sm[];
@@ -319,19 +330,8 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
       v[e] = p.w_b[static_cast<size_t>(o) * 64 + ch * 8 + e];           // row o = out channel c, K = c''
       vt[e] = p.w_b[static_cast<size_t>(ch * 8 + e) * 64 + o];          // row o = c'', K = c
     }
-    store_split3(Wp, kPlW, o, ch, v);
-    // two planes of the transpose
-    const uint32_t off = static_cast<uint32_t>(o) * 128u + (static_cast<uint32_t>((ch ^ (o & 7)) & 7) << 4);
-#pragma unroll
-    for (int pl = 0; pl < 2; ++pl) {
-      __nv_bfloat16 h[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        h[e] = __float2bfloat16_rn(vt[e]);
-        vt[e] -= __bfloat162float(h[e]);
-      }
-      *reinterpret_cast<uint4*>(WTp + pl * kPlW + off) = *reinterpret_cast<const uint4*>(h);
-    }
+    store_split<2>(Wp, kPlW, o, ch, v);
+    store_split<2>(WTp, kPlW, o, ch, vt);
   }
   if (tid < 192) {
     aff[tid] = p.aff_a[tid];
@@ -379,13 +379,13 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
           v[e] = lrelu(bn_apply(y[e], aff[c], aff[64 + c], aff[128 + c]));
         }
       }
-      store_split3(Hp, kPlA, row, ch, v);
+      store_split<2>(Hp, kPlA, row, ch, v);
     }
     tc::fence_proxy_async();
     __syncthreads();  // S1
     if (tid == 0) {
       tc::fence_after_sync();
-      tc::mma_split_katom<3>(taddr, tc::smem_u32(Hp), kPlA, tc::smem_u32(Wp), kPlW, idesc_k, true);   // y_b
+      tc::mma_split_katom<2>(taddr, tc::smem_u32(Hp), kPlA, tc::smem_u32(Wp), kPlW, idesc_k, true);   // y_b
       tc::mma_commit(bar);
     }
     __syncwarp();
@@ -406,18 +406,7 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
           const float dz = (args[erp * kCout + col] == ers) ? gs[erp * kCout + col] : 0.f;
           d[e] = valid ? cb[col] * dz - cb[64 + col] - cb[128 + col] * v[c8 * 8 + e] : 0.f;
         }
-        const int ch = half * 4 + c8;
-        const uint32_t off = static_cast<uint32_t>(erow) * 128u + (static_cast<uint32_t>((ch ^ (erow & 7)) & 7) << 4);
-#pragma unroll
-        for (int pl = 0; pl < 2; ++pl) {
-          __nv_bfloat16 h[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            h[e] = __float2bfloat16_rn(d[e]);
-            d[e] -= __bfloat162float(h[e]);
-          }
-          *reinterpret_cast<uint4*>(DYp + pl * kPlA + off) = *reinterpret_cast<const uint4*>(h);
-        }
+        store_split<2>(DYp, kPlA, erow, half * 4 + c8, d);
       }
     }
     tc::fence_proxy_async();

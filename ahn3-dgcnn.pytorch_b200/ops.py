@@ -342,19 +342,23 @@ class EdgeConvTrain(torch.autograd.Function):
                                                _ptr(dga[0]), _ptr(dga[1]), _ptr(coef_a), st)
         else:
             dz_a, coef_a, dga = None, coef_l, dgl
-        s = torch.empty(M, COUT, **f32)
-        r = torch.zeros(M, COUT, **f32)
+        rs = torch.zeros(M, 2 * COUT, **f32)            # [ r | s ]: scatter target and per-point sums, one GEMM operand
+        r, s = rs[:, :COUT], rs[:, COUT:]
         _call("dgcnn_edgeconv_bwd_a", C.byref(a), _ptr(y_a), _ptr(dz_a), _ptr(g), _ptr(arg), _ptr(coef_a),
-                                            _ptr(s), _ptr(r), st)
-        # point-level GEMMs (M x 64 x C): dX = r Wa1 + s (Wa2 - Wa1);  dWa = [(r - s)^T X | s^T X]
+              _ptr(s), _ptr(r), 2 * COUT, st)
+        # point-level GEMMs on the tensor cores (bf16x2 split: gradient path):
+        #   dX  = r Wa1 + s (Wa2 - Wa1)            = [r|s] @ [Wa1 ; Wa2-Wa1]
+        #   dWa = [(r - s)^T X | s^T X]            from G = [r|s]^T X  (contraction over the points, split-K)
         X = rows[:, :Cn]
         wa1, wa2 = wa[:, :Cn], wa[:, Cn:]
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = r @ wa1 + s @ (wa2 - wa1)
+            wcat = torch.cat((wa1, wa2 - wa1), dim=0)                   # [128, C]
+            dx = tc_gemm(rs, wcat.t(), nsplit=2) if Cn >= 16 else rs @ wcat
             if dx.shape != ctx.x_shape:
                 dx = dx.reshape(ctx.x_shape)
-        dwa = torch.cat(((r - s).t() @ X, s.t() @ X), dim=1)
+        G = tc_gemm(rs.t(), X.t(), nsplit=2)                            # [128, C]
+        dwa = torch.cat((G[:COUT] - G[COUT:], G[COUT:]), dim=1)
         # returns: x, idx, meta, w_a, gamma_a, beta_a, w_b, gamma_b, beta_b, bn_a, bn_b
         if two:
             return (dx, None, None, dwa.view(COUT, 2 * Cn, 1, 1), dga[0], dga[1], dw_b.view(COUT, COUT, 1, 1),

@@ -143,10 +143,11 @@ int dgcnn_edgeconv_bwd_b(const dgcnn_edgeconv_args* a, const float* y_a, const f
                          const float* g, const uint8_t* arg, const float* coef_b,
                          float* dz_a, float* dw_b, double* partials, float* dw_partials, void* stream);
 /* Edge pass through BN_a: dy_a = cA*dz_a - cB - cC*y_a; s[p,:] = sum_k dy_a; r[j,:] += dy_a (scatter).
- * dz_a == NULL selects the single-conv form (dz_a given implicitly by g/arg).  r must be zero-filled. */
+ * dz_a == NULL selects the single-conv form (dz_a given implicitly by g/arg).  r must be zero-filled.
+ * s and r are [B*N, 64] with row stride ld_rs (so they can be the two halves of one [B*N,128] GEMM operand). */
 int dgcnn_edgeconv_bwd_a(const dgcnn_edgeconv_args* a, const float* y_a, const float* dz_a,
                          const float* g, const uint8_t* arg, const float* coef_a,
-                         float* s, float* r, void* stream);
+                         float* s, float* r, int ld_rs, void* stream);
 
 /* ---- FP32-accurate tensor-core GEMM (tcgen05, bf16 split planes):  D[M,N] = A[M,K] * B[N,K]^T ---------------
  * A and B are FP32 with arbitrary element strides (row stride, column stride), so transposed operands need no
