@@ -89,6 +89,58 @@ __global__ void __launch_bounds__(256) split_planes_t_kernel(const float* __rest
 // GEMM kernel: one 128 x BN output tile per CTA, K streamed in 64-wide atoms through a STAGES-deep ring.
 // warp 0: bulk-copy producer | warp 1: TMEM owner + MMA issuer | warps 2-5: epilogue (one TMEM lane quarter each)
 // ---------------------------------------------------------------------------------------------
+// Epilogue variants.  EPI_STORE writes D.  EPI_COLSTATS never writes D: per row-tile it emits the column sums and
+// sums of squares (for batch-statistics BN) and, per segment of `seg_len` consecutive rows (= one point-cloud block),
+// the column maximum / minimum with the row where it is attained (64-bit atomicMax on (ordered value << 32 | row)).
+// With them  max_n LReLU(BN(y[n,c]))  is known without ever materialising y (conv6 + bn6 + global max, model.py:172-175).
+enum { EPI_STORE = 0, EPI_COLSTATS = 1 };
+struct GemmEpi {
+  int seg_len;
+  float* stat_partials;            // [row tiles][2][N]
+  unsigned long long* gmax;        // [segments][N]   (zero-initialised by the caller)
+  unsigned long long* gmin;        // [segments][N]   keys of -y
+};
+
+__device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
+__device__ __forceinline__ void warp_transpose_max(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, s));
+    }
+  }
+}
+// column-wise max over the lanes selected by `in_seg` and the lane attaining it; result for column l in lane l
+__device__ __forceinline__ void warp_col_argmax(const float (&v)[32], bool in_seg, int lane, float& best, int& best_lane) {
+  float t[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) t[i] = in_seg ? v[i] : -INFINITY;
+  warp_transpose_max(t, lane);
+  best = t[0];
+  best_lane = 0;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const float m = __shfl_sync(0xffffffffu, best, c);
+    const unsigned hit = __ballot_sync(0xffffffffu, in_seg && v[c] == m);
+    if (lane == c) best_lane = hit ? __ffs(hit) - 1 : 0;
+  }
+}
+
 template <int NS, int BN, int STAGES>
 struct GemmSmem {
   static constexpr uint32_t a_plane = 128 * 128;          // 128 rows x 128 B
@@ -97,10 +149,10 @@ struct GemmSmem {
   static constexpr uint32_t bytes = STAGES * stage + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-template <int NS, int BN, int STAGES>
+template <int NS, int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(192, 1)
 tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __restrict__ Bp, float* __restrict__ D,
-               int ldd, int M, int N, int KA, int ka_per_split, size_t split_stride) {
+               int ldd, int M, int N, int KA, int ka_per_split, size_t split_stride, GemmEpi epi) {
   using SM = GemmSmem<NS, BN, STAGES>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -108,6 +160,7 @@ tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __rest
   uint64_t* empty = full + STAGES;
   uint64_t* accfull = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
+  float* statS = reinterpret_cast<float*>(tiles);     // EPI_COLSTATS: [4 quarters][2][BN], reuses stage 0 after the last MMA
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = blockIdx.x, mt = blockIdx.y;
@@ -171,20 +224,76 @@ tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __rest
     tc::mbar_wait(accfull, 0);
     tc::fence_after_sync();
     const int row = mt * 128 + quarter * 32 + lane;
+    if (EPI == EPI_STORE) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
-      const int n0 = nt * BN + c0;
-      if (row < M) {
-        float* dst = D + static_cast<size_t>(row) * ldd + n0;
-        if (n0 + 32 <= N && (ldd & 3) == 0) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
+        const int n0 = nt * BN + c0;
+        if (row < M) {
+          float* dst = D + static_cast<size_t>(row) * ldd + n0;
+          if (n0 + 32 <= N && (ldd & 3) == 0) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        } else {
+            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (n0 + i < N) dst[i] = v[i];
+            for (int i = 0; i < 32; ++i)
+              if (n0 + i < N) dst[i] = v[i];
+          }
+        }
+      }
+    } else {
+      const bool rvalid = row < M;
+      const int seg = rvalid ? row / epi.seg_len : -1;
+      const unsigned vmask = __ballot_sync(0xffffffffu, rvalid);
+      const int seg_lo = __shfl_sync(0xffffffffu, seg, 0);
+      const int seg_hi = vmask ? __shfl_sync(0xffffffffu, seg, 31 - __clz(vmask)) : -1;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
+        const int col = nt * BN + c0 + lane;
+        {
+          float a[32], q[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            a[i] = rvalid ? v[i] : 0.f;
+            q[i] = a[i] * a[i];
+          }
+          warp_transpose_sum(a, lane);
+          warp_transpose_sum(q, lane);
+          statS[(quarter * 2 + 0) * BN + c0 + lane] = a[0];
+          statS[(quarter * 2 + 1) * BN + c0 + lane] = q[0];
+        }
+        if (vmask) {
+          for (int pass = 0; pass < 2; ++pass) {
+            const int sg = pass == 0 ? seg_lo : seg_hi;
+            if (pass == 1 && seg_hi == seg_lo) break;
+            const bool in_seg = rvalid && seg == sg;
+            float best; int bl;
+            warp_col_argmax(v, in_seg, lane, best, bl);
+            if (col < N && best > -INFINITY)
+              atomicMax(epi.gmax + static_cast<size_t>(sg) * N + col,
+                        (static_cast<unsigned long long>(ordered_bits(best)) << 32) | static_cast<uint32_t>(mt * 128 + quarter * 32 + bl));
+            float nv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) nv[i] = -v[i];
+            warp_col_argmax(nv, in_seg, lane, best, bl);
+            if (col < N && best > -INFINITY)
+              atomicMax(epi.gmin + static_cast<size_t>(sg) * N + col,
+                        (static_cast<unsigned long long>(ordered_bits(best)) << 32) | static_cast<uint32_t>(mt * 128 + quarter * 32 + bl));
+          }
+        }
+      }
+      // combine the four lane quarters in a fixed order: one partial per (row tile, column)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int t = threadIdx.x - 64;                      // 0..127 over the four epilogue warps
+      if (t < BN && nt * BN + t < N) {
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const float sum = ((statS[(0 * 2 + w) * BN + t] + statS[(1 * 2 + w) * BN + t]) + statS[(2 * 2 + w) * BN + t]) +
+                            statS[(3 * 2 + w) * BN + t];
+          epi.stat_partials[(static_cast<size_t>(mt) * 2 + w) * N + nt * BN + t] = sum;
         }
       }
     }
@@ -236,19 +345,19 @@ template <int NS, int BN, int STAGES>
 static int launch_gemm(const unsigned char* Ap, const unsigned char* Bp, float* D, int ldd, int M, int N, int KA,
                        float* partials, cudaStream_t st) {
   using SM = GemmSmem<NS, BN, STAGES>;
-  auto kern = tc_gemm_kernel<NS, BN, STAGES>;
+  auto kern = tc_gemm_kernel<NS, BN, STAGES, EPI_STORE>;
   DG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SM::bytes)));
   const int splits = splitk_factor(M, N, KA);
   dim3 grid((N + BN - 1) / BN, (M + 127) / 128, splits);
   if (splits == 1) {
-    kern<<<grid, 192, SM::bytes, st>>>(Ap, Bp, D, ldd, M, N, KA, KA, 0);
+    kern<<<grid, 192, SM::bytes, st>>>(Ap, Bp, D, ldd, M, N, KA, KA, 0, GemmEpi{});
     DG_CUDA(cudaGetLastError());
     return DGCNN_OK;
   }
   const int per = (KA + splits - 1) / splits;
   const size_t stride = static_cast<size_t>(M) * N;
   grid.z = (KA + per - 1) / per;
-  kern<<<grid, 192, SM::bytes, st>>>(Ap, Bp, partials, N, M, N, KA, per, stride);
+  kern<<<grid, 192, SM::bytes, st>>>(Ap, Bp, partials, N, M, N, KA, per, stride, GemmEpi{});
   DG_CUDA(cudaGetLastError());
   const size_t total = stride;
   splitk_reduce_kernel<<<static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 8)), 256, 0, st>>>(partials, stride, grid.z, D,
@@ -290,6 +399,105 @@ extern "C" int dgcnn_tc_gemm_f32(const float* A, int64_t a_sr, int64_t a_sc, con
   if ((rc = launch_split<2>(A, a_sr, a_sc, M, K, Mp, KA, Ap, st))) return rc;
   if ((rc = launch_split<2>(B, b_sr, b_sc, N, K, Np, KA, Bp, st))) return rc;
   return launch_gemm<2, 128, 3>(Ap, Bp, D, ldd, M, N, KA, partials, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM + batch statistics + per-block column extrema (conv6 + bn6 + LeakyReLU + max over the points), no D store
+// ---------------------------------------------------------------------------------------------
+namespace dg {
+// one thread per column: reduce the row-tile partials in FP64 (fixed order), BN scalars, then the per-block outputs
+__global__ void colstats_finalize_kernel(const float* __restrict__ stat_partials, int num_mt, int N, double count,
+                                         const unsigned long long* __restrict__ gmax, const unsigned long long* __restrict__ gmin,
+                                         int segments, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         float eps, float momentum, int use_batch_stats, float* running_mean,
+                                         float* running_var, float* mean_out, float* rstd_out, float* gout,
+                                         float* ysel, int* nstar) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  double m, rs;
+  if (use_batch_stats) {
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < num_mt; ++i) {
+      s += stat_partials[(static_cast<size_t>(i) * 2 + 0) * N + c];
+      q += stat_partials[(static_cast<size_t>(i) * 2 + 1) * N + c];
+    }
+    m = s / count;
+    double var = q / count - m * m;
+    if (var < 0.0) var = 0.0;
+    rs = 1.0 / sqrt(var + static_cast<double>(eps));
+    if (running_mean) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[c] = static_cast<float>((1.0 - momentum) * running_mean[c] + momentum * m);
+      running_var[c] = static_cast<float>((1.0 - momentum) * running_var[c] + momentum * unbiased);
+    }
+  } else {
+    m = running_mean[c];
+    rs = 1.0 / sqrt(static_cast<double>(running_var[c]) + static_cast<double>(eps));
+  }
+  mean_out[c] = static_cast<float>(m);
+  rstd_out[c] = static_cast<float>(rs);
+  const float mean = static_cast<float>(m), scale = static_cast<float>(static_cast<double>(gamma[c]) * rs), be = beta[c];
+  for (int b = 0; b < segments; ++b) {
+    const bool up = scale >= 0.f;          // BN affine increasing iff scale >= 0; LeakyReLU is increasing
+    const unsigned long long key = up ? gmax[static_cast<size_t>(b) * N + c] : gmin[static_cast<size_t>(b) * N + c];
+    const uint32_t u = static_cast<uint32_t>(key >> 32);
+    float y = __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+    if (!up) y = -y;
+    const float z = __fmaf_rn(y - mean, scale, be);
+    gout[static_cast<size_t>(b) * N + c] = z > 0.f ? z : kSlope * z;
+    ysel[static_cast<size_t>(b) * N + c] = y;
+    nstar[static_cast<size_t>(b) * N + c] = static_cast<int>(key & 0xFFFFFFFFull);
+  }
+}
+}  // namespace dg
+
+extern "C" size_t dgcnn_tc_gemm_colstats_workspace_bytes(int M, int N, int K, int segments) {
+  if (M <= 0 || N <= 0 || K <= 0 || segments <= 0) return 0;
+  const int KA = (K + 63) / 64;
+  const size_t planes = planes_bytes((M + 127) / 128 * 128, KA, 3) + planes_bytes((N + 127) / 128 * 128, KA, 3);
+  const size_t stats = static_cast<size_t>((M + 127) / 128) * 2 * N * sizeof(float);
+  const size_t ext = static_cast<size_t>(segments) * N * 8 * 2;
+  return planes + stats + ext + 8192;
+}
+
+// g[segments,N] = max over the rows of each segment of LeakyReLU(BN(A B^T)); BN with batch statistics over all M rows
+// (use_batch_stats = 1: training, running stats updated when given) or with the running statistics (0: inference).
+// Also returns mean/rstd [N] and, per (segment, column), the selected pre-BN value `ysel` and its row `nstar`.
+extern "C" int dgcnn_tc_gemm_bn_lrelu_segmax_f32(const float* A, int64_t a_sr, int64_t a_sc, const float* B, int64_t b_sr,
+                                                 int64_t b_sc, int M, int N, int K, int seg_len, const float* gamma,
+                                                 const float* beta, float eps, float momentum, int use_batch_stats,
+                                                 float* running_mean, float* running_var, float* mean, float* rstd,
+                                                 float* g, float* ysel, int32_t* nstar, void* workspace,
+                                                 size_t workspace_bytes, void* stream) {
+  DG_REQUIRE(A && B && gamma && beta && mean && rstd && g && ysel && nstar && workspace, DGCNN_E_INVALID, "gemm_segmax: null pointer");
+  DG_REQUIRE(M > 0 && N > 0 && K > 0 && seg_len >= 32 && M % seg_len == 0, DGCNN_E_INVALID,
+             "gemm_segmax: need seg_len >= 32 and M a multiple of seg_len (M=%d seg_len=%d)", M, seg_len);
+  DG_REQUIRE(use_batch_stats || (running_mean && running_var), DGCNN_E_INVALID, "gemm_segmax: inference needs running statistics");
+  DG_REQUIRE(!running_mean == !running_var, DGCNN_E_INVALID, "gemm_segmax: running_mean/var must come together");
+  const int segments = M / seg_len;
+  DG_REQUIRE(workspace_bytes >= dgcnn_tc_gemm_colstats_workspace_bytes(M, N, K, segments), DGCNN_E_WORKSPACE, "gemm_segmax: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int KA = (K + 63) / 64, Mp = (M + 127) / 128 * 128, Np = (N + 127) / 128 * 128, num_mt = Mp / 128;
+  unsigned char* Ap = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  unsigned char* Bp = Ap + planes_bytes(Mp, KA, 3);
+  float* stats = reinterpret_cast<float*>(Bp + planes_bytes(Np, KA, 3));
+  unsigned long long* gmax = reinterpret_cast<unsigned long long*>(stats + static_cast<size_t>(num_mt) * 2 * N);
+  unsigned long long* gmin = gmax + static_cast<size_t>(segments) * N;
+  int rc;
+  if ((rc = launch_split<3>(A, a_sr, a_sc, M, K, Mp, KA, Ap, st))) return rc;
+  if ((rc = launch_split<3>(B, b_sr, b_sc, N, K, Np, KA, Bp, st))) return rc;
+  DG_CUDA(cudaMemsetAsync(gmax, 0, static_cast<size_t>(segments) * N * 16, st));
+  using SM = GemmSmem<3, 128, 2>;
+  auto kern = tc_gemm_kernel<3, 128, 2, EPI_COLSTATS>;
+  DG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SM::bytes)));
+  GemmEpi epi{seg_len, stats, gmax, gmin};
+  kern<<<dim3(Np / 128, num_mt, 1), 192, SM::bytes, st>>>(Ap, Bp, nullptr, 0, M, N, KA, KA, 0, epi);
+  DG_CUDA(cudaGetLastError());
+  colstats_finalize_kernel<<<(N + 127) / 128, 128, 0, st>>>(stats, num_mt, N, static_cast<double>(M), gmax, gmin, segments, gamma, beta,
+                                                            eps, momentum, use_batch_stats, running_mean, running_var, mean, rstd,
+                                                            g, ysel, nstar);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -157,10 +157,15 @@ class DGCNN(nn.Module):
         feat = torch.cat((x1, x2, x3), dim=1)                              # [M,192]
         if depth == 4:
             return self._bcn(feat, B, N)
-        h6 = self._dense(feat, 6)                                          # [M,emb]
         if depth == 5:
-            return self._bcn(h6, B, N)
-        g = h6.view(B, N, -1).max(dim=1)[0]                                # [B,emb] global feature
+            return self._bcn(self._dense(feat, 6), B, N)                   # [M,emb] only materialised on request
+        # conv6 + bn6 + LeakyReLU + max over the points fused: the [B,emb,N] activation is never formed
+        bn6 = self.bn6
+        g = ops.GlobalFeature.apply(feat, self.conv6[0].weight.squeeze(-1), bn6.weight, bn6.bias,
+                                    ops.BNState(bn6.running_mean, bn6.running_var, bn6.eps, bn6.momentum),
+                                    self.training, B, N)                   # [B,emb] global feature
+        if self.training:
+            bn6.num_batches_tracked.add_(1)
         if depth == 6:
             return g.unsqueeze(-1)
         if depth == 7:

@@ -61,7 +61,7 @@ class KernelLog:
 LOG = KernelLog()
 
 # kernels launched by each entry point
-_LAUNCHES = {"dgcnn_knn_f32": 2, "dgcnn_knn_tc_f32": 4, "dgcnn_knn_small_f32": 3, "dgcnn_edgeconv_bwd_b": 2, "dgcnn_tc_gemm_f32": 3}
+_LAUNCHES = {"dgcnn_knn_f32": 2, "dgcnn_knn_tc_f32": 4, "dgcnn_knn_small_f32": 3, "dgcnn_edgeconv_bwd_b": 2, "dgcnn_tc_gemm_f32": 3, "dgcnn_tc_gemm_bn_lrelu_segmax_f32": 4}
 
 
 def _call(name: str, *args) -> None:
@@ -204,6 +204,68 @@ class TcLinear(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = tc_gemm(dy.t(), x.t())             # [N,K] = dy^T[N,M] @ x[M,K]   (split-K over the points)
         return dx, dw
+
+
+class GlobalFeature(torch.autograd.Function):
+    """g[B,E] = max_n LeakyReLU(BN(feat W^T)) per block (conv6 + bn6 + max, model.py:172-175), never materialising [M,E].
+
+    Backward uses the linearity of the dense batch-statistics-BN gradient dy = a dz - b' - kappa y (dz is non-zero only
+    at the B*E arg-max entries, y = feat W^T):
+        dfeat = scatter(a dz W) - b' W - feat (W^T diag(kappa) W)
+        dW    = a (dz^T feat) - b' colsum(feat)^T - diag(kappa) W (feat^T feat)
+    i.e. two 192x192-wide GEMMs instead of three E-wide ones."""
+
+    @staticmethod
+    def forward(ctx, feat, w, gamma, beta, bn: BNState, training: bool, B: int, N: int):
+        lib = _lib.load()
+        M, K = feat.shape
+        E = w.shape[0]
+        dev = feat.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        nbytes = lib.dgcnn_tc_gemm_colstats_workspace_bytes(M, E, K, B)
+        ws = _gemm_ws.get(dev.index)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(int(nbytes * 1.25), dtype=torch.uint8, device=dev)
+            _gemm_ws[dev.index] = ws
+        g = torch.empty(B, E, **f32)
+        ysel = torch.empty(B, E, **f32)
+        nstar = torch.empty(B, E, dtype=torch.int32, device=dev)
+        stat = torch.empty(2, E, **f32)
+        fd, wd = feat.detach(), w.detach()
+        _call("dgcnn_tc_gemm_bn_lrelu_segmax_f32", _ptr(fd), fd.stride(0), fd.stride(1), _ptr(wd), wd.stride(0), wd.stride(1),
+              M, E, K, N, _ptr(gamma.detach()), _ptr(beta.detach()), bn.eps, bn.momentum, 1 if training else 0,
+              _ptr(bn.running_mean), _ptr(bn.running_var), _ptr(stat[0]), _ptr(stat[1]), _ptr(g), _ptr(ysel), _ptr(nstar),
+              _ptr(ws), ws.numel(), _stream())
+        ctx.save_for_backward(fd, wd, gamma.detach(), beta.detach(), stat, ysel, nstar)
+        ctx.training = training
+        return g
+
+    @staticmethod
+    def backward(ctx, dg):
+        feat, w, gamma, beta, stat, ysel, nstar = ctx.saved_tensors
+        if not ctx.training:
+            raise RuntimeError("GlobalFeature: the inference form (running statistics) is not differentiable")
+        M = feat.shape[0]
+        B, E = ysel.shape
+        mean, rstd = stat[0], stat[1]
+        a = gamma * rstd
+        yhat = (ysel - mean) * rstd
+        z = yhat * gamma + beta
+        gdz = dg * torch.where(z > 0, 1.0, 0.2)                        # [B,E]: dz at the arg-max entries
+        s1, s2 = gdz.sum(0), (gdz * yhat).sum(0)
+        kappa = a * (s2 / M) * rstd
+        bprime = a * (s1 / M) - kappa * mean
+        idx = nstar.reshape(-1).long()
+        # dfeat
+        gram_w = (w * kappa[:, None]).t() @ w                          # [K,K] = W^T diag(kappa) W (symmetric)
+        dfeat = tc_gemm(feat, gram_w)
+        dfeat.neg_().sub_(bprime @ w)
+        dfeat.index_add_(0, idx, (a * gdz).reshape(-1, 1) * w.repeat(B, 1))
+        # dW
+        t1 = (gdz.unsqueeze(-1) * feat[idx].view(B, E, -1)).sum(0)     # [E,K] = dz^T feat
+        f2 = tc_gemm(feat.t(), feat.t())                               # [K,K] = feat^T feat (split-K over the points)
+        dw = a[:, None] * t1 - bprime[:, None] * feat.sum(0)[None, :] - kappa[:, None] * (w @ f2)
+        return dfeat, dw, s2, s1, None, None, None, None
 
 
 def linear(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:

@@ -160,6 +160,21 @@ int dgcnn_tc_gemm_f32(const float* A, int64_t a_row_stride, int64_t a_col_stride
                       float* D, int ldd, int M, int N, int K, int nsplit,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- conv6 + bn6 + LeakyReLU + global max over the points (model.py:172-175) without materialising [B,emb,N] -------
+ * g[segments,N] = max over the `seg_len` rows of each segment of LeakyReLU(BN(A B^T)).  The GEMM epilogue only emits
+ * per-row-tile column sums / sums of squares and per-segment column max / min (with the attaining row); BN-affine and
+ * LeakyReLU are monotone, so the max of the activations is the activation of the max (or min, for negative scale).
+ * use_batch_stats = 1: training (batch statistics over all M rows, running stats updated if given); 0: inference.
+ * Outputs for backward: mean, rstd [N]; ysel (selected pre-BN value) and nstar (its row) [segments, N].        */
+size_t dgcnn_tc_gemm_colstats_workspace_bytes(int M, int N, int K, int segments);
+int dgcnn_tc_gemm_bn_lrelu_segmax_f32(const float* A, int64_t a_row_stride, int64_t a_col_stride,
+                                      const float* B, int64_t b_row_stride, int64_t b_col_stride,
+                                      int M, int N, int K, int seg_len, const float* gamma, const float* beta,
+                                      float eps, float momentum, int use_batch_stats,
+                                      float* running_mean, float* running_var, float* mean, float* rstd,
+                                      float* g, float* ysel, int32_t* nstar,
+                                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* debug: exercises MN-major tcgen05 operand descriptors on one 128x64 tile pair (tests only) */
 int dgcnn_debug_mn_lab(const float* X, const float* Y, float* D, int lbo_a, int sbo_a, int lbo_b, int sbo_b,
                        int kstep, int a_major, int b_major, void* stream);
