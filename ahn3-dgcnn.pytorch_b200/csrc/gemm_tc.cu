@@ -91,14 +91,15 @@ __global__ void __launch_bounds__(256) split_planes_t_kernel(const float* __rest
 // ---------------------------------------------------------------------------------------------
 // Epilogue variants.  EPI_STORE writes D.  EPI_COLSTATS never writes D: per row-tile it emits the column sums and
 // sums of squares (for batch-statistics BN) and, per segment of `seg_len` consecutive rows (= one point-cloud block),
-// the column maximum / minimum with the row where it is attained (64-bit atomicMax on (ordered value << 32 | row)).
+// the column extremum that the monotone BN+LeakyReLU maps to the maximum (max of y for gamma >= 0, min otherwise) with
+// the 32-row group where it is attained (64-bit atomicMax); the exact row is resolved by the finalize kernel.
 // With them  max_n LReLU(BN(y[n,c]))  is known without ever materialising y (conv6 + bn6 + global max, model.py:172-175).
 enum { EPI_STORE = 0, EPI_COLSTATS = 1 };
 struct GemmEpi {
   int seg_len;
   float* stat_partials;            // [row tiles][2][N]
-  unsigned long long* gmax;        // [segments][N]   (zero-initialised by the caller)
-  unsigned long long* gmin;        // [segments][N]   keys of -y
+  unsigned long long* gext;        // [segments][N]  (ordered(sign*y) << 32 | 32-row group), zero-initialised by the caller
+  const float* gamma;              // [N]: sign(gamma) = sign of the BN scale decides whether the max or the min is needed
 };
 
 __device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
@@ -125,22 +126,6 @@ __device__ __forceinline__ void warp_transpose_max(float (&v)[32], int lane) {
     }
   }
 }
-// column-wise max over the lanes selected by `in_seg` and the lane attaining it; result for column l in lane l
-__device__ __forceinline__ void warp_col_argmax(const float (&v)[32], bool in_seg, int lane, float& best, int& best_lane) {
-  float t[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) t[i] = in_seg ? v[i] : -INFINITY;
-  warp_transpose_max(t, lane);
-  best = t[0];
-  best_lane = 0;
-#pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    const float m = __shfl_sync(0xffffffffu, best, c);
-    const unsigned hit = __ballot_sync(0xffffffffu, in_seg && v[c] == m);
-    if (lane == c) best_lane = hit ? __ffs(hit) - 1 : 0;
-  }
-}
-
 template <int NS, int BN, int STAGES>
 struct GemmSmem {
   static constexpr uint32_t a_plane = 128 * 128;          // 128 rows x 128 B
@@ -266,22 +251,21 @@ tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __rest
           statS[(quarter * 2 + 1) * BN + c0 + lane] = q[0];
         }
         if (vmask) {
+          const float sgn = (col < N && epi.gamma[col] < 0.f) ? -1.f : 1.f;     // column of lane after the transpose
           for (int pass = 0; pass < 2; ++pass) {
             const int sg = pass == 0 ? seg_lo : seg_hi;
             if (pass == 1 && seg_hi == seg_lo) break;
             const bool in_seg = rvalid && seg == sg;
-            float best; int bl;
-            warp_col_argmax(v, in_seg, lane, best, bl);
-            if (col < N && best > -INFINITY)
-              atomicMax(epi.gmax + static_cast<size_t>(sg) * N + col,
-                        (static_cast<unsigned long long>(ordered_bits(best)) << 32) | static_cast<uint32_t>(mt * 128 + quarter * 32 + bl));
-            float nv[32];
+            float t[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) nv[i] = -v[i];
-            warp_col_argmax(nv, in_seg, lane, best, bl);
-            if (col < N && best > -INFINITY)
-              atomicMax(epi.gmin + static_cast<size_t>(sg) * N + col,
-                        (static_cast<unsigned long long>(ordered_bits(best)) << 32) | static_cast<uint32_t>(mt * 128 + quarter * 32 + bl));
+            for (int i = 0; i < 32; ++i) {
+              const float si = __shfl_sync(0xffffffffu, sgn, i);                  // sign of column c0 + i
+              t[i] = in_seg ? si * v[i] : -INFINITY;
+            }
+            warp_transpose_max(t, lane);
+            if (col < N && t[0] > -INFINITY)
+              atomicMax(epi.gext + static_cast<size_t>(sg) * N + col,
+                        (static_cast<unsigned long long>(ordered_bits(t[0])) << 32) | static_cast<uint32_t>(mt * 4 + quarter));
           }
         }
       }
@@ -405,13 +389,10 @@ extern "C" int dgcnn_tc_gemm_f32(const float* A, int64_t a_sr, int64_t a_sc, con
 // GEMM + batch statistics + per-block column extrema (conv6 + bn6 + LeakyReLU + max over the points), no D store
 // ---------------------------------------------------------------------------------------------
 namespace dg {
-// one thread per column: reduce the row-tile partials in FP64 (fixed order), BN scalars, then the per-block outputs
-__global__ void colstats_finalize_kernel(const float* __restrict__ stat_partials, int num_mt, int N, double count,
-                                         const unsigned long long* __restrict__ gmax, const unsigned long long* __restrict__ gmin,
-                                         int segments, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                         float eps, float momentum, int use_batch_stats, float* running_mean,
-                                         float* running_var, float* mean_out, float* rstd_out, float* gout,
-                                         float* ysel, int* nstar) {
+// one thread per column: reduce the row-tile partials in FP64 (fixed order) and derive the BN scalars
+__global__ void colstats_bn_kernel(const float* __restrict__ stat_partials, int num_mt, int N, double count,
+                                   const float* __restrict__ gamma, float eps, float momentum, int use_batch_stats,
+                                   float* running_mean, float* running_var, float* mean_out, float* rstd_out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= N) return;
   double m, rs;
@@ -436,17 +417,44 @@ __global__ void colstats_finalize_kernel(const float* __restrict__ stat_partials
   }
   mean_out[c] = static_cast<float>(m);
   rstd_out[c] = static_cast<float>(rs);
-  const float mean = static_cast<float>(m), scale = static_cast<float>(static_cast<double>(gamma[c]) * rs), be = beta[c];
-  for (int b = 0; b < segments; ++b) {
-    const bool up = scale >= 0.f;          // BN affine increasing iff scale >= 0; LeakyReLU is increasing
-    const unsigned long long key = up ? gmax[static_cast<size_t>(b) * N + c] : gmin[static_cast<size_t>(b) * N + c];
-    const uint32_t u = static_cast<uint32_t>(key >> 32);
-    float y = __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
-    if (!up) y = -y;
-    const float z = __fmaf_rn(y - mean, scale, be);
-    gout[static_cast<size_t>(b) * N + c] = z > 0.f ? z : kSlope * z;
-    ysel[static_cast<size_t>(b) * N + c] = y;
-    nstar[static_cast<size_t>(b) * N + c] = static_cast<int>(key & 0xFFFFFFFFull);
+}
+
+// one warp per (segment, column): decode the extremum, apply BN + LeakyReLU, and resolve the attaining row inside the
+// recorded 32-row group by recomputing the 32 dot products in FP32 (lane = row)
+__global__ void segmax_finalize_kernel(const float* __restrict__ A, long long a_sr, long long a_sc, const float* __restrict__ Bw,
+                                       long long b_sr, long long b_sc, int M, int N, int K, int segments, int seg_len,
+                                       const unsigned long long* __restrict__ gext, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, const float* __restrict__ mean,
+                                       const float* __restrict__ rstd, float* __restrict__ gout, float* __restrict__ ysel,
+                                       int* __restrict__ nstar) {
+  const int lane = threadIdx.x & 31;
+  const long long item = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (item >= static_cast<long long>(segments) * N) return;
+  const int b = static_cast<int>(item / N), c = static_cast<int>(item % N);
+  const unsigned long long key = gext[item];
+  const uint32_t u = static_cast<uint32_t>(key >> 32);
+  const float sgn = gamma[c] < 0.f ? -1.f : 1.f;
+  const float y = sgn * __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+  const int row = static_cast<int>(key & 0xFFFFFFFFull) * 32 + lane;
+  float d = -INFINITY;
+  if (row < M && row / seg_len == b) {
+    float acc = 0.f;
+    for (int kk = 0; kk < K; ++kk) acc = __fmaf_rn(A[row * a_sr + kk * a_sc], Bw[c * b_sr + kk * b_sc], acc);
+    d = -fabsf(acc - y);                       // the row whose value reproduces the recorded extremum best
+  }
+  float best = d;
+  int bl = lane;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+    if (ob > best || (ob == best && ol < bl)) { best = ob; bl = ol; }
+  }
+  if (lane == 0) {
+    const float z = __fmaf_rn(y - mean[c], gamma[c] * rstd[c], beta[c]);
+    gout[item] = z > 0.f ? z : kSlope * z;
+    ysel[item] = y;
+    nstar[item] = static_cast<int>(key & 0xFFFFFFFFull) * 32 + bl;
   }
 }
 }  // namespace dg
@@ -456,7 +464,7 @@ extern "C" size_t dgcnn_tc_gemm_colstats_workspace_bytes(int M, int N, int K, in
   const int KA = (K + 63) / 64;
   const size_t planes = planes_bytes((M + 127) / 128 * 128, KA, 3) + planes_bytes((N + 127) / 128 * 128, KA, 3);
   const size_t stats = static_cast<size_t>((M + 127) / 128) * 2 * N * sizeof(float);
-  const size_t ext = static_cast<size_t>(segments) * N * 8 * 2;
+  const size_t ext = static_cast<size_t>(segments) * N * 8;
   return planes + stats + ext + 8192;
 }
 
@@ -481,21 +489,24 @@ extern "C" int dgcnn_tc_gemm_bn_lrelu_segmax_f32(const float* A, int64_t a_sr, i
   unsigned char* Ap = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
   unsigned char* Bp = Ap + planes_bytes(Mp, KA, 3);
   float* stats = reinterpret_cast<float*>(Bp + planes_bytes(Np, KA, 3));
-  unsigned long long* gmax = reinterpret_cast<unsigned long long*>(stats + static_cast<size_t>(num_mt) * 2 * N);
-  unsigned long long* gmin = gmax + static_cast<size_t>(segments) * N;
+  unsigned long long* gext = reinterpret_cast<unsigned long long*>(stats + static_cast<size_t>(num_mt) * 2 * N);
   int rc;
   if ((rc = launch_split<3>(A, a_sr, a_sc, M, K, Mp, KA, Ap, st))) return rc;
   if ((rc = launch_split<3>(B, b_sr, b_sc, N, K, Np, KA, Bp, st))) return rc;
-  DG_CUDA(cudaMemsetAsync(gmax, 0, static_cast<size_t>(segments) * N * 16, st));
+  DG_CUDA(cudaMemsetAsync(gext, 0, static_cast<size_t>(segments) * N * 8, st));
   using SM = GemmSmem<3, 128, 2>;
   auto kern = tc_gemm_kernel<3, 128, 2, EPI_COLSTATS>;
   DG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SM::bytes)));
-  GemmEpi epi{seg_len, stats, gmax, gmin};
+  GemmEpi epi{seg_len, stats, gext, gamma};
   kern<<<dim3(Np / 128, num_mt, 1), 192, SM::bytes, st>>>(Ap, Bp, nullptr, 0, M, N, KA, KA, 0, epi);
   DG_CUDA(cudaGetLastError());
-  colstats_finalize_kernel<<<(N + 127) / 128, 128, 0, st>>>(stats, num_mt, N, static_cast<double>(M), gmax, gmin, segments, gamma, beta,
-                                                            eps, momentum, use_batch_stats, running_mean, running_var, mean, rstd,
-                                                            g, ysel, nstar);
+  colstats_bn_kernel<<<(N + 127) / 128, 128, 0, st>>>(stats, num_mt, N, static_cast<double>(M), gamma, eps, momentum, use_batch_stats,
+                                                      running_mean, running_var, mean, rstd);
+  DG_CUDA(cudaGetLastError());
+  const long long items = static_cast<long long>(segments) * N;
+  segmax_finalize_kernel<<<static_cast<int>((items * 32 + 255) / 256), 256, 0, st>>>(A, a_sr, a_sc, B, b_sr, b_sc, M, N, K, segments,
+                                                                                  seg_len, gext, gamma, beta, mean, rstd, g, ysel,
+                                                                                  nstar);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
 }
