@@ -130,34 +130,49 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
       }
       __syncthreads();  // S1
     }
-    // ---- produce the A planes -----------------------------------------------------------------------------------
+    // ---- produce the A planes: all global loads of the thread are issued before the first use ------------------------
+    {
+      float4 ra[4], rb[4];
+      bool ok[4];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int i = tid + it * kThreads, row = i >> 3, ch = i & 7;
-      float v[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = 0.f;
-      if (MODE == MODE_TRAIN_A) {
-        const int j = nbr[row];
-        if (j >= 0) {
-          const float* src = p.rows + static_cast<size_t>(j) * p.ld + ch * 8;
-          const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-          const float* xi = xis + (row / k) * 64 + ch * 8;
-          const float4 c = *reinterpret_cast<const float4*>(xi), d = *reinterpret_cast<const float4*>(xi + 4);
-          v[0] = a.x - c.x; v[1] = a.y - c.y; v[2] = a.z - c.z; v[3] = a.w - c.w;       // x_j - x_i (model.py:81)
-          v[4] = b.x - d.x; v[5] = b.y - d.y; v[6] = b.z - d.z; v[7] = b.w - d.w;
+      for (int it = 0; it < 4; ++it) {
+        const int i = tid + it * kThreads, row = i >> 3, ch = i & 7;
+        const float* src;
+        if (MODE == MODE_TRAIN_A) {
+          const int j = nbr[row];
+          ok[it] = j >= 0;
+          src = p.rows + static_cast<size_t>(max(j, 0)) * p.ld + ch * 8;
+        } else {
+          ok[it] = row < nvalid;
+          src = p.y_a_in + (e0 + min(row, max(nvalid - 1, 0))) * kCout + ch * 8;
         }
-      } else if (row < nvalid) {
-        const float* src = p.y_a_in + (e0 + row) * kCout + ch * 8;
-        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-        const float y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = ch * 8 + e;
-          v[e] = lrelu(bn_apply(y[e], aff[c], aff[64 + c], aff[128 + c]));               // h = LReLU(BN_a(y_a))
+        ra[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        rb[it] = ra[it];
+        if (ok[it]) {
+          ra[it] = *reinterpret_cast<const float4*>(src);
+          rb[it] = *reinterpret_cast<const float4*>(src + 4);
         }
       }
-      store_split3(Ap, kPlA, row, ch, v);
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int i = tid + it * kThreads, row = i >> 3, ch = i & 7;
+        float v[8] = {ra[it].x, ra[it].y, ra[it].z, ra[it].w, rb[it].x, rb[it].y, rb[it].z, rb[it].w};
+        if (MODE == MODE_TRAIN_A) {
+          if (ok[it]) {
+            const float* xi = xis + (row / k) * 64 + ch * 8;
+            const float4 c = *reinterpret_cast<const float4*>(xi), d = *reinterpret_cast<const float4*>(xi + 4);
+            v[0] -= c.x; v[1] -= c.y; v[2] -= c.z; v[3] -= c.w;       // x_j - x_i (model.py:81)
+            v[4] -= d.x; v[5] -= d.y; v[6] -= d.z; v[7] -= d.w;
+          }
+        } else if (ok[it]) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = ch * 8 + e;
+            v[e] = lrelu(bn_apply(v[e], aff[c], aff[64 + c], aff[128 + c]));             // h = LReLU(BN_a(y_a))
+          }
+        }
+        store_split3(Ap, kPlA, row, ch, v);
+      }
     }
     if (MODE == MODE_TRAIN_A) {
       // hoisted centre term V[p] = Wa2 x_i
@@ -267,9 +282,9 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
 struct EcTcBwdSmem {
   static constexpr uint32_t dy_off = 0;                         // DY planes (2)
   static constexpr uint32_t h_off = 2 * kPlA;                   // H planes (2)
-  static constexpr uint32_t w_off = h_off + 2 * kPlA;           // W_b planes (2): rows = c (out), K = c'' (in)
-  static constexpr uint32_t wt_off = w_off + 2 * kPlW;          // W_b^T planes (2): rows = c'', K = c
-  static constexpr uint32_t g_off = wt_off + 2 * kPlW;          // gs [16][64]
+  static constexpr uint32_t w_off = h_off + 2 * kPlA;           // W_b planes (2): rows = c (out), 128 B of c'' (in): K-major
+                                                                // for y_b = H W_b^T, MN-major view (N = c'', K = c) for dh
+  static constexpr uint32_t g_off = w_off + 2 * kPlW;           // gs [16][64]
   static constexpr uint32_t aff_off = g_off + kMaxP * 64 * 4;   // affine of BN_a (192) + coefficients of BN_b (192)
   static constexpr uint32_t arg_off = aff_off + 2 * 192 * 4;    // args [16][64] u8
   static constexpr uint32_t red_off = arg_off + kMaxP * 64;     // [2][4][64] floats
@@ -304,7 +319,6 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
   unsigned char* DYp = sm + EcTcBwdSmem::dy_off;
   unsigned char* Hp = sm + EcTcBwdSmem::h_off;
   unsigned char* Wp = sm + EcTcBwdSmem::w_off;
-  unsigned char* WTp = sm + EcTcBwdSmem::wt_off;
   float* gs = reinterpret_cast<float*>(sm + EcTcBwdSmem::g_off);
   float* aff = reinterpret_cast<float*>(sm + EcTcBwdSmem::aff_off);
   float* cb = aff + 192;
@@ -324,14 +338,10 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
   if (warp == 0) tc::tmem_alloc(tmem_slot, 128);     // columns 0-63: y_b / dh, columns 64-127: dW_b accumulator
   for (int i = tid; i < 64 * 8; i += kThreads) {
     const int o = i >> 3, ch = i & 7;
-    float v[8], vt[8];
+    float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      v[e] = p.w_b[static_cast<size_t>(o) * 64 + ch * 8 + e];           // row o = out channel c, K = c''
-      vt[e] = p.w_b[static_cast<size_t>(ch * 8 + e) * 64 + o];          // row o = c'', K = c
-    }
+    for (int e = 0; e < 8; ++e) v[e] = p.w_b[static_cast<size_t>(o) * 64 + ch * 8 + e];   // row o = out channel c, K = c''
     store_split<2>(Wp, kPlW, o, ch, v);
-    store_split<2>(WTp, kPlW, o, ch, vt);
   }
   if (tid < 192) {
     aff[tid] = p.aff_a[tid];
@@ -344,6 +354,7 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
   const uint32_t taddr = *tmem_slot;
   constexpr uint32_t idesc_k = tc::idesc_bf16(128, 64);
   constexpr uint32_t idesc_mn = tc::idesc_bf16(128, 64) | (1u << 15) | (1u << 16);
+  constexpr uint32_t idesc_kb = tc::idesc_bf16(128, 64) | (1u << 16);            // A K-major, B MN-major
   uint32_t phase = 0;
   bool first_tile = true;
 
@@ -363,23 +374,27 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
       gs[i] = ok ? g[static_cast<size_t>(gp) * kCout + (i & 63)] : 0.f;
       args[i] = ok ? arg[static_cast<size_t>(gp) * kCout + (i & 63)] : 255;
     }
+    // producer with the EPILOGUE's mapping (thread = tile row erow, 32 columns of half `half`): the thread's y_a values
+    // stay in registers until epilogue 2, so y_a is read from memory once per tile
+    float ya[32];
+    {
+      const bool valid = erow < nvalid;
+      const float* src = p.y_a_in + (e0 + (valid ? erow : 0)) * kCout + half * 32;
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int i = tid + it * kThreads, row = i >> 3, ch = i & 7;
-      float v[8];
+      for (int i = 0; i < 32; i += 4) {
+        const float4 y = valid ? *reinterpret_cast<const float4*>(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ya[i] = y.x; ya[i + 1] = y.y; ya[i + 2] = y.z; ya[i + 3] = y.w;
+      }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = 0.f;
-      if (row < nvalid) {
-        const float* src = p.y_a_in + (e0 + row) * kCout + ch * 8;
-        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-        const float y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      for (int c8 = 0; c8 < 4; ++c8) {
+        float h[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const int c = ch * 8 + e;
-          v[e] = lrelu(bn_apply(y[e], aff[c], aff[64 + c], aff[128 + c]));
+          const int c = half * 32 + c8 * 8 + e;
+          h[e] = valid ? lrelu(bn_apply(ya[c8 * 8 + e], aff[c], aff[64 + c], aff[128 + c])) : 0.f;
         }
+        store_split<2>(Hp, kPlA, erow, half * 4 + c8, h);
       }
-      store_split<2>(Hp, kPlA, row, ch, v);
     }
     tc::fence_proxy_async();
     __syncthreads();  // S1
@@ -414,7 +429,19 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
     __syncthreads();  // S2: DY planes complete, accumulator 0 drained
     if (tid == 0) {
       tc::fence_after_sync();
-      tc::mma_split_katom<2>(taddr, tc::smem_u32(DYp), kPlA, tc::smem_u32(WTp), kPlW, idesc_k, true);   // dh = DY W_b
+      // dh = DY W_b: A = DY planes (K-major), B = the W_b planes read MN-major (N = c'' contiguous, K = c = rows)
+      {
+        uint32_t acc3 = 0u;
+        const int pa[3] = {0, 1, 0}, pb[3] = {1, 0, 0};
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            tc::mma_bf16(taddr, tc::smem_desc_sw128(tc::smem_u32(DYp) + pa[q] * kPlA + k16 * 32),
+                         smem_desc_mn(tc::smem_u32(Wp) + pb[q] * kPlW + k16 * 2048, 1024), idesc_kb, acc3);
+            acc3 = 1u;
+          }
+      }
       // dW_b += DY^T H over the 128 tile rows: pairs (DY plane i, H plane j), i + j <= 3, smallest first
       const uint32_t lbo = tc::smem_u32(Hp) - tc::smem_u32(DYp);
       uint32_t acc = first_tile ? 0u : 1u;
@@ -436,24 +463,22 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
     tc::fence_after_sync();
     // ---- epilogue 2: dz_a = dh * LReLU'(BN_a(y_a)); store; column sums of dz_a and dz_a*y_a ------------------------
     {
-      float v[32], w[32];
+      float v[32];
       tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + half * 32, v);
       const bool valid = erow < nvalid;
+      float (&w)[32] = ya;                      // dz_a * y_a overwrites the cached y_a values
       if (valid) {
-        const float* src = p.y_a_in + (e0 + erow) * kCout + half * 32;
         float* dst = dz_a + (e0 + erow) * kCout + half * 32;
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          const float4 y = *reinterpret_cast<const float4*>(src + i);
-          const float ya[4] = {y.x, y.y, y.z, y.w};
           float o[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int col = half * 32 + i + e;
-            const float z = bn_apply(ya[e], aff[col], aff[64 + col], aff[128 + col]);
+            const float z = bn_apply(ya[i + e], aff[col], aff[64 + col], aff[128 + col]);
             o[e] = v[i + e] * (z > 0.f ? 1.f : kSlope);
             v[i + e] = o[e];
-            w[i + e] = o[e] * ya[e];
+            w[i + e] = o[e] * ya[i + e];
           }
           *reinterpret_cast<float4*>(dst + i) = make_float4(o[0], o[1], o[2], o[3]);
         }
