@@ -341,7 +341,12 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
       }
       const float norm_i = norms[g];
       const float ni = sqrtf(norm_i);
-      const float eps = 1.01f * (kC1 * ni * rmax + kC2 * (ni + rmax) * (ni + rmax));
+      // Only keys with |x_j| <= |x_i| + d_tau can have a score near tau (score <= |x_i|^2 - (|x_j| - |x_i|)^2), so the
+      // error bound uses R_i = min(R, |x_i| + 1.1 d_tau) instead of the block maximum R: one far outlier no longer
+      // inflates every row's margin (derivation in DESIGN.md, kNN filter bound).
+      const float dtau = sqrtf(fmaxf(norm_i - tau_r, 0.f));
+      const float ri = tau_r > -INFINITY ? fminf(rmax, ni + 1.1f * dtau + 1e-3f * ni) : rmax;
+      const float eps = 1.01f * (kC1 * ni * ri + kC2 * (ni + ri) * (ni + ri));
       const float cut = lo - 2.0f * eps;
       // compact the survivors (approx > cut) into the warp's staging area
       int base = 0;
