@@ -35,9 +35,25 @@ constexpr float kC2 = 4.8e-7f;          // final roundings, relative to (|x_i|+|
 // prep: rows -> per-block tiles of 64 points: two swizzled bf16 planes + the 64 squared norms; also the squared
 // norms themselves (torch.sum order, see knn.cu) and the per-block maximum norm.
 // ---------------------------------------------------------------------------------------------
+// per-block channel means (the filter works on centred features: distances are translation invariant and the error
+// bound scales with the norms, which centring shrinks by 10-100x on post-LeakyReLU features)
+__global__ void __launch_bounds__(256) knn_tc_mean_kernel(const float* __restrict__ rows, int ld, int N, int C4,
+                                                          float* __restrict__ mu) {
+  __shared__ float red[4][64];
+  const int b = blockIdx.x, c = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  float s = 0.f;
+  if (c < C4)
+    for (int n = grp; n < N; n += 4) s += rows[(static_cast<size_t>(b) * N + n) * ld + c];
+  red[grp][c] = s;
+  __syncthreads();
+  if (threadIdx.x < 64) mu[b * 64 + c] = (red[0][c] + red[1][c] + red[2][c] + red[3][c]) / static_cast<float>(N);
+}
+
 __global__ void knn_tc_prep_kernel(const float* __restrict__ rows, int ld, int N, int C4, int T,
-                                   const float* __restrict__ norms, unsigned char* __restrict__ tiles) {
-  // one thread per (tile row, 16-byte chunk); grid.y = block
+                                   const float* __restrict__ mu, unsigned char* __restrict__ tiles,
+                                   float* __restrict__ normc, unsigned int* __restrict__ maxnormc_bits) {
+  // one thread per (tile row, 16-byte chunk); grid.y = block.  total is a multiple of 8, so the 8 chunk-threads of a
+  // row are always in the same warp and all active.
   const int b = blockIdx.y;
   const int total = T * 64 * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -48,13 +64,20 @@ __global__ void knn_tc_prep_kernel(const float* __restrict__ rows, int ld, int N
     for (int e = 0; e < 8; ++e) v[e] = 0.f;
     if (n < N && ch * 8 < C4) {
       const float* src = rows + (static_cast<size_t>(b) * N + n) * ld + ch * 8;
+      const float* m = mu + b * 64 + ch * 8;
       const float4 lo = *reinterpret_cast<const float4*>(src);
-      v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+      v[0] = lo.x - m[0]; v[1] = lo.y - m[1]; v[2] = lo.z - m[2]; v[3] = lo.w - m[3];
       if (ch * 8 + 4 < C4) {
         const float4 hi = *reinterpret_cast<const float4*>(src + 4);
-        v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+        v[4] = hi.x - m[4]; v[5] = hi.y - m[5]; v[6] = hi.z - m[6]; v[7] = hi.w - m[7];
       }
     }
+    float sq = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sq = __fmaf_rn(v[e], v[e], sq);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 4);
     unsigned char* tile = tiles + (static_cast<size_t>(b) * T + t) * kTileBytes;
     const uint32_t off = tc::unit_elem_offset(rl, ch * 8);
 #pragma unroll
@@ -67,7 +90,13 @@ __global__ void knn_tc_prep_kernel(const float* __restrict__ rows, int ld, int N
       }
       *reinterpret_cast<uint4*>(tile + p * tc::kUnitBytes + off) = *reinterpret_cast<const uint4*>(h);
     }
-    if (ch == 0) reinterpret_cast<float*>(tile + 2 * tc::kUnitBytes)[rl] = n < N ? norms[static_cast<size_t>(b) * N + n] : 0.f;
+    if (ch == 0) {
+      reinterpret_cast<float*>(tile + 2 * tc::kUnitBytes)[rl] = sq;       // centred squared norm (0 for padding rows)
+      if (n < N) {
+        normc[static_cast<size_t>(b) * N + n] = sq;
+        atomicMax(maxnormc_bits + b, __float_as_uint(sq));
+      }
+    }
   }
 }
 
@@ -141,7 +170,8 @@ __device__ __forceinline__ void top8_insert(float (&t)[8], float v) {
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__ rows, int ld,
-              const float* __restrict__ norms, const unsigned int* __restrict__ maxnorm_bits, int N, int C4, int T,
+              const float* __restrict__ norms, const unsigned int* __restrict__ maxnorm_bits,
+              const float* __restrict__ normc, const unsigned int* __restrict__ maxnormc_bits, int N, int C4, int T,
               int k, int T1, unsigned long long* __restrict__ cand, int32_t* __restrict__ idx,
               int* __restrict__ fb_count, int* __restrict__ fb_rows) {
   // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (checked below), and plain
@@ -294,7 +324,8 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
     named_bar_sync(1, kScanWarps * 32);
 
     // ---- pass 3: bisect, re-score exactly, certify (warp per row, 8 rows per warp) ----------------------------------
-    const float rmax = sqrtf(__uint_as_float(maxnorm_bits[b]));
+    const float rmax = sqrtf(__uint_as_float(maxnormc_bits[b]));      // largest CENTRED norm of the block
+    const float rx = sqrtf(__uint_as_float(maxnorm_bits[b]));         // largest raw norm (rounding of the centring)
     unsigned long long* stg = stageS + warp * kSurvivors;
     for (int rr = 0; rr < 8; ++rr) {
       const int row = warp * 8 + rr, q = q0 + row;
@@ -339,14 +370,15 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         if (c >= want) lo = mid; else hi = mid;
       }
-      const float norm_i = norms[g];
-      const float ni = sqrtf(norm_i);
-      // Only keys with |x_j| <= |x_i| + d_tau can have a score near tau (score <= |x_i|^2 - (|x_j| - |x_i|)^2), so the
-      // error bound uses R_i = min(R, |x_i| + 1.1 d_tau) instead of the block maximum R: one far outlier no longer
-      // inflates every row's margin (derivation in DESIGN.md, kNN filter bound).
-      const float dtau = sqrtf(fmaxf(norm_i - tau_r, 0.f));
+      const float norm_i = norms[g];                 // reference |x_i|^2 (exact scores)
+      const float nci = normc[g];                    // centred |y_i|^2: approx score of the row = exact pd + nci
+      const float ni = sqrtf(nci);
+      // Only keys with |y_j| <= |y_i| + d_tau can have a score near tau (score <= |y_i|^2 - (|y_j| - |y_i|)^2), so the
+      // error bound uses R_i = min(R, |y_i| + 1.1 d_tau) instead of the block maximum R: one far outlier does not
+      // inflate every row's margin.  Third term: rounding of y = fl(x - mu) (2^-22 Rx (|y_i| + 2 R_i)).
+      const float dtau = sqrtf(fmaxf(nci - tau_r, 0.f));
       const float ri = tau_r > -INFINITY ? fminf(rmax, ni + 1.1f * dtau + 1e-3f * ni) : rmax;
-      const float eps = 1.01f * (kC1 * ni * ri + kC2 * (ni + ri) * (ni + ri));
+      const float eps = 1.01f * (kC1 * ni * ri + kC2 * (ni + ri) * (ni + ri) + 2.4e-7f * rx * (ni + 2.0f * ri));
       const float cut = lo - 2.0f * eps;
       // compact the survivors (approx > cut) into the warp's staging area
       int base = 0;
@@ -390,7 +422,14 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
       if (ex[1] != 0ull && rank1 == k - 1) pdk = sel::key_score(ex[1]);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) pdk = fmaxf(pdk, __shfl_xor_sync(0xffffffffu, pdk, o));
-      bad = bad || !((tau_r - norm_i) + eps < pdk);
+      const bool cert = (tau_r - nci) + eps < pdk;
+      if (lane == 0) {     // diagnostics: fb_count[1..4] count the reasons (overflow, too few, too many near-ties, certificate)
+        if (max(max(c4.x, c4.y), max(c4.z, c4.w)) > kSubCands) atomicAdd(fb_count + 1, 1);
+        else if (ntot < k) atomicAdd(fb_count + 2, 1);
+        else if (base > kSurvivors) atomicAdd(fb_count + 3, 1);
+        else if (!cert) atomicAdd(fb_count + 4, 1);
+      }
+      bad = bad || !cert;
       if (bad && lane == 0) fb_rows[atomicAdd(fb_count, 1)] = static_cast<int>(g);
     }
   }
@@ -637,7 +676,7 @@ static int launch_knn_small(const float* rows, int ld, const float* norms, int B
 using namespace dg;
 
 static size_t knn_tc_layout(int B, int N, size_t* o_norms, size_t* o_max, size_t* o_cnt, size_t* o_rows, size_t* o_tiles,
-                            size_t* o_cand) {
+                            size_t* o_cand, size_t* o_normc = nullptr, size_t* o_mu = nullptr, size_t* o_maxc = nullptr) {
   const int T = 2 * ((N + 127) / 128);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 1023) & ~size_t(1023); return o; };
@@ -648,6 +687,10 @@ static size_t knn_tc_layout(int B, int N, size_t* o_norms, size_t* o_max, size_t
   *o_tiles = take(static_cast<size_t>(B) * T * kTileBytes);
   // candidate buffers; query tiles are padded to 128 rows, so allow for the rows past the end of the last block
   *o_cand = take((static_cast<size_t>(B) * N + 128) * 4 * kSubCands * 8);
+  const size_t a = take(static_cast<size_t>(B) * N * 4), m = take(static_cast<size_t>(B) * 64 * 4), x = take(static_cast<size_t>(B) * 4);
+  if (o_normc) *o_normc = a;
+  if (o_mu) *o_mu = m;
+  if (o_maxc) *o_maxc = x;
   return off + 1024;
 }
 
@@ -671,8 +714,8 @@ extern "C" int dgcnn_knn_tc_f32(const float* rows, int ld, int B, int C, int N, 
              "knn_tc: rows must be 16-byte aligned with ld %% 4 == 0 and ld >= round4(C)");
   DG_REQUIRE(workspace_bytes >= dgcnn_knn_tc_workspace_bytes(B, N), DGCNN_E_WORKSPACE, "knn_tc: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  size_t o_norms, o_max, o_cnt, o_rows, o_tiles, o_cand;
-  knn_tc_layout(B, N, &o_norms, &o_max, &o_cnt, &o_rows, &o_tiles, &o_cand);
+  size_t o_norms, o_max, o_cnt, o_rows, o_tiles, o_cand, o_normc, o_mu, o_maxc;
+  knn_tc_layout(B, N, &o_norms, &o_max, &o_cnt, &o_rows, &o_tiles, &o_cand, &o_normc, &o_mu, &o_maxc);
   unsigned char* ws = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
   float* norms = reinterpret_cast<float*>(ws + o_norms);
   unsigned int* maxnorm = reinterpret_cast<unsigned int*>(ws + o_max);
@@ -684,7 +727,13 @@ extern "C" int dgcnn_knn_tc_f32(const float* rows, int ld, int B, int C, int N, 
   DG_CUDA(cudaMemsetAsync(ws + o_max, 0, o_rows - o_max, st));     // maxnorm + fallback counter
   knn_norms_max_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(rows, ld, N, C, norms, maxnorm);
   DG_CUDA(cudaGetLastError());
-  knn_tc_prep_kernel<<<dim3(std::min((T * 512 + 255) / 256, 4096), B), 256, 0, st>>>(rows, ld, N, C4, T, norms, tiles);
+  float* normc = reinterpret_cast<float*>(ws + o_normc);
+  float* mu = reinterpret_cast<float*>(ws + o_mu);
+  unsigned int* maxnormc = reinterpret_cast<unsigned int*>(ws + o_maxc);
+  DG_CUDA(cudaMemsetAsync(maxnormc, 0, static_cast<size_t>(B) * 4, st));
+  knn_tc_mean_kernel<<<B, 256, 0, st>>>(rows, ld, N, C4, mu);
+  DG_CUDA(cudaGetLastError());
+  knn_tc_prep_kernel<<<dim3(std::min((T * 512 + 255) / 256, 4096), B), 256, 0, st>>>(rows, ld, N, C4, T, mu, tiles, normc, maxnormc);
   DG_CUDA(cudaGetLastError());
   DG_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(KnnTcSmem::bytes)));
   // pass-1 sample: the 8th best of a thread's 16*T1 keys estimates global rank N/(2*T1); aim at ~max(100, 3k)
@@ -692,8 +741,8 @@ extern "C" int dgcnn_knn_tc_f32(const float* rows, int ld, int B, int C, int N, 
   const int target = std::max(100, 3 * k);
   const int T1 = std::max(1, std::min(Tk, (N + 2 * target - 1) / (2 * target)));
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(ws + o_cand);
-  knn_tc_kernel<<<dim3((N + 127) / 128, B), kTcThreads, KnnTcSmem::bytes, st>>>(tiles, rows, ld, norms, maxnorm, N, C4, T, k, T1,
-                                                                               cand, idx, fb_count, fb_rows);
+  knn_tc_kernel<<<dim3((N + 127) / 128, B), kTcThreads, KnnTcSmem::bytes, st>>>(tiles, rows, ld, norms, maxnorm, normc, maxnormc, N,
+                                                                               C4, T, k, T1, cand, idx, fb_count, fb_rows);
   DG_CUDA(cudaGetLastError());
   knn_fallback_kernel<<<64, kThreads, 0, st>>>(rows, ld, norms, N, C4, k, idx, fb_count, fb_rows);
   DG_CUDA(cudaGetLastError());
