@@ -38,15 +38,17 @@ constexpr float kC2 = 4.8e-7f;          // final roundings, relative to (|x_i|+|
 // per-block channel means (the filter works on centred features: distances are translation invariant and the error
 // bound scales with the norms, which centring shrinks by 10-100x on post-LeakyReLU features)
 __global__ void __launch_bounds__(256) knn_tc_mean_kernel(const float* __restrict__ rows, int ld, int N, int C4,
-                                                          float* __restrict__ mu) {
+                                                          float* __restrict__ musum) {
+  // grid (slices, B): each CTA sums a slice of the block's rows; musum (zero-initialised) receives the channel SUMS
   __shared__ float red[4][64];
-  const int b = blockIdx.x, c = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int b = blockIdx.y, c = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int per = (N + gridDim.x - 1) / gridDim.x, n0 = blockIdx.x * per, n1 = min(N, n0 + per);
   float s = 0.f;
   if (c < C4)
-    for (int n = grp; n < N; n += 4) s += rows[(static_cast<size_t>(b) * N + n) * ld + c];
+    for (int n = n0 + grp; n < n1; n += 4) s += rows[(static_cast<size_t>(b) * N + n) * ld + c];
   red[grp][c] = s;
   __syncthreads();
-  if (threadIdx.x < 64) mu[b * 64 + c] = (red[0][c] + red[1][c] + red[2][c] + red[3][c]) / static_cast<float>(N);
+  if (threadIdx.x < 64) atomicAdd(musum + b * 64 + c, red[0][c] + red[1][c] + red[2][c] + red[3][c]);
 }
 
 __global__ void knn_tc_prep_kernel(const float* __restrict__ rows, int ld, int N, int C4, int T,
@@ -64,12 +66,13 @@ __global__ void knn_tc_prep_kernel(const float* __restrict__ rows, int ld, int N
     for (int e = 0; e < 8; ++e) v[e] = 0.f;
     if (n < N && ch * 8 < C4) {
       const float* src = rows + (static_cast<size_t>(b) * N + n) * ld + ch * 8;
-      const float* m = mu + b * 64 + ch * 8;
+      const float* m = mu + b * 64 + ch * 8;       // channel sums; any value near the mean is a valid centre
+      const float inv_n = 1.0f / static_cast<float>(N);
       const float4 lo = *reinterpret_cast<const float4*>(src);
-      v[0] = lo.x - m[0]; v[1] = lo.y - m[1]; v[2] = lo.z - m[2]; v[3] = lo.w - m[3];
+      v[0] = lo.x - m[0] * inv_n; v[1] = lo.y - m[1] * inv_n; v[2] = lo.z - m[2] * inv_n; v[3] = lo.w - m[3] * inv_n;
       if (ch * 8 + 4 < C4) {
         const float4 hi = *reinterpret_cast<const float4*>(src + 4);
-        v[4] = hi.x - m[4]; v[5] = hi.y - m[5]; v[6] = hi.z - m[6]; v[7] = hi.w - m[7];
+        v[4] = hi.x - m[4] * inv_n; v[5] = hi.y - m[5] * inv_n; v[6] = hi.z - m[6] * inv_n; v[7] = hi.w - m[7] * inv_n;
       }
     }
     float sq = 0.f;
@@ -731,7 +734,8 @@ extern "C" int dgcnn_knn_tc_f32(const float* rows, int ld, int B, int C, int N, 
   float* mu = reinterpret_cast<float*>(ws + o_mu);
   unsigned int* maxnormc = reinterpret_cast<unsigned int*>(ws + o_maxc);
   DG_CUDA(cudaMemsetAsync(maxnormc, 0, static_cast<size_t>(B) * 4, st));
-  knn_tc_mean_kernel<<<B, 256, 0, st>>>(rows, ld, N, C4, mu);
+  DG_CUDA(cudaMemsetAsync(mu, 0, static_cast<size_t>(B) * 64 * 4, st));
+  knn_tc_mean_kernel<<<dim3(std::max(1, std::min(64, N / 256)), B), 256, 0, st>>>(rows, ld, N, C4, mu);
   DG_CUDA(cudaGetLastError());
   knn_tc_prep_kernel<<<dim3(std::min((T * 512 + 255) / 256, 4096), B), 256, 0, st>>>(rows, ld, N, C4, T, mu, tiles, normc, maxnormc);
   DG_CUDA(cudaGetLastError());
