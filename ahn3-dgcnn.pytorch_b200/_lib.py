@@ -14,7 +14,7 @@ class EdgeConvArgs(C.Structure):
     """mirror of `dgcnn_edgeconv_args`"""
     _fields_ = [("rows", c_void_p), ("ld", c_int), ("idx", c_void_p),
                 ("B", c_int), ("C", c_int), ("N", c_int), ("k", c_int),
-                ("w_a", c_void_p), ("w_b", c_void_p), ("out", c_void_p), ("ld_out", c_int)]
+                ("w_a", c_void_p), ("w_b", c_void_p), ("out", c_void_p), ("ld_out", c_int), ("v_scratch", c_void_p)]
 
 
 _P = c_void_p

@@ -582,6 +582,7 @@ static int fill_common(const dgcnn_edgeconv_args* a, EcK& p, const char* who) {
   p.num_tiles = (p.M + p.P - 1) / p.P;
   p.w_a = a->w_a; p.w_b = a->w_b; p.two = a->w_b != nullptr;
   p.out = a->out; p.ld_out = a->ld_out;
+  p.v_center = a->v_scratch;
   return DGCNN_OK;
 }
 
@@ -631,6 +632,8 @@ extern "C" int dgcnn_edgeconv_fwd_eval(const dgcnn_edgeconv_args* a, const float
   if ((rc = check_rows(a, "edgeconv_fwd_eval"))) return rc;
   DG_REQUIRE(a->out && aff_a && (!p.two || aff_b), DGCNN_E_INVALID, "edgeconv_fwd_eval: null pointer");
   p.aff_a = aff_a; p.aff_b = aff_b;
+  if (p.C == 64 && p.v_center && edgeconv_tc_enabled())
+    return launch_ec_tc_fwd(p, MODE_EVAL, persistent_grid(p.num_tiles), static_cast<cudaStream_t>(stream));
   return dispatch_cp<MODE_EVAL>(p, static_cast<cudaStream_t>(stream));
 }
 
@@ -645,7 +648,7 @@ extern "C" int dgcnn_edgeconv_conv_a_train(const dgcnn_edgeconv_args* a, float* 
              "edgeconv_conv_a_train: single-conv block needs the extrema outputs");
   p.y_a_out = y_a; p.partials = partials;
   p.ymax = ymax; p.ymin = ymin; p.amax = amax; p.amin = amin;
-  if (p.C == 64 && edgeconv_tc_enabled())
+  if (p.C == 64 && p.v_center && edgeconv_tc_enabled())
     return launch_ec_tc_fwd(p, MODE_TRAIN_A, persistent_grid(p.num_tiles), static_cast<cudaStream_t>(stream));
   return dispatch_cp<MODE_TRAIN_A>(p, static_cast<cudaStream_t>(stream));
 }

@@ -17,6 +17,7 @@ struct EcK {
   float* out; int ld_out;
   const float* aff_a; const float* aff_b;     // float[192]: mean | scale | beta
   float* y_a_out; const float* y_a_in;
+  float* v_center;                            // [M,64] scratch: hoisted centre term Wa2 x_i (tensor-core kernels)
   double* partials;
   float* ymax; float* ymin; uint8_t* amax; uint8_t* amin;
 };
@@ -25,7 +26,7 @@ __device__ __forceinline__ float bn_apply(float y, float mean, float scale, floa
   return __fmaf_rn(y - mean, scale, beta);
 }
 
-// tensor-core training-forward kernels (edgeconv_tc.cu); mode = MODE_TRAIN_A (needs C == 64) or MODE_TRAIN_B
+// tensor-core forward kernels (edgeconv_tc.cu); mode = MODE_EVAL / MODE_TRAIN_A (need C == 64 and v_center) or MODE_TRAIN_B
 int launch_ec_tc_fwd(const EcK& p, int mode, int grid, cudaStream_t st);
 int launch_ec_tc_bwd_b(const EcK& p, const float* g, const uint8_t* arg, const float* coef_b, float* dz_a,
                        float* dw_partials, int grid, cudaStream_t st);

@@ -6,8 +6,11 @@
 //     fly into three bf16 planes in the SWIZZLE_128B K-major layout (fence.proxy.async hands it to the tensor core);
 //   * the 64 x 64 weight is split once per CTA;
 //   * six kind::f16 MMAs per k16 step (bf16x3 split, FP32-accurate, see tc.cuh) — 24 MMAs per tile;
-//   * the epilogue reads TMEM (tcgen05.ld), adds the hoisted centre term, and parks the FP32 tile in shared memory
-//     (aliasing the A planes) for the column statistics, the coalesced y_a store and the max/min over k.
+//   * the epilogue reads TMEM (tcgen05.ld), adds the hoisted centre term (computed once per point by
+//     center_term_kernel), and parks the FP32 tile in shared memory (aliasing the A planes) for the column statistics,
+//     the coalesced y_a store and the max/min over k;
+//   * MODE_EVAL is the fully fused inference block: BN_a + LeakyReLU in the epilogue, H re-split into the A planes,
+//     conv_b as a second tcgen05 GEMM, BN_b + LeakyReLU, max over k — nothing per-edge touches HBM.
 // Two CTAs per SM overlap one CTA's gather/epilogue with the other's MMA.
 #include "edgeconv.cuh"
 #include "tc.cuh"
@@ -23,16 +26,37 @@ constexpr int kYs = 65;                // row stride of the FP32 tile parked ove
 
 struct EcTcSmem {
   static constexpr uint32_t a_off = 0;                       // 3 A planes, later the FP32 Y tile
-  static constexpr uint32_t w_off = 3 * kPlA;                // 3 weight planes
-  static constexpr uint32_t v_off = w_off + 3 * kPlW;        // Vs [16][64]
+  static constexpr uint32_t w_off = 3 * kPlA;                // 3 weight planes (conv_a: Wa1, conv_b: W_b)
+  static constexpr uint32_t w2_off = w_off + 3 * kPlW;       // 3 planes of W_b (fused inference kernel only)
+  static constexpr uint32_t v_off = w2_off + 3 * kPlW;       // Vs [16][64]: hoisted centre term Wa2 x_i of the tile's points
   static constexpr uint32_t xi_off = v_off + kMaxP * 64 * 4; // xis [16][64]
-  static constexpr uint32_t w2_off = xi_off + kMaxP * 64 * 4;   // Wa2 FP32 [64][68]
-  static constexpr uint32_t aff_off = w2_off + 64 * kLdH * 4;   // affine 192 floats
-  static constexpr uint32_t nbr_off = aff_off + 192 * 4;
+  static constexpr uint32_t aff_off = xi_off + kMaxP * 64 * 4;   // affine a | affine b (2 x 192 floats)
+  static constexpr uint32_t nbr_off = aff_off + 2 * 192 * 4;
   static constexpr uint32_t red_off = nbr_off + 128 * 4;        // [2][4][64] floats for the final statistics flush
   static constexpr uint32_t bar_off = red_off + 2 * 4 * 64 * 4;
   static constexpr uint32_t bytes = bar_off + 64;
 };
+
+// V[p][o] = sum_c Wa2[o][c] x[p][c]: the centre half of conv_a (w_a[:, 64:128]), once per point instead of once per edge
+__global__ void __launch_bounds__(256) center_term_kernel(const float* __restrict__ rows, int ld, int M,
+                                                          const float* __restrict__ w_a, float* __restrict__ V) {
+  __shared__ float Wt[64][65];      // [c][o]
+  __shared__ __align__(16) float xs[4][64];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 64 * 64; i += 256) Wt[i & 63][i >> 6] = w_a[static_cast<size_t>(i >> 6) * 128 + 64 + (i & 63)];
+  const int o = tid & 63, pl = tid >> 6;
+  for (int p0 = blockIdx.x * 4; p0 < M; p0 += gridDim.x * 4) {
+    __syncthreads();
+    if (p0 + pl < M) xs[pl][o] = rows[static_cast<size_t>(p0 + pl) * ld + o];
+    __syncthreads();
+    if (p0 + pl < M) {
+      float a = 0.f;
+#pragma unroll 16
+      for (int c = 0; c < 64; ++c) a = __fmaf_rn(Wt[c][o], xs[pl][c], a);
+      V[static_cast<size_t>(p0 + pl) * 64 + o] = a;
+    }
+  }
+}
 
 // 8 consecutive channels (chunk ch) of tile row r -> NP bf16 planes (x = x1 + x2 (+ x3)), swizzled.
 // Packed conversions: one cvt.rn.bf16x2 per pair and plane; the residual is exact in FP32.
@@ -64,10 +88,11 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
   unsigned char* Ap = sm + EcTcSmem::a_off;
   float* Ys = reinterpret_cast<float*>(sm + EcTcSmem::a_off);
   unsigned char* Wp = sm + EcTcSmem::w_off;
+  unsigned char* Wp2 = sm + EcTcSmem::w2_off;
   float* Vs = reinterpret_cast<float*>(sm + EcTcSmem::v_off);
   float* xis = reinterpret_cast<float*>(sm + EcTcSmem::xi_off);
-  float* Wa2s = reinterpret_cast<float*>(sm + EcTcSmem::w2_off);
   float* aff = reinterpret_cast<float*>(sm + EcTcSmem::aff_off);
+  float* affB = aff + 192;
   int* nbr = reinterpret_cast<int*>(sm + EcTcSmem::nbr_off);
   float* red = reinterpret_cast<float*>(sm + EcTcSmem::red_off);
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + EcTcSmem::bar_off);
@@ -84,8 +109,8 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
   if (warp == 0) tc::tmem_alloc(tmem_slot, 64);
   // weights: B operand rows = output channel, K = input channel.  conv_a uses Wa1 = w_a[:, 0:64]; conv_b uses w_b.
   {
-    const float* W = MODE == MODE_TRAIN_A ? p.w_a : p.w_b;
-    const int ldw = MODE == MODE_TRAIN_A ? 128 : 64;
+    const float* W = MODE == MODE_TRAIN_B ? p.w_b : p.w_a;
+    const int ldw = MODE == MODE_TRAIN_B ? 64 : 128;
     for (int i = tid; i < 64 * 8; i += kThreads) {
       const int o = i >> 3, ch = i & 7;
       float v[8];
@@ -93,9 +118,19 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
       for (int e = 0; e < 8; ++e) v[e] = W[static_cast<size_t>(o) * ldw + ch * 8 + e];
       store_split3(Wp, kPlW, o, ch, v);
     }
-    if (MODE == MODE_TRAIN_A)
-      for (int i = tid; i < 64 * 64; i += kThreads) Wa2s[(i >> 6) * kLdH + (i & 63)] = p.w_a[static_cast<size_t>(i >> 6) * 128 + 64 + (i & 63)];
-    if (tid < 192) aff[tid] = p.aff_a ? p.aff_a[tid] : 0.f;
+    if (MODE == MODE_EVAL && p.two) {
+      for (int i = tid; i < 64 * 8; i += kThreads) {
+        const int o = i >> 3, ch = i & 7;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = p.w_b[static_cast<size_t>(o) * 64 + ch * 8 + e];
+        store_split3(Wp2, kPlW, o, ch, v);
+      }
+    }
+    if (tid < 192) {
+      aff[tid] = p.aff_a ? p.aff_a[tid] : 0.f;
+      affB[tid] = p.aff_b ? p.aff_b[tid] : 0.f;
+    }
   }
   tc::fence_proxy_async();
   tc::fence_before_sync();
@@ -118,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
     const size_t e0 = static_cast<size_t>(gp0) * k;
     const int nvalid = min(P, M - gp0) * k;
     __syncthreads();  // S0: previous tile's Y tile / Vs / nbr fully consumed
-    if (MODE == MODE_TRAIN_A) {
+    if (MODE != MODE_TRAIN_B) {
       if (tid < kTileRows) {
         const int pp = tid / k, slot = tid - pp * k, gp = gp0 + pp;
         nbr[tid] = (pp < P && gp < M) ? (gp / p.N) * p.N + p.idx[static_cast<size_t>(gp) * k + slot] : -1;
@@ -127,6 +162,8 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
         const int pp = i >> 4, c4 = i & 15, gp = gp0 + pp;
         *reinterpret_cast<float4*>(xis + pp * 64 + 4 * c4) =
             gp < M ? *reinterpret_cast<const float4*>(p.rows + static_cast<size_t>(gp) * p.ld + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(Vs + pp * 64 + 4 * c4) =
+            gp < M ? *reinterpret_cast<const float4*>(p.v_center + static_cast<size_t>(gp) * 64 + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       __syncthreads();  // S1
     }
@@ -138,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
       for (int it = 0; it < 4; ++it) {
         const int i = tid + it * kThreads, row = i >> 3, ch = i & 7;
         const float* src;
-        if (MODE == MODE_TRAIN_A) {
+        if (MODE != MODE_TRAIN_B) {
           const int j = nbr[row];
           ok[it] = j >= 0;
           src = p.rows + static_cast<size_t>(max(j, 0)) * p.ld + ch * 8;
@@ -157,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
       for (int it = 0; it < 4; ++it) {
         const int i = tid + it * kThreads, row = i >> 3, ch = i & 7;
         float v[8] = {ra[it].x, ra[it].y, ra[it].z, ra[it].w, rb[it].x, rb[it].y, rb[it].z, rb[it].w};
-        if (MODE == MODE_TRAIN_A) {
+        if (MODE != MODE_TRAIN_B) {
           if (ok[it]) {
             const float* xi = xis + (row / k) * 64 + ch * 8;
             const float4 c = *reinterpret_cast<const float4*>(xi), d = *reinterpret_cast<const float4*>(xi + 4);
@@ -174,23 +211,6 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
         store_split3(Ap, kPlA, row, ch, v);
       }
     }
-    if (MODE == MODE_TRAIN_A) {
-      // hoisted centre term V[p] = Wa2 x_i
-      for (int i = tid; i < P * kCout; i += kThreads) {
-        const int pp = i >> 6, o = i & 63;
-        float a = 0.f;
-#pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
-          const float4 w = *reinterpret_cast<const float4*>(Wa2s + o * kLdH + 4 * c4);
-          const float4 x = *reinterpret_cast<const float4*>(xis + pp * 64 + 4 * c4);
-          a = __fmaf_rn(w.x, x.x, a);
-          a = __fmaf_rn(w.y, x.y, a);
-          a = __fmaf_rn(w.z, x.z, a);
-          a = __fmaf_rn(w.w, x.w, a);
-        }
-        Vs[i] = a;
-      }
-    }
     tc::fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core
     __syncthreads();                   // S2
     if (tid == 0) {
@@ -203,7 +223,49 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
     phase ^= 1;
     tc::fence_after_sync();
     // ---- epilogue: TMEM -> FP32 tile in smem (over the A planes, which the MMA has finished reading) ------------
-    {
+    if (MODE == MODE_EVAL) {
+      // fused inference block: BN_a + LeakyReLU [-> conv_b on the tensor cores -> BN_b + LeakyReLU] -> max over k
+      float v[32];
+      tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + half * 32, v);
+      const float* vr = Vs + erp * kCout + half * 32;
+      const bool valid = erow < nvalid;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int col = half * 32 + i;
+        v[i] = valid ? lrelu(bn_apply(v[i] + vr[i], aff[col], aff[64 + col], aff[128 + col])) : 0.f;
+      }
+      if (p.two) {
+        tc::fence_before_sync();
+        __syncthreads();               // every warp has drained the accumulator; the A planes can be overwritten with H
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          float h[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) h[e] = v[c8 * 8 + e];
+          store_split3(Ap, kPlA, erow, half * 4 + c8, h);
+        }
+        tc::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+          tc::fence_after_sync();
+          tc::mma_split_katom<3>(taddr, tc::smem_u32(Ap), kPlA, tc::smem_u32(Wp2), kPlW, idesc, true);
+          tc::mma_commit(bar);
+        }
+        __syncwarp();
+        tc::mbar_wait(bar, phase);
+        phase ^= 1;
+        tc::fence_after_sync();
+        tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + half * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int col = half * 32 + i;
+          v[i] = lrelu(bn_apply(v[i], affB[col], affB[64 + col], affB[128 + col]));
+        }
+      }
+      float* dst = Ys + erow * kYs + half * 32;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) dst[i] = v[i];
+    } else {
       float v[32];
       tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + half * 32, v);
       float* dst = Ys + erow * kYs + half * 32;
@@ -218,6 +280,17 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
     }
     tc::fence_before_sync();
     __syncthreads();                   // S3: Y tile complete
+    if (MODE == MODE_EVAL) {
+      for (int i = tid; i < P * kCout; i += kThreads) {
+        const int pp = i >> 6, c = i & 63, gp = gp0 + pp;
+        if (gp < M) {
+          float m = Ys[(pp * k) * kYs + c];
+          for (int s2 = 1; s2 < k; ++s2) m = fmaxf(m, Ys[(pp * k + s2) * kYs + c]);
+          p.out[static_cast<size_t>(gp) * p.ld_out + c] = m;
+        }
+      }
+      continue;
+    }
     // ---- batch statistics of the raw conv output (valid rows only) ----------------------------------------------
     {
       const int r_lo = sg * 32, r_hi = min(r_lo + 32, nvalid);
@@ -529,12 +602,19 @@ int launch_ec_tc_bwd_b(const EcK& p, const float* g, const uint8_t* arg, const f
 }
 
 int launch_ec_tc_fwd(const EcK& p, int mode, int grid, cudaStream_t st) {
+  if (mode != MODE_TRAIN_B) {
+    center_term_kernel<<<std::max(1, std::min((p.M + 3) / 4, 148 * 8)), 256, 0, st>>>(p.rows, p.ld, p.M, p.w_a, p.v_center);
+    DG_CUDA(cudaGetLastError());
+  }
   if (mode == MODE_TRAIN_A) {
     DG_CUDA(cudaFuncSetAttribute(ec_tc_fwd_kernel<MODE_TRAIN_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcTcSmem::bytes)));
     ec_tc_fwd_kernel<MODE_TRAIN_A><<<grid, kThreads, EcTcSmem::bytes, st>>>(p);
-  } else {
+  } else if (mode == MODE_TRAIN_B) {
     DG_CUDA(cudaFuncSetAttribute(ec_tc_fwd_kernel<MODE_TRAIN_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcTcSmem::bytes)));
     ec_tc_fwd_kernel<MODE_TRAIN_B><<<grid, kThreads, EcTcSmem::bytes, st>>>(p);
+  } else {
+    DG_CUDA(cudaFuncSetAttribute(ec_tc_fwd_kernel<MODE_EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcTcSmem::bytes)));
+    ec_tc_fwd_kernel<MODE_EVAL><<<grid, kThreads, EcTcSmem::bytes, st>>>(p);
   }
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;

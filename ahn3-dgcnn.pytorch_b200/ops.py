@@ -289,9 +289,15 @@ class BNState:
     momentum: float = 0.1
 
 
-def _args(rows, ld, idx, B, Cn, N, k, w_a, w_b, out, ld_out):
+def _args(rows, ld, idx, B, Cn, N, k, w_a, w_b, out, ld_out, v_scratch=None):
     return _lib.EdgeConvArgs(rows.data_ptr(), ld, idx.data_ptr(), B, Cn, N, k, w_a.data_ptr(),
-                             0 if w_b is None else w_b.data_ptr(), 0 if out is None else out.data_ptr(), ld_out)
+                             0 if w_b is None else w_b.data_ptr(), 0 if out is None else out.data_ptr(), ld_out,
+                             0 if v_scratch is None else v_scratch.data_ptr())
+
+
+def _v_scratch(B: int, Cn: int, N: int, dev) -> Optional[torch.Tensor]:
+    """Scratch for the per-point centre term; its presence switches the 64-channel blocks to the tensor-core kernels."""
+    return torch.empty(B * N, COUT, dtype=torch.float32, device=dev) if Cn == COUT else None
 
 
 def eval_affine(gamma: torch.Tensor, beta: torch.Tensor, bn: BNState) -> torch.Tensor:
@@ -308,7 +314,8 @@ def edgeconv_eval(rows: torch.Tensor, idx: torch.Tensor, B: int, Cn: int, N: int
     out = torch.empty(B * N, COUT, dtype=torch.float32, device=rows.device)
     wa = w_a.detach().reshape(COUT, -1).contiguous()
     wb = None if w_b is None else w_b.detach().reshape(COUT, COUT).contiguous()
-    a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, out, COUT)
+    vs = _v_scratch(B, Cn, N, rows.device)
+    a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, out, COUT, vs)
     _call("dgcnn_edgeconv_fwd_eval", C.byref(a), _ptr(aff_a), _ptr(aff_b), _stream())
     return out
 
@@ -342,7 +349,8 @@ class EdgeConvTrain(torch.autograd.Function):
         ysel = torch.empty(M, COUT, **f32)
         arg = torch.empty(M, COUT, dtype=torch.uint8, device=dev)
         stat_a = torch.empty(2 + 3, COUT, **f32)     # mean, rstd, affine(mean|scale|beta)
-        a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, None, COUT)
+        vs = _v_scratch(B, Cn, N, dev)
+        a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, None, COUT, vs)
 
         _call("dgcnn_edgeconv_conv_a_train", C.byref(a), _ptr(y_a), _ptr(partials), _ptr(ymax), _ptr(ymin),
                                                    _ptr(amax), _ptr(amin), st)

@@ -87,6 +87,8 @@ typedef struct dgcnn_edgeconv_args {
   const float* w_b;       /* [64, 64] or NULL                                                         */
   float* out;             /* [B*N, 64] block output, row stride ld_out                                */
   int ld_out;
+  float* v_scratch;       /* optional float[B*N*64] scratch: enables the tensor-core kernels for C == 64
+                             (holds the per-point centre term Wa2 x_i); NULL selects the FP32-FMA kernels   */
 } dgcnn_edgeconv_args;
 
 /* BN "affine" vectors are float[192] = mean[64] | scale[64] | beta[64]; the kernels apply
