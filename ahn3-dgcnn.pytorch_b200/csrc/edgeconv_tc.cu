@@ -327,16 +327,18 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
   }
   // ---- per-CTA statistics -> partials ---------------------------------------------------------------------------------
   __syncthreads();
-  red[(0 * 4 + sg) * 64 + sc] = t1;
-  red[(1 * 4 + sg) * 64 + sc] = t2;
-  __syncthreads();
-  if (tid < 128) {
-    const int w = tid >> 6, c = tid & 63;
-    const double s = ((static_cast<double>(red[(w * 4 + 0) * 64 + c]) + red[(w * 4 + 1) * 64 + c]) + red[(w * 4 + 2) * 64 + c]) +
-                     red[(w * 4 + 3) * 64 + c];
-    p.partials[128 + static_cast<size_t>(blockIdx.x) * 128 + tid] = s;
+  if (MODE != MODE_EVAL) {
+    red[(0 * 4 + sg) * 64 + sc] = t1;
+    red[(1 * 4 + sg) * 64 + sc] = t2;
+    __syncthreads();
+    if (tid < 128) {
+      const int w = tid >> 6, c = tid & 63;
+      const double s = ((static_cast<double>(red[(w * 4 + 0) * 64 + c]) + red[(w * 4 + 1) * 64 + c]) + red[(w * 4 + 2) * 64 + c]) +
+                       red[(w * 4 + 3) * 64 + c];
+      p.partials[128 + static_cast<size_t>(blockIdx.x) * 128 + tid] = s;
+    }
+    if (blockIdx.x == 0 && tid == 0) p.partials[0] = static_cast<double>(gridDim.x);
   }
-  if (blockIdx.x == 0 && tid == 0) p.partials[0] = static_cast<double>(gridDim.x);
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(taddr, 64);
