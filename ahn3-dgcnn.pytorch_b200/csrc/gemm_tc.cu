@@ -294,9 +294,17 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ P, size_t split_s
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const size_t r = i / N, c = i % N;
-    float acc = 0.f;
-    for (int z = 0; z < splits; ++z) acc += P[z * split_stride + r * N + c];
-    D[r * ldd + c] = acc;
+    // fixed summation order (deterministic); four independent chains hide the load latency
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int z = 0;
+    for (; z + 4 <= splits; z += 4) {
+      a0 += P[(z + 0) * split_stride + i];
+      a1 += P[(z + 1) * split_stride + i];
+      a2 += P[(z + 2) * split_stride + i];
+      a3 += P[(z + 3) * split_stride + i];
+    }
+    for (; z < splits; ++z) a0 += P[z * split_stride + i];
+    D[r * ldd + c] = (a0 + a1) + (a2 + a3);
   }
 }
 
@@ -435,13 +443,24 @@ __global__ void segmax_finalize_kernel(const float* __restrict__ A, long long a_
   const uint32_t u = static_cast<uint32_t>(key >> 32);
   const float sgn = gamma[c] < 0.f ? -1.f : 1.f;
   const float y = sgn * __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
-  const int row = static_cast<int>(key & 0xFFFFFFFFull) * 32 + lane;
-  float d = -INFINITY;
-  if (row < M && row / seg_len == b) {
-    float acc = 0.f;
-    for (int kk = 0; kk < K; ++kk) acc = __fmaf_rn(A[row * a_sr + kk * a_sc], Bw[c * b_sr + kk * b_sc], acc);
-    d = -fabsf(acc - y);                       // the row whose value reproduces the recorded extremum best
+  const int row0 = static_cast<int>(key & 0xFFFFFFFFull) * 32;
+  // dot products of the 32 candidate rows with weight row c: lane = slice of k (coalesced loads), then a transpose-
+  // reduce leaves row r's dot product in lane r
+  float part[32];
+#pragma unroll
+  for (int r = 0; r < 32; ++r) part[r] = 0.f;
+  for (int kk = lane; kk < K; kk += 32) {
+    const float w = Bw[c * b_sr + kk * b_sc];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const int rr = min(row0 + r, M - 1);
+      part[r] = __fmaf_rn(A[rr * a_sr + kk * a_sc], w, part[r]);
+    }
   }
+  warp_transpose_sum(part, lane);
+  const int row = row0 + lane;
+  float d = -INFINITY;
+  if (row < M && row / seg_len == b) d = -fabsf(part[0] - y);   // the row whose value reproduces the recorded extremum best
   float best = d;
   int bl = lane;
 #pragma unroll

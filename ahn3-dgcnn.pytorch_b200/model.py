@@ -182,5 +182,5 @@ class DGCNN(nn.Module):
         h8 = self._dense(h7, 8)
         if depth == 9:
             return self._bcn(h8, B, N)
-        logits = self.dp1(h8) @ self.conv9.weight.squeeze(-1).t()          # [M,classes]
+        logits = ops.linear(self.dp1(h8), self.conv9.weight.squeeze(-1))   # [M,classes]
         return self._bcn(logits, B, N)
