@@ -35,7 +35,8 @@ int num_sms();
   } while (0)
 
 // ---- device helpers -----------------------------------------------------------------------------
-__device__ __forceinline__ float lrelu(float z) { return z > 0.f ? z : kSlope * z; }
+// slope < 1: max(z, slope z) is z for z > 0 and slope z otherwise, bit for bit (also for +-0 and NaN); one FMUL + one FMNMX
+__device__ __forceinline__ float lrelu(float z) { return fmaxf(z, kSlope * z); }
 __device__ __forceinline__ float lrelu_grad(float z) { return z > 0.f ? 1.f : kSlope; }
 
 // Order-preserving map float -> uint32 (larger float => larger uint).

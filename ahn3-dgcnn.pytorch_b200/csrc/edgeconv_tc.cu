@@ -12,17 +12,13 @@
 //   * MODE_EVAL is the fully fused inference block: BN_a + LeakyReLU in the epilogue, H re-split into the A planes,
 //     conv_b as a second tcgen05 GEMM, BN_b + LeakyReLU, max over k — nothing per-edge touches HBM.
 // Two CTAs per SM overlap one CTA's gather/epilogue with the other's MMA.
-#include "edgeconv.cuh"
-#include "tc.cuh"
+#include "ec_tc_common.cuh"
 
 namespace dg {
 
-static int g_edgeconv_tc = 1;
+static int g_edgeconv_tc = 2;
 bool edgeconv_tc_enabled() { return g_edgeconv_tc != 0; }
-
-constexpr uint32_t kPlA = 128 * 128;   // bytes of one A plane (128 rows x 64 bf16)
-constexpr uint32_t kPlW = 64 * 128;    // bytes of one weight plane
-constexpr int kYs = 65;                // row stride of the FP32 tile parked over the A planes
+int edgeconv_tc_mode() { return g_edgeconv_tc; }
 
 struct EcTcSmem {
   static constexpr uint32_t a_off = 0;                       // 3 A planes, later the FP32 Y tile
@@ -56,30 +52,6 @@ __global__ void __launch_bounds__(256) center_term_kernel(const float* __restric
       V[static_cast<size_t>(p0 + pl) * 64 + o] = a;
     }
   }
-}
-
-// 8 consecutive channels (chunk ch) of tile row r -> NP bf16 planes (x = x1 + x2 (+ x3)), swizzled.
-// Packed conversions: one cvt.rn.bf16x2 per pair and plane; the residual is exact in FP32.
-template <int NP>
-__device__ __forceinline__ void store_split(unsigned char* planes, uint32_t plane_bytes, int r, int ch, float (&v)[8]) {
-  const uint32_t off = static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>((ch ^ (r & 7)) & 7) << 4);
-#pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    __nv_bfloat162 h[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-      if (p + 1 < NP) {
-        const float2 f = __bfloat1622float2(h[e]);
-        v[2 * e] -= f.x;
-        v[2 * e + 1] -= f.y;
-      }
-    }
-    *reinterpret_cast<uint4*>(planes + p * plane_bytes + off) = *reinterpret_cast<const uint4*>(h);
-  }
-}
-__device__ __forceinline__ void store_split3(unsigned char* planes, uint32_t plane_bytes, int r, int ch, float (&v)[8]) {
-  store_split<3>(planes, plane_bytes, r, ch, v);
 }
 
 template <int MODE>
@@ -367,26 +339,6 @@ struct EcTcBwdSmem {
   static constexpr uint32_t bytes = bar_off + 64;
 };
 
-__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t saddr, uint32_t lbo) {
-  const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16);
-  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-  return (static_cast<uint64_t>(hi) << 32) | lo;
-}
-
-// column sums over the 32 lanes of a warp for 32 per-lane values: afterwards v[0] of lane l is the sum of column l
-__device__ __forceinline__ void warp_transpose_reduce(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float send = up ? v[i] : v[i + s];
-      const float keep = up ? v[i + s] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-}
-
 __global__ void __launch_bounds__(kThreads, 2)
 ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __restrict__ arg,
                    const float* __restrict__ coef_b, float* __restrict__ dz_a, float* __restrict__ dw_partials) {
@@ -443,6 +395,11 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
     const size_t e0 = static_cast<size_t>(gp0) * k;
     const int nvalid = min(P, M - gp0) * k;
     __syncthreads();  // S0
+    if (tid == 0 && tile + static_cast<int>(gridDim.x) < p.num_tiles) {      // DRAM -> L2 prefetch of this CTA's next y_a tile
+      const size_t e2 = static_cast<size_t>(tile + gridDim.x) * P * k;
+      const size_t rows_left = static_cast<size_t>(M) * k - e2;
+      tc::prefetch_l2(p.y_a_in + e2 * kCout, static_cast<uint32_t>(min(rows_left, static_cast<size_t>(P) * k) * kCout * 4));
+    }
     for (int i = tid; i < P * kCout; i += kThreads) {
       const int gp = gp0 + (i >> 6);
       const bool ok = gp < M;
@@ -608,6 +565,7 @@ int launch_ec_tc_fwd(const EcK& p, int mode, int grid, cudaStream_t st) {
     center_term_kernel<<<std::max(1, std::min((p.M + 3) / 4, 148 * 8)), 256, 0, st>>>(p.rows, p.ld, p.M, p.w_a, p.v_center);
     DG_CUDA(cudaGetLastError());
   }
+  if (mode != MODE_EVAL && g_edgeconv_tc >= 2) return launch_ec_pipe_fwd(p, mode, (grid + 1) / 2, st);
   if (mode == MODE_TRAIN_A) {
     DG_CUDA(cudaFuncSetAttribute(ec_tc_fwd_kernel<MODE_TRAIN_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcTcSmem::bytes)));
     ec_tc_fwd_kernel<MODE_TRAIN_A><<<grid, kThreads, EcTcSmem::bytes, st>>>(p);

@@ -122,8 +122,9 @@ int dgcnn_bn_finalize(const double* partials, int C, double count, const float* 
 int dgcnn_edgeconv_select(int M, const float* ymax, const float* ymin, const uint8_t* amax, const uint8_t* amin,
                           const float* affine, float* out, int ld_out, float* ysel, uint8_t* arg, void* stream);
 
-/* Select the implementation of the 64-channel EdgeConv training passes: 1 (default) = tcgen05 tensor cores with the
- * FP32-accurate bf16x3 split, 0 = FP32 FMA.  Returns the previous setting.  Process-wide; for A/B checks.   */
+/* Select the implementation of the 64-channel EdgeConv passes: 2 (default) = warp-specialised, pipelined tcgen05
+ * kernels (training passes; inference uses the serial tcgen05 kernel), 1 = serial tcgen05 kernels, 0 = FP32 FMA.
+ * The tensor-core paths use the FP32-accurate bf16x3 split.  Returns the previous setting.  Process-wide; for A/B checks. */
 int dgcnn_set_edgeconv_tc(int enabled);
 
 /* Training backward (dense because of batch-stat BN; SURVEY.md §7 hard part 3).  Sequence:
