@@ -61,10 +61,23 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 // mbarrier wait with a watchdog: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
 // (nanosleep back-off was measured slower: the hand-overs of the pipelined kernels are latency-critical.)
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(tc::smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
-  while (!tc::mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {      // suspended in hardware until the phase flips (or 20 us pass)
+    if (++spins > (1u << 20)) __trap();
   }
 }
 // 256-bit global store (sm_100): 8 consecutive floats, 32-byte aligned

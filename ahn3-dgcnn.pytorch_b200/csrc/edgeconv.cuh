@@ -31,8 +31,8 @@ int launch_ec_tc_fwd(const EcK& p, int mode, int grid, cudaStream_t st);
 int launch_ec_tc_bwd_b(const EcK& p, const float* g, const uint8_t* arg, const float* coef_b, float* dz_a,
                        float* dw_partials, int grid, cudaStream_t st);
 bool edgeconv_tc_enabled();
-int edgeconv_tc_mode();       // 0 = FFMA kernels, 1 = serial tensor-core kernels, 2 = warp-specialised pipelined kernels (default)
-// pipelined training passes (edgeconv_pipe.cu); one CTA per SM
-int launch_ec_pipe_fwd(const EcK& p, int mode, int sms, cudaStream_t st);
+int edgeconv_tc_mode();       // 0 = FFMA kernels, 1 = serial tensor-core kernels, 2 = 1 + warp-specialised pipelined conv_b (default)
+// pipelined conv_b training pass (edgeconv_pipe.cu); one CTA per SM
+int launch_ec_pipe_conv_b(const EcK& p, int sms, cudaStream_t st);
 
 }  // namespace dg

@@ -565,7 +565,9 @@ int launch_ec_tc_fwd(const EcK& p, int mode, int grid, cudaStream_t st) {
     center_term_kernel<<<std::max(1, std::min((p.M + 3) / 4, 148 * 8)), 256, 0, st>>>(p.rows, p.ld, p.M, p.w_a, p.v_center);
     DG_CUDA(cudaGetLastError());
   }
-  if (mode != MODE_EVAL && g_edgeconv_tc >= 2) return launch_ec_pipe_fwd(p, mode, (grid + 1) / 2, st);
+  // conv_b streams a contiguous tile: the warp-specialised pipeline wins there.  conv_a is bound by the L2 gather and
+  // shared-memory bandwidth either way and runs faster as two serial CTAs per SM.
+  if (mode == MODE_TRAIN_B && g_edgeconv_tc >= 2) return launch_ec_pipe_conv_b(p, (grid + 1) / 2, st);
   if (mode == MODE_TRAIN_A) {
     DG_CUDA(cudaFuncSetAttribute(ec_tc_fwd_kernel<MODE_TRAIN_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcTcSmem::bytes)));
     ec_tc_fwd_kernel<MODE_TRAIN_A><<<grid, kThreads, EcTcSmem::bytes, st>>>(p);

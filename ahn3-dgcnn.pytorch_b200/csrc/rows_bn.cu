@@ -1,0 +1,256 @@
+// rows_bn.cu — BatchNorm1d (+ optional per-block bias) + LeakyReLU over point-major rows [M, C], forward and backward.
+//
+// Used by the shared-MLP head (reference model.py:131-139,176-187: conv7/conv8 -> bn7/bn8 -> LeakyReLU).  The library
+// composition (add, batch_norm stats, transform, leaky_relu; backward: leaky_relu_backward, bn reduce, bn elemt) makes
+// 5 + 8 passes over the [M, C] activations; these kernels make 2 + 2 (+1 for the per-block bias gradient):
+//   forward   pass 1: per-CTA column sums of v = y + bias[block] and v^2  -> FP64 partials -> mean / rstd / running stats
+//             pass 2: h = LReLU((v - mean) * gamma * rstd + beta)
+//   backward  pass 1: dz = dh * LReLU'(z(v)); per-CTA column sums of dz and dz * vhat -> dgamma, dbeta
+//             pass 2: dy = gamma * rstd * (dz - mean(dz) - vhat * mean(dz * vhat))
+// All reductions are per-CTA partials in a fixed order (deterministic), finished in FP64.
+// HBM-bound streaming kernels: 16-byte accesses, a warp covers 512 contiguous bytes of a row.
+#include "common.cuh"
+
+namespace dg {
+
+constexpr int kRbThreads = 256;
+constexpr int kRbMaxCtas = 1184;          // 148 SMs x 8
+
+struct RowsBn {
+  const float* y; int M, C, N;            // rows, channels, points per block (bias row = row / N)
+  const float* bias;                      // [M / N, C] or null
+  const float* a;                         // float[3C]: mean | scale | beta
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// thread -> float4 column group cg = tid % (C/4), row lane rl = tid / (C/4); CTA b owns rows [b*rpc, (b+1)*rpc)
+template <bool BWD>
+__global__ void __launch_bounds__(kRbThreads) rows_bn_reduce_kernel(RowsBn p, const float* __restrict__ dh, int rows_per_cta,
+                                                                   double* __restrict__ partials) {
+  __shared__ float4 red[2][kRbThreads];
+  const int c4n = p.C >> 2, RL = kRbThreads / c4n;
+  const int cg = threadIdx.x % c4n, rl = threadIdx.x / c4n;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(p.M, r0 + rows_per_cta);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+  float4 mean = s, scale = s, beta = s;
+  if (BWD) {
+    mean = ld4(p.a + 4 * cg);
+    scale = ld4(p.a + p.C + 4 * cg);
+    beta = ld4(p.a + 2 * p.C + 4 * cg);
+  }
+  for (int r = r0 + rl; r < r1; r += RL) {
+    float4 v = ld4(p.y + static_cast<size_t>(r) * p.C + 4 * cg);
+    if (p.bias) {
+      const float4 b = ld4(p.bias + static_cast<size_t>(r / p.N) * p.C + 4 * cg);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (!BWD) {
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      q.x = __fmaf_rn(v.x, v.x, q.x); q.y = __fmaf_rn(v.y, v.y, q.y); q.z = __fmaf_rn(v.z, v.z, q.z); q.w = __fmaf_rn(v.w, v.w, q.w);
+    } else {
+      // s = sum dz, q = sum dz * (v - mean)   (the factor rstd of vhat is applied once in the finalize kernel)
+      const float4 g = ld4(dh + static_cast<size_t>(r) * p.C + 4 * cg);
+      const float dx = v.x - mean.x, dy = v.y - mean.y, dzc = v.z - mean.z, dw = v.w - mean.w;
+      const float gx = g.x * lrelu_grad(__fmaf_rn(dx, scale.x, beta.x)), gy = g.y * lrelu_grad(__fmaf_rn(dy, scale.y, beta.y));
+      const float gz = g.z * lrelu_grad(__fmaf_rn(dzc, scale.z, beta.z)), gw = g.w * lrelu_grad(__fmaf_rn(dw, scale.w, beta.w));
+      s.x += gx; s.y += gy; s.z += gz; s.w += gw;
+      q.x = __fmaf_rn(gx, dx, q.x); q.y = __fmaf_rn(gy, dy, q.y); q.z = __fmaf_rn(gz, dzc, q.z); q.w = __fmaf_rn(gw, dw, q.w);
+    }
+  }
+  red[0][threadIdx.x] = s;
+  red[1][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.x < c4n) {
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int l = 0; l < RL; ++l) {           // fixed order over the row lanes
+      const float4 a = red[0][l * c4n + cg], b = red[1][l * c4n + cg];
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    double* dst = partials + static_cast<size_t>(blockIdx.x) * 2 * p.C;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      dst[4 * cg + e] = acc[e];
+      dst[p.C + 4 * cg + e] = acc[4 + e];
+    }
+  }
+}
+
+// one warp per channel: lane l sums partials l, l+32, ... then a fixed shuffle tree (deterministic), all in FP64
+__device__ __forceinline__ void rows_bn_sum_partials(const double* __restrict__ partials, int nparts, int C, int c, double& s, double& q) {
+  const int lane = threadIdx.x & 31;
+  s = 0.0; q = 0.0;
+  for (int i = lane; i < nparts; i += 32) {
+    s += partials[static_cast<size_t>(i) * 2 * C + c];
+    q += partials[static_cast<size_t>(i) * 2 * C + C + c];
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+}
+
+__global__ void __launch_bounds__(256) rows_bn_fwd_finalize_kernel(const double* __restrict__ partials, int nparts, int C, double count,
+                                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                            float momentum, float* running_mean, float* running_var, float* __restrict__ mean,
+                                            float* __restrict__ rstd, float* __restrict__ aff) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double s, q;
+  rows_bn_sum_partials(partials, nparts, C, c, s, q);
+  if (threadIdx.x & 31) return;
+  const double m = s / count;
+  double var = q / count - m * m;
+  if (var < 0.0) var = 0.0;
+  const double rs = 1.0 / sqrt(var + static_cast<double>(eps));
+  mean[c] = static_cast<float>(m);
+  rstd[c] = static_cast<float>(rs);
+  aff[c] = static_cast<float>(m);
+  aff[C + c] = static_cast<float>(static_cast<double>(gamma[c]) * rs);
+  aff[2 * C + c] = beta[c];
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = static_cast<float>((1.0 - momentum) * running_mean[c] + momentum * m);
+    running_var[c] = static_cast<float>((1.0 - momentum) * running_var[c] + momentum * unbiased);
+  }
+}
+
+// inference: affine from the running statistics
+__global__ void rows_bn_eval_affine_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                           const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                           float* __restrict__ aff) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  aff[c] = running_mean[c];
+  aff[C + c] = gamma[c] * rsqrtf(running_var[c] + eps);
+  aff[2 * C + c] = beta[c];
+}
+
+// coef = [kA | kB | kC] with dy = kA * dz - kB - kC * (v - mean):   kA = gamma rstd, kB = kA * s1 / M, kC = kA * rstd^2 * s2 / M
+__global__ void __launch_bounds__(256) rows_bn_bwd_finalize_kernel(const double* __restrict__ partials, int nparts, int C, double count,
+                                            const float* __restrict__ gamma, const float* __restrict__ rstd,
+                                            float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double s1, s2;
+  rows_bn_sum_partials(partials, nparts, C, c, s1, s2);
+  if (threadIdx.x & 31) return;
+  const double rs = rstd[c], kA = static_cast<double>(gamma[c]) * rs;
+  dbeta[c] = static_cast<float>(s1);
+  dgamma[c] = static_cast<float>(s2 * rs);                  // sum dz * vhat
+  coef[c] = static_cast<float>(kA);
+  coef[C + c] = static_cast<float>(kA * s1 / count);
+  coef[2 * C + c] = static_cast<float>(kA * rs * rs * s2 / count);
+}
+
+// BWD = false: out = LReLU((v - mean) scale + beta);   BWD = true: out = kA dz - kB - kC (v - mean)
+template <bool BWD>
+__global__ void __launch_bounds__(kRbThreads) rows_bn_apply_kernel(RowsBn p, const float* __restrict__ dh,
+                                                                  const float* __restrict__ coef, float* __restrict__ out) {
+  const int c4n = p.C >> 2, RL = kRbThreads / c4n;
+  const int cg = threadIdx.x % c4n, rl = threadIdx.x / c4n;
+  const float4 mean = ld4(p.a + 4 * cg), scale = ld4(p.a + p.C + 4 * cg), beta = ld4(p.a + 2 * p.C + 4 * cg);
+  float4 kA = mean, kB = mean, kC = mean;
+  if (BWD) {
+    kA = ld4(coef + 4 * cg);
+    kB = ld4(coef + p.C + 4 * cg);
+    kC = ld4(coef + 2 * p.C + 4 * cg);
+  }
+  for (int r = blockIdx.x * RL + rl; r < p.M; r += gridDim.x * RL) {
+    const size_t off = static_cast<size_t>(r) * p.C + 4 * cg;
+    float4 v = ld4(p.y + off);
+    if (p.bias) {
+      const float4 b = ld4(p.bias + static_cast<size_t>(r / p.N) * p.C + 4 * cg);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    const float dx = v.x - mean.x, dy = v.y - mean.y, dz = v.z - mean.z, dw = v.w - mean.w;
+    const float zx = __fmaf_rn(dx, scale.x, beta.x), zy = __fmaf_rn(dy, scale.y, beta.y);
+    const float zz = __fmaf_rn(dz, scale.z, beta.z), zw = __fmaf_rn(dw, scale.w, beta.w);
+    float4 o;
+    if (!BWD) {
+      o = make_float4(lrelu(zx), lrelu(zy), lrelu(zz), lrelu(zw));
+    } else {
+      const float4 g = ld4(dh + off);
+      o.x = kA.x * (g.x * lrelu_grad(zx)) - kB.x - kC.x * dx;
+      o.y = kA.y * (g.y * lrelu_grad(zy)) - kB.y - kC.y * dy;
+      o.z = kA.z * (g.z * lrelu_grad(zz)) - kB.z - kC.z * dz;
+      o.w = kA.w * (g.w * lrelu_grad(zw)) - kB.w - kC.w * dw;
+    }
+    *reinterpret_cast<float4*>(out + off) = o;
+  }
+}
+
+static bool rows_bn_shape_ok(int C) { return C == 64 || C == 128 || C == 256 || C == 512 || C == 1024; }
+
+static int rows_bn_grid(int M, int* rows_per_cta) {
+  const int sms = std::max(1, num_sms());
+  int ctas = std::max(1, std::min(std::min(M, sms * 8), kRbMaxCtas));
+  *rows_per_cta = (M + ctas - 1) / ctas;
+  return (M + *rows_per_cta - 1) / *rows_per_cta;
+}
+
+static int rows_bn_apply_grid(int M, int C) {
+  const int RL = kRbThreads / (C / 4);
+  return std::max(1, std::min((M + RL - 1) / RL, std::max(1, num_sms()) * 8));
+}
+
+}  // namespace dg
+
+using namespace dg;
+
+extern "C" int dgcnn_rows_bn_supported(int C) { return rows_bn_shape_ok(C) ? 1 : 0; }
+
+extern "C" size_t dgcnn_rows_bn_workspace_bytes(int C) {
+  return (static_cast<size_t>(kRbMaxCtas) * 2 * C) * sizeof(double) + 3 * static_cast<size_t>(C) * sizeof(float);
+}
+
+extern "C" int dgcnn_rows_bn_lrelu_fwd(const float* y, int M, int C, const float* bias, int N, const float* gamma,
+                                       const float* beta, float eps, float momentum, int use_batch_stats,
+                                       float* running_mean, float* running_var, float* mean, float* rstd, float* aff,
+                                       float* h, void* workspace, size_t workspace_bytes, void* stream) {
+  DG_REQUIRE(y && gamma && beta && aff && h && workspace, DGCNN_E_INVALID, "rows_bn_lrelu_fwd: null pointer");
+  DG_REQUIRE(rows_bn_shape_ok(C), DGCNN_E_UNSUPPORTED, "rows_bn_lrelu_fwd: C must be 64, 128, 256, 512 or 1024");
+  DG_REQUIRE(M > 0 && N > 0 && (!bias || M % N == 0), DGCNN_E_INVALID, "rows_bn_lrelu_fwd: bad shape");
+  DG_REQUIRE(workspace_bytes >= dgcnn_rows_bn_workspace_bytes(C), DGCNN_E_INVALID, "rows_bn_lrelu_fwd: workspace too small");
+  DG_REQUIRE(use_batch_stats ? (mean && rstd && (!running_mean == !running_var)) : (running_mean && running_var),
+             DGCNN_E_INVALID, "rows_bn_lrelu_fwd: statistics buffers missing");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RowsBn p{y, M, C, N, bias, aff};
+  if (use_batch_stats) {
+    double* partials = static_cast<double*>(workspace);
+    int rpc;
+    const int grid = rows_bn_grid(M, &rpc);
+    rows_bn_reduce_kernel<false><<<grid, kRbThreads, 0, st>>>(p, nullptr, rpc, partials);
+    rows_bn_fwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partials, grid, C, static_cast<double>(M), gamma, beta, eps,
+                                                                 momentum, running_mean, running_var, mean, rstd, aff);
+  } else {
+    rows_bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, eps, running_mean, running_var, aff);
+  }
+  const int blocks = rows_bn_apply_grid(M, C);
+  rows_bn_apply_kernel<false><<<blocks, kRbThreads, 0, st>>>(p, nullptr, nullptr, h);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}
+
+extern "C" int dgcnn_rows_bn_lrelu_bwd(const float* dh, const float* y, int M, int C, const float* bias, int N,
+                                       const float* gamma, const float* rstd, const float* aff, float* dy, float* dgamma,
+                                       float* dbeta, void* workspace, size_t workspace_bytes, void* stream) {
+  DG_REQUIRE(dh && y && gamma && rstd && aff && dy && dgamma && dbeta && workspace, DGCNN_E_INVALID, "rows_bn_lrelu_bwd: null pointer");
+  DG_REQUIRE(rows_bn_shape_ok(C), DGCNN_E_UNSUPPORTED, "rows_bn_lrelu_bwd: C must be 64, 128, 256, 512 or 1024");
+  DG_REQUIRE(M > 0 && N > 0 && (!bias || M % N == 0), DGCNN_E_INVALID, "rows_bn_lrelu_bwd: bad shape");
+  DG_REQUIRE(workspace_bytes >= dgcnn_rows_bn_workspace_bytes(C), DGCNN_E_INVALID, "rows_bn_lrelu_bwd: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RowsBn p{y, M, C, N, bias, aff};
+  double* partials = static_cast<double*>(workspace);
+  float* coef = reinterpret_cast<float*>(partials + static_cast<size_t>(kRbMaxCtas) * 2 * C);
+  int rpc;
+  const int grid = rows_bn_grid(M, &rpc);
+  rows_bn_reduce_kernel<true><<<grid, kRbThreads, 0, st>>>(p, dh, rpc, partials);
+  rows_bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partials, grid, C, static_cast<double>(M), gamma, rstd, dgamma, dbeta, coef);
+  const int blocks = rows_bn_apply_grid(M, C);
+  rows_bn_apply_kernel<true><<<blocks, kRbThreads, 0, st>>>(p, dh, coef, dy);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}

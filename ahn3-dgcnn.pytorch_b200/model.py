@@ -175,11 +175,11 @@ class DGCNN(nn.Module):
         if E + feat.size(1) != w7.size(1):
             raise RuntimeError(f"conv7 expects {w7.size(1)} input channels but emb_dims+192 = {E + feat.size(1)}")
         # conv7([g ; x1,x2,x3]) = W7[:, :E] g (once per block) + W7[:, E:] feat  — no repeat/cat of the global feature
-        y7 = ops.linear(feat, w7[:, E:]).view(B, N, -1) + (g @ w7[:, :E].t()).unsqueeze(1)
-        h7 = F.leaky_relu(self.bn7(y7.view(B * N, -1)), LRELU_SLOPE)
+        # the per-block term is added inside the fused BatchNorm + LeakyReLU passes
+        h7 = ops.bn_lrelu_rows(ops.linear(feat, w7[:, E:]), self.bn7, self.training, N, bias=g @ w7[:, :E].t())
         if depth == 8:
             return self._bcn(h7, B, N)
-        h8 = self._dense(h7, 8)
+        h8 = ops.bn_lrelu_rows(ops.linear(h7, self.conv8[0].weight.squeeze(-1)), self.bn8, self.training, N)
         if depth == 9:
             return self._bcn(h8, B, N)
         logits = ops.linear(self.dp1(h8), self.conv9.weight.squeeze(-1))   # [M,classes]

@@ -269,6 +269,53 @@ class GlobalFeature(torch.autograd.Function):
         return dfeat, dw, s2, s1, None, None, None, None
 
 
+class RowsBnLrelu(torch.autograd.Function):
+    """h = LeakyReLU(BatchNorm1d(y + bias[block])) on point-major rows y[M,C] (model.py:131-139,179-184), two fused
+    passes forward and two backward instead of the library's five and eight."""
+
+    @staticmethod
+    def forward(ctx, y, bias, gamma, beta, bn: BNState, training: bool, N: int):
+        lib = _lib.load()
+        M, Cn = y.shape
+        dev = y.device
+        y = y.contiguous()
+        bias_c = None if bias is None else bias.detach().contiguous()
+        ws = torch.empty(lib.dgcnn_rows_bn_workspace_bytes(Cn), dtype=torch.uint8, device=dev)
+        stat = torch.empty(2, Cn, dtype=torch.float32, device=dev)
+        aff = torch.empty(3 * Cn, dtype=torch.float32, device=dev)
+        h = torch.empty_like(y)
+        _call("dgcnn_rows_bn_lrelu_fwd", _ptr(y.detach()), M, Cn, _ptr(bias_c), N, _ptr(gamma.detach()), _ptr(beta.detach()),
+              bn.eps, bn.momentum, 1 if training else 0, _ptr(bn.running_mean), _ptr(bn.running_var), _ptr(stat[0]),
+              _ptr(stat[1]), _ptr(aff), _ptr(h), _ptr(ws), ws.numel(), _stream())
+        ctx.save_for_backward(y.detach(), bias_c, gamma.detach(), stat, aff)
+        ctx.training, ctx.N, ctx.ws = training, N, ws
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        y, bias, gamma, stat, aff = ctx.saved_tensors
+        if not ctx.training:
+            raise RuntimeError("RowsBnLrelu: the inference form (running statistics) is not differentiable")
+        M, Cn = y.shape
+        dh = dh.contiguous()
+        dy = torch.empty_like(y)
+        dgamma = torch.empty(Cn, dtype=torch.float32, device=y.device)
+        dbeta = torch.empty_like(dgamma)
+        _call("dgcnn_rows_bn_lrelu_bwd", _ptr(dh), _ptr(y), M, Cn, _ptr(bias), ctx.N, _ptr(gamma), _ptr(stat[1]), _ptr(aff),
+              _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(ctx.ws), ctx.ws.numel(), _stream())
+        dbias = None if bias is None else dy.view(-1, ctx.N, Cn).sum(1)
+        return dy, dbias, dgamma, dbeta, None, None, None
+
+
+def bn_lrelu_rows(y: torch.Tensor, bn_mod, training: bool, N: int, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LeakyReLU(bn_mod(y + bias[block])) for y[M,C]; `bn_mod` is the reference's nn.BatchNorm1d (state and parameters)."""
+    st = BNState(bn_mod.running_mean, bn_mod.running_var, bn_mod.eps, bn_mod.momentum)
+    h = RowsBnLrelu.apply(y, bias, bn_mod.weight, bn_mod.bias, st, training, N)
+    if training:
+        bn_mod.num_batches_tracked.add_(1)
+    return h
+
+
 def linear(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """x @ w^T; tensor-core path for GEMMs big enough to fill the machine, library GEMM otherwise."""
     M, K = x.shape

@@ -122,8 +122,8 @@ int dgcnn_bn_finalize(const double* partials, int C, double count, const float* 
 int dgcnn_edgeconv_select(int M, const float* ymax, const float* ymin, const uint8_t* amax, const uint8_t* amin,
                           const float* affine, float* out, int ld_out, float* ysel, uint8_t* arg, void* stream);
 
-/* Select the implementation of the 64-channel EdgeConv passes: 2 (default) = warp-specialised, pipelined tcgen05
- * kernels (training passes; inference uses the serial tcgen05 kernel), 1 = serial tcgen05 kernels, 0 = FP32 FMA.
+/* Select the implementation of the 64-channel EdgeConv passes: 2 (default) = tcgen05 kernels with the warp-specialised,
+ * pipelined conv_b training pass, 1 = serial tcgen05 kernels only, 0 = FP32 FMA.
  * The tensor-core paths use the FP32-accurate bf16x3 split.  Returns the previous setting.  Process-wide; for A/B checks. */
 int dgcnn_set_edgeconv_tc(int enabled);
 
@@ -177,6 +177,23 @@ int dgcnn_tc_gemm_bn_lrelu_segmax_f32(const float* A, int64_t a_row_stride, int6
                                       float* running_mean, float* running_var, float* mean, float* rstd,
                                       float* g, float* ysel, int32_t* nstar,
                                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- shared-MLP head: BatchNorm1d (+ per-block bias) + LeakyReLU(0.2) over point-major rows ---------------------------
+ * Replaces `bn7(conv7(..))`, `bn8(conv8(..))` + LeakyReLU of reference model.py:131-139,179-184 on y[M,C] (row-major,
+ * contiguous).  v = y + bias[row / N] (bias may be NULL: it carries the once-per-block global-feature half of conv7),
+ * h = LReLU(BN(v)).  use_batch_stats != 0: training statistics over the M rows (written to mean/rstd; running_* updated
+ * with `momentum` when given, unbiased variance); == 0: running statistics.  aff (float[3C], out) = mean | gamma*rstd |
+ * beta, consumed by the backward.  workspace: dgcnn_rows_bn_workspace_bytes(C) bytes.  C in {64,128,256,512,1024}.     */
+int dgcnn_rows_bn_supported(int C);
+size_t dgcnn_rows_bn_workspace_bytes(int C);
+int dgcnn_rows_bn_lrelu_fwd(const float* y, int M, int C, const float* bias, int N, const float* gamma, const float* beta,
+                            float eps, float momentum, int use_batch_stats, float* running_mean, float* running_var,
+                            float* mean, float* rstd, float* aff, float* h, void* workspace, size_t workspace_bytes,
+                            void* stream);
+/* backward of the training form: dy[M,C] (gradient w.r.t. y, equally w.r.t. v), dgamma[C], dbeta[C] from dh[M,C].    */
+int dgcnn_rows_bn_lrelu_bwd(const float* dh, const float* y, int M, int C, const float* bias, int N, const float* gamma,
+                            const float* rstd, const float* aff, float* dy, float* dgamma, float* dbeta,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* debug: exercises MN-major tcgen05 operand descriptors on one 128x64 tile pair (tests only) */
 int dgcnn_debug_mn_lab(const float* X, const float* Y, float* D, int lbo_a, int sbo_a, int lbo_b, int sbo_b,
