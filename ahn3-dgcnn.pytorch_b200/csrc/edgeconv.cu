@@ -264,26 +264,32 @@ __global__ void __launch_bounds__(kThreads, 2) ec_fwd_kernel(const EcK p) {
 // ---------------------------------------------------------------------------------------------
 // small per-channel kernels
 // ---------------------------------------------------------------------------------------------
-// Sum partials[part][2][C] over the parts with 4 thread groups (fixed order -> deterministic): thread (grp, c)
-// accumulates parts grp, grp+4, ... ; the four group sums are added in order.  Result valid for threadIdx.x < C.
+// Sum partials[part][2][C] over the parts with 16 thread groups (fixed order -> deterministic): thread (grp, c)
+// accumulates parts grp, grp+16, ... with all its loads in flight together (the kernel is pure latency: a few hundred
+// parts, one CTA); the group sums are added in order.  Result valid for threadIdx.x < C.  blockDim.x = 1024.
+constexpr int kRedGroups = 16;
 __device__ __forceinline__ void reduce_partials(const double* __restrict__ partials, int C, double& s, double& q) {
-  __shared__ double red[2][4][64];
+  __shared__ double red[2][kRedGroups][64];
   const int c = threadIdx.x & 63, grp = threadIdx.x >> 6;
   const int nparts = static_cast<int>(partials[0]);
   double a = 0.0, b = 0.0;
-#pragma unroll 4
-  for (int i = grp; i < nparts; i += 4) {
+#pragma unroll 8
+  for (int i = grp; i < nparts; i += kRedGroups) {
     a += partials[128 + static_cast<size_t>(i) * 2 * C + c];
     b += partials[128 + static_cast<size_t>(i) * 2 * C + C + c];
   }
   red[0][grp][c] = a;
   red[1][grp][c] = b;
   __syncthreads();
-  s = ((red[0][0][c] + red[0][1][c]) + red[0][2][c]) + red[0][3][c];
-  q = ((red[1][0][c] + red[1][1][c]) + red[1][2][c]) + red[1][3][c];
+  s = 0.0; q = 0.0;
+#pragma unroll
+  for (int g2 = 0; g2 < kRedGroups; ++g2) {
+    s += red[0][g2][c];
+    q += red[1][g2][c];
+  }
 }
 
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restrict__ partials, int C, double count,
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const double* __restrict__ partials, int C, double count,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float eps, float momentum, float* running_mean,
                                                           float* running_var, float* mean, float* rstd, float* aff) {
@@ -355,7 +361,7 @@ __global__ void __launch_bounds__(kThreads) bwd_prep_kernel(int M, const float* 
 
 // From S1 = sum dz, S2 = sum dz*y:  dgamma = rstd (S2 - mean S1), dbeta = S1 and the coefficients of
 // dy = cA dz - cB - cC y  (BatchNorm backward with batch statistics).
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const double* __restrict__ partials, int C, double count,
+__global__ void __launch_bounds__(1024) bn_bwd_reduce_kernel(const double* __restrict__ partials, int C, double count,
                                                             const float* __restrict__ gamma, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, float* dgamma, float* dbeta,
                                                             float* coef) {
@@ -622,7 +628,10 @@ static int dispatch_cp(const EcK& p, cudaStream_t st) {
 using namespace dg;
 
 extern "C" size_t dgcnn_edgeconv_partials_bytes(void) { return (128 + static_cast<size_t>(kMaxPartialCtas) * 128) * sizeof(double); }
-extern "C" size_t dgcnn_edgeconv_dw_partials_bytes(void) { return static_cast<size_t>(kMaxPartialCtas) * kCout * kCout * sizeof(float); }
+// per-CTA partials [128][64] (tensor-core path: D'^T H over H^T H; the FMA path uses the first [64][64]) + one summed copy
+extern "C" size_t dgcnn_edgeconv_dw_partials_bytes(void) {
+  return (static_cast<size_t>(kMaxPartialCtas) + 1) * 2 * kCout * kCout * sizeof(float);
+}
 
 extern "C" int dgcnn_edgeconv_fwd_eval(const dgcnn_edgeconv_args* a, const float* aff_a, const float* aff_b,
                                        void* stream) {
@@ -674,7 +683,7 @@ extern "C" int dgcnn_bn_finalize(const double* partials, int C, double count, co
   DG_REQUIRE(partials && gamma && beta && mean && rstd && aff, DGCNN_E_INVALID, "bn_finalize: null pointer");
   DG_REQUIRE(C == kCout, DGCNN_E_UNSUPPORTED, "bn_finalize: C must be 64");
   DG_REQUIRE(count >= 1.0 && (!running_mean == !running_var), DGCNN_E_INVALID, "bn_finalize: bad count / running stats");
-  bn_finalize_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, C, count, gamma, beta, eps, momentum,
+  bn_finalize_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(partials, C, count, gamma, beta, eps, momentum,
                                                                     running_mean, running_var, mean, rstd, aff);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
@@ -706,7 +715,7 @@ extern "C" int dgcnn_bn_bwd_reduce(const double* partials, int C, double count, 
                                    const float* rstd, float* dgamma, float* dbeta, float* coef, void* stream) {
   DG_REQUIRE(partials && gamma && mean && rstd && dgamma && dbeta && coef, DGCNN_E_INVALID, "bn_bwd_reduce: null pointer");
   DG_REQUIRE(C == kCout && count >= 1.0, DGCNN_E_UNSUPPORTED, "bn_bwd_reduce: C must be 64");
-  bn_bwd_reduce_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, C, count, gamma, mean, rstd, dgamma, dbeta, coef);
+  bn_bwd_reduce_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(partials, C, count, gamma, mean, rstd, dgamma, dbeta, coef);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
 }
@@ -724,7 +733,7 @@ extern "C" int dgcnn_edgeconv_bwd_b(const dgcnn_edgeconv_args* a, const float* y
   if (edgeconv_tc_enabled()) {
     // two CTAs per SM; every CTA gets at least one tile so that its dW partial is defined
     const int grid = std::max(1, std::min(p.num_tiles, 2 * std::max(1, num_sms())));
-    if ((rc = launch_ec_tc_bwd_b(p, g, arg, coef_b, dz_a, dw_partials, grid, st))) return rc;
+    return launch_ec_tc_bwd_b(p, g, arg, coef_b, dz_a, dw_partials, dw_b, grid, st);
   } else {
     DG_CUDA(cudaFuncSetAttribute(ec_bwd_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcBwdSmem::bytes)));
     ec_bwd_b_kernel<<<persistent_grid(p.num_tiles), kThreads, EcBwdSmem::bytes, st>>>(p, g, arg, coef_b, dz_a, dw_partials);

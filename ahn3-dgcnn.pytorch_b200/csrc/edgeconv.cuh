@@ -29,7 +29,7 @@ __device__ __forceinline__ float bn_apply(float y, float mean, float scale, floa
 // tensor-core forward kernels (edgeconv_tc.cu); mode = MODE_EVAL / MODE_TRAIN_A (need C == 64 and v_center) or MODE_TRAIN_B
 int launch_ec_tc_fwd(const EcK& p, int mode, int grid, cudaStream_t st);
 int launch_ec_tc_bwd_b(const EcK& p, const float* g, const uint8_t* arg, const float* coef_b, float* dz_a,
-                       float* dw_partials, int grid, cudaStream_t st);
+                       float* dw_partials, float* dw_b, int grid, cudaStream_t st);
 bool edgeconv_tc_enabled();
 int edgeconv_tc_mode();       // 0 = FFMA kernels, 1 = serial tensor-core kernels, 2 = 1 + warp-specialised pipelined conv_b (default)
 // pipelined conv_b training pass (edgeconv_pipe.cu); one CTA per SM

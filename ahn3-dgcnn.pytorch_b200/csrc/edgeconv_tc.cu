@@ -33,24 +33,46 @@ struct EcTcSmem {
   static constexpr uint32_t bytes = bar_off + 64;
 };
 
-// V[p][o] = sum_c Wa2[o][c] x[p][c]: the centre half of conv_a (w_a[:, 64:128]), once per point instead of once per edge
+// V[p][o] = sum_c Wa2[o][c] x[p][c]: the centre half of conv_a (w_a[:, 64:128]), once per point instead of once per edge.
+// 64 points per CTA iteration, 4 points x 4 outputs per thread, sequential FMA chain over c (same order as the FMA path).
 __global__ void __launch_bounds__(256) center_term_kernel(const float* __restrict__ rows, int ld, int M,
                                                           const float* __restrict__ w_a, float* __restrict__ V) {
-  __shared__ float Wt[64][65];      // [c][o]
-  __shared__ __align__(16) float xs[4][64];
+  __shared__ __align__(16) float Wt[64][68];      // [c][o]
+  __shared__ float xs[64][65];                    // [p][c]
   const int tid = threadIdx.x;
   for (int i = tid; i < 64 * 64; i += 256) Wt[i & 63][i >> 6] = w_a[static_cast<size_t>(i >> 6) * 128 + 64 + (i & 63)];
-  const int o = tid & 63, pl = tid >> 6;
-  for (int p0 = blockIdx.x * 4; p0 < M; p0 += gridDim.x * 4) {
+  const int og = tid & 15, pg = tid >> 4;
+  for (int p0 = blockIdx.x * 64; p0 < M; p0 += gridDim.x * 64) {
     __syncthreads();
-    if (p0 + pl < M) xs[pl][o] = rows[static_cast<size_t>(p0 + pl) * ld + o];
-    __syncthreads();
-    if (p0 + pl < M) {
-      float a = 0.f;
-#pragma unroll 16
-      for (int c = 0; c < 64; ++c) a = __fmaf_rn(Wt[c][o], xs[pl][c], a);
-      V[static_cast<size_t>(p0 + pl) * 64 + o] = a;
+    for (int i = tid; i < 64 * 16; i += 256) {
+      const int pp = i >> 4, c4 = i & 15;
+      const float4 v = p0 + pp < M ? *reinterpret_cast<const float4*>(rows + static_cast<size_t>(p0 + pp) * ld + 4 * c4)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      xs[pp][4 * c4] = v.x; xs[pp][4 * c4 + 1] = v.y; xs[pp][4 * c4 + 2] = v.z; xs[pp][4 * c4 + 3] = v.w;
     }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < 64; ++c) {
+      const float4 w = *reinterpret_cast<const float4*>(&Wt[c][4 * og]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float x = xs[4 * pg + i][c];
+        acc[i][0] = __fmaf_rn(w.x, x, acc[i][0]);
+        acc[i][1] = __fmaf_rn(w.y, x, acc[i][1]);
+        acc[i][2] = __fmaf_rn(w.z, x, acc[i][2]);
+        acc[i][3] = __fmaf_rn(w.w, x, acc[i][3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (p0 + 4 * pg + i < M)
+        *reinterpret_cast<float4*>(V + static_cast<size_t>(p0 + 4 * pg + i) * 64 + 4 * og) =
+            make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   }
 }
 
@@ -318,20 +340,28 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
 
 // ---------------------------------------------------------------------------------------------
 // backward edge pass through conv_b on the tensor cores (same contract as ec_bwd_b_kernel in edgeconv.cu)
-//   MMA1  y_b  = H W_b^T            K-major (recomputed pre-BN output, needed by the dense BN backward)
-//   MMA3  dh   = DY W_b             K-major
-//   all three with the 2-plane bf16 split: this is the gradient path, 2^-17 relative error is far below its 1e-3 noise
-//   floor (tests/test_gpu_parity.py), and two planes per operand let two CTAs share an SM
-//   MMA2  dW_b += DY^T H            MN-major views of the same tiles (contraction over the 128 tile rows), bf16x2;
-//                                   A = [DY ; H] stacked to M = 128 through the descriptor's leading-dimension offset,
-//                                   accumulated in TMEM across all tiles of the CTA
+//
+// The dense BN_b backward is dy_b = cA dz - cB - cC y_b with y_b = H W_b^T (dz: the max-over-k gradient, non-zero at the
+// arg-max rows only).  Substituting y_b removes the recomputation of y_b and the epilogue that depended on it:
+//   dh   = dy_b W_b           = D' W_b - H G,        D' = cA dz - cB,   G = W_b^T diag(cC) W_b   (64 x 64, once per CTA)
+//   dW_b = dy_b^T H           = D'^T H - diag(cC) W_b (H^T H)
+// so a tile is ONE batch of MMAs after ONE producer phase:
+//   MMA a  dh    = D' W_b      A = D' planes (K-major), B = the W_b planes read MN-major
+//   MMA b  dh   -= H G         A = H planes (K-major),  B = planes of -G (symmetric, K-major)
+//   MMA c  T    += [D' ; H]^T H  MN-major views of the same tiles (contraction over the 128 tile rows); A stacked to
+//                              M = 128 through the descriptor's leading-dimension offset, accumulated in TMEM over all
+//                              tiles of the CTA: lanes 0-63 = D'^T H, lanes 64-127 = H^T H
+// all with the 2-plane bf16 split: this is the gradient path, 2^-17 relative error is far below its 1e-3 noise floor
+// (tests/test_gpu_parity.py), and two planes per operand let two CTAs share an SM.  ec_tc_dw_finish_kernel turns the
+// per-CTA T partials into dW_b.
 // ---------------------------------------------------------------------------------------------
 struct EcTcBwdSmem {
   static constexpr uint32_t dy_off = 0;                         // DY planes (2)
   static constexpr uint32_t h_off = 2 * kPlA;                   // H planes (2)
   static constexpr uint32_t w_off = h_off + 2 * kPlA;           // W_b planes (2): rows = c (out), 128 B of c'' (in): K-major
                                                                 // for y_b = H W_b^T, MN-major view (N = c'', K = c) for dh
-  static constexpr uint32_t g_off = w_off + 2 * kPlW;           // gs [16][64]
+  static constexpr uint32_t gm_off = w_off + 2 * kPlW;          // planes (2) of -G = -W_b^T diag(cC) W_b (K-major, symmetric)
+  static constexpr uint32_t g_off = gm_off + 2 * kPlW;          // gs [16][64]
   static constexpr uint32_t aff_off = g_off + kMaxP * 64 * 4;   // affine of BN_a (192) + coefficients of BN_b (192)
   static constexpr uint32_t arg_off = aff_off + 2 * 192 * 4;    // args [16][64] u8
   static constexpr uint32_t red_off = arg_off + kMaxP * 64;     // [2][4][64] floats
@@ -346,6 +376,7 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
   unsigned char* DYp = sm + EcTcBwdSmem::dy_off;
   unsigned char* Hp = sm + EcTcBwdSmem::h_off;
   unsigned char* Wp = sm + EcTcBwdSmem::w_off;
+  unsigned char* Gp = sm + EcTcBwdSmem::gm_off;
   float* gs = reinterpret_cast<float*>(sm + EcTcBwdSmem::g_off);
   float* aff = reinterpret_cast<float*>(sm + EcTcBwdSmem::aff_off);
   float* cb = aff + 192;
@@ -374,6 +405,26 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
     aff[tid] = p.aff_a[tid];
     cb[tid] = coef_b[tid];
   }
+  {
+    // -G[i][j] = -sum_c cC_c W_b[c][i] W_b[c][j]; FP32 copy of W_b parked in the (still unused) DY plane area
+    float* Wf = reinterpret_cast<float*>(DYp);      // [c][65]
+    for (int i = tid; i < 64 * 64; i += kThreads) Wf[(i >> 6) * 65 + (i & 63)] = p.w_b[i];
+    __syncthreads();
+    const int gi = tid >> 2, gj0 = (tid & 3) * 16;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int c = 0; c < 64; ++c) {
+      const float a = -cb[128 + c] * Wf[c * 65 + gi];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = __fmaf_rn(a, Wf[c * 65 + gj0 + j], acc[j]);
+    }
+    float lo[8], hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { lo[j] = acc[j]; hi[j] = acc[8 + j]; }
+    store_split<2>(Gp, kPlW, gi, (tid & 3) * 2, lo);          // row n = i, K chunk of j: -G is symmetric
+    store_split<2>(Gp, kPlW, gi, (tid & 3) * 2 + 1, hi);
+  }
   tc::fence_proxy_async();
   tc::fence_before_sync();
   __syncthreads();
@@ -394,7 +445,7 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
     const int gp0 = tile * P;
     const size_t e0 = static_cast<size_t>(gp0) * k;
     const int nvalid = min(P, M - gp0) * k;
-    __syncthreads();  // S0
+    // (no barrier here: gs / args of the previous tile were last read before its S1)
     if (tid == 0 && tile + static_cast<int>(gridDim.x) < p.num_tiles) {      // DRAM -> L2 prefetch of this CTA's next y_a tile
       const size_t e2 = static_cast<size_t>(tile + gridDim.x) * P * k;
       const size_t rows_left = static_cast<size_t>(M) * k - e2;
@@ -407,61 +458,37 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
       args[i] = ok ? arg[static_cast<size_t>(gp) * kCout + (i & 63)] : 255;
     }
     // producer with the EPILOGUE's mapping (thread = tile row erow, 32 columns of half `half`): the thread's y_a values
-    // stay in registers until epilogue 2, so y_a is read from memory once per tile
+    // stay in registers until the epilogue, so y_a is read from memory once per tile
     float ya[32];
+    const bool valid = erow < nvalid;
     {
-      const bool valid = erow < nvalid;
       const float* src = p.y_a_in + (e0 + (valid ? erow : 0)) * kCout + half * 32;
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         const float4 y = valid ? *reinterpret_cast<const float4*>(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         ya[i] = y.x; ya[i + 1] = y.y; ya[i + 2] = y.z; ya[i + 3] = y.w;
       }
-#pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        float h[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = half * 32 + c8 * 8 + e;
-          h[e] = valid ? lrelu(bn_apply(ya[c8 * 8 + e], aff[c], aff[64 + c], aff[128 + c])) : 0.f;
-        }
-        store_split<2>(Hp, kPlA, erow, half * 4 + c8, h);
-      }
     }
-    tc::fence_proxy_async();
-    __syncthreads();  // S1
-    if (tid == 0) {
-      tc::fence_after_sync();
-      tc::mma_split_katom<2>(taddr, tc::smem_u32(Hp), kPlA, tc::smem_u32(Wp), kPlW, idesc_k, true);   // y_b
-      tc::mma_commit(bar);
-    }
-    __syncwarp();
-    tc::mbar_wait(bar, phase);
-    phase ^= 1;
-    tc::fence_after_sync();
-    // ---- epilogue 1: dy_b = cA dz - cB - cC y_b  -> two bf16 planes -----------------------------------------------
-    {
-      float v[32];
-      tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + half * 32, v);
-      const bool valid = erow < nvalid;
+    __syncthreads();  // S0b: gs / args staged
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        float d[8];
+    for (int c8 = 0; c8 < 4; ++c8) {
+      float h[8], d[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int col = half * 32 + c8 * 8 + e;
-          const float dz = (args[erp * kCout + col] == ers) ? gs[erp * kCout + col] : 0.f;
-          d[e] = valid ? cb[col] * dz - cb[64 + col] - cb[128 + col] * v[c8 * 8 + e] : 0.f;
-        }
-        store_split<2>(DYp, kPlA, erow, half * 4 + c8, d);
+      for (int e = 0; e < 8; ++e) {
+        const int c = half * 32 + c8 * 8 + e;
+        h[e] = valid ? lrelu(bn_apply(ya[c8 * 8 + e], aff[c], aff[64 + c], aff[128 + c])) : 0.f;
+        const float dz = (args[erp * kCout + c] == ers) ? gs[erp * kCout + c] : 0.f;
+        d[e] = valid ? __fmaf_rn(cb[c], dz, -cb[64 + c]) : 0.f;                    // D' = cA dz - cB
       }
+      store_split<2>(Hp, kPlA, erow, half * 4 + c8, h);
+      store_split<2>(DYp, kPlA, erow, half * 4 + c8, d);
     }
     tc::fence_proxy_async();
     tc::fence_before_sync();
-    __syncthreads();  // S2: DY planes complete, accumulator 0 drained
+    __syncthreads();  // S1: H and D' planes complete, accumulator of the previous tile drained
     if (tid == 0) {
       tc::fence_after_sync();
-      // dh = DY W_b: A = DY planes (K-major), B = the W_b planes read MN-major (N = c'' contiguous, K = c = rows)
+      // dh = D' W_b: A = D' planes (K-major), B = the W_b planes read MN-major (N = c'' contiguous, K = c = rows)
       {
         uint32_t acc3 = 0u;
         const int pa[3] = {0, 1, 0}, pb[3] = {1, 0, 0};
@@ -474,7 +501,8 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
             acc3 = 1u;
           }
       }
-      // dW_b += DY^T H over the 128 tile rows: pairs (DY plane i, H plane j), i + j <= 3, smallest first
+      tc::mma_split_katom<2>(taddr, tc::smem_u32(Hp), kPlA, tc::smem_u32(Gp), kPlW, idesc_k, false);     // dh -= H G
+      // T += [D' ; H]^T H over the 128 tile rows: pairs (plane i, plane j), i + j <= 3, smallest first
       const uint32_t lbo = tc::smem_u32(Hp) - tc::smem_u32(DYp);
       uint32_t acc = first_tile ? 0u : 1u;
       const int pi[3] = {0, 1, 0}, pj[3] = {1, 0, 0};
@@ -497,7 +525,6 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
     {
       float v[32];
       tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + half * 32, v);
-      const bool valid = erow < nvalid;
       float (&w)[32] = ya;                      // dz_a * y_a overwrites the cached y_a values
       if (valid) {
         float* dst = dz_a + (e0 + erow) * kCout + half * 32;
@@ -527,8 +554,8 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
   }
   // ---- dW_b partial of this CTA (TMEM lanes 0-63, columns 64-127) and the BN_a statistics -----------------------------
   __syncthreads();
-  if (warp < 2 && !first_tile) {
-    float* dst = dw_partials + static_cast<size_t>(blockIdx.x) * kCout * kCout + static_cast<size_t>(warp * 32 + lane) * kCout;
+  if (warp < 4 && !first_tile) {            // T partial of this CTA: rows 0-63 = D'^T H, rows 64-127 = H^T H
+    float* dst = dw_partials + static_cast<size_t>(blockIdx.x) * 2 * kCout * kCout + static_cast<size_t>(warp * 32 + lane) * kCout;
 #pragma unroll 1
     for (int c0 = 0; c0 < 64; c0 += 32) {
       float v[32];
@@ -552,17 +579,40 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
   if (warp == 0) tc::tmem_dealloc(taddr, 128);
 }
 
+// T[128][64] = sum over the CTAs of their partials (FP64, fixed order) -> scratch behind the partials
+__global__ void __launch_bounds__(256) ec_tc_dw_sum_kernel(const float* __restrict__ dw_partials, int nparts, float* __restrict__ T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * kCout * kCout) return;
+  double s = 0.0;
+#pragma unroll 8
+  for (int c = 0; c < nparts; ++c) s += dw_partials[static_cast<size_t>(c) * 2 * kCout * kCout + i];
+  T[i] = static_cast<float>(s);
+}
+// dW_b[c][j] = T[c][j] - cC_c * sum_i W_b[c][i] T[64 + i][j]
+__global__ void __launch_bounds__(256) ec_tc_dw_finish_kernel(const float* __restrict__ T, const float* __restrict__ w_b,
+                                                              const float* __restrict__ coef_b, float* __restrict__ dw) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= kCout * kCout) return;
+  const int c = o >> 6, j = o & 63;
+  double a = 0.0;
+  for (int i = 0; i < 64; ++i) a += static_cast<double>(w_b[c * 64 + i]) * T[(64 + i) * 64 + j];
+  dw[o] = static_cast<float>(static_cast<double>(T[o]) - static_cast<double>(coef_b[128 + c]) * a);
+}
+
 int launch_ec_tc_bwd_b(const EcK& p, const float* g, const uint8_t* arg, const float* coef_b, float* dz_a,
-                       float* dw_partials, int grid, cudaStream_t st) {
+                       float* dw_partials, float* dw_b, int grid, cudaStream_t st) {
   DG_CUDA(cudaFuncSetAttribute(ec_tc_bwd_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcTcBwdSmem::bytes)));
   ec_tc_bwd_b_kernel<<<grid, kThreads, EcTcBwdSmem::bytes, st>>>(p, g, arg, coef_b, dz_a, dw_partials);
+  float* T = dw_partials + static_cast<size_t>(kMaxPartialCtas) * 2 * kCout * kCout;
+  ec_tc_dw_sum_kernel<<<(2 * kCout * kCout + 255) / 256, 256, 0, st>>>(dw_partials, grid, T);
+  ec_tc_dw_finish_kernel<<<(kCout * kCout + 255) / 256, 256, 0, st>>>(T, p.w_b, coef_b, dw_b);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
 }
 
 int launch_ec_tc_fwd(const EcK& p, int mode, int grid, cudaStream_t st) {
   if (mode != MODE_TRAIN_B) {
-    center_term_kernel<<<std::max(1, std::min((p.M + 3) / 4, 148 * 8)), 256, 0, st>>>(p.rows, p.ld, p.M, p.w_a, p.v_center);
+    center_term_kernel<<<std::max(1, std::min((p.M + 63) / 64, 148 * 4)), 256, 0, st>>>(p.rows, p.ld, p.M, p.w_a, p.v_center);
     DG_CUDA(cudaGetLastError());
   }
   // conv_b streams a contiguous tile: the warp-specialised pipeline wins there.  conv_a is bound by the L2 gather and
