@@ -122,6 +122,13 @@ def cpu_reference_steps(steps: int, warmup: int, sample_blocks: int):
     return times, torch.get_num_threads()
 
 
+def workload_config(world: int) -> dict:
+    """`config` of the JSON line: identical for our arm and for the reference arm."""
+    return {"workload": f"AHN3 train step (fwd+loss+bwd+allreduce+Adam) B={B_PER_GPU}/GPU F={FEAT} N={NPTS} k={KNN} classes={CLASSES} emb={EMB}",
+            "parallelism": f"dp{world}", "global_batch": B_PER_GPU * world,
+            "l2": "no explicit flush: each step streams >1.5 GB of per-edge intermediates (L2 is 126 MB); 4 rotating input batches"}
+
+
 def run_reference(args, rank: int):
     if rank != 0:
         return
@@ -134,8 +141,7 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"AHN3 train step B={B_PER_GPU}/GPU F={FEAT} N={NPTS} k={KNN} classes={CLASSES} (CPU sample: B={sample_blocks})",
-                   "l2": "n/a (CPU)"},
+        "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -269,8 +275,14 @@ def run_ours(args, rank: int, local: int, world: int):
                 "kind::f16 MMAs per algorithmic product for FP32-level accuracy, so the ceiling for ALGORITHMIC flops is "
                 "peak/3 .. peak/6" if on_tensor else
                 f"FP32 FMA pipe at the median SM clock under load ({sm_mhz:.0f} MHz); kernel is FFMA-based")
+        # measured DRAM bytes per launch of that entry point from the committed `ncu --set full` capture (not a live number)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(dom, {}).get("bytes_per_launch")
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "peak_kind": kind,
+                "frac": achieved / peak, "traffic": traffic, "peak_kind": kind,
                 "launches_per_step": per_kernel[dom][0] / args.steps, "ms_per_step": dom_ms / args.steps}
 
     # ---- CPU baseline (bounded sample) -------------------------------------------------------------------
@@ -285,9 +297,7 @@ def run_ours(args, rank: int, local: int, world: int):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"AHN3 train step (fwd+loss+bwd+allreduce+Adam) B={B_PER_GPU}/GPU F={FEAT} N={NPTS} k={KNN} classes={CLASSES} emb={EMB}",
-                   "parallelism": f"dp{world}", "global_batch": B_PER_GPU * world,
-                   "l2": "no explicit flush: each step streams >1.5 GB of per-edge intermediates (L2 is 126 MB); 4 rotating input batches"},
+        "config": workload_config(world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
