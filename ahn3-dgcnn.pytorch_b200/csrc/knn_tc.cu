@@ -520,8 +520,9 @@ __global__ void __launch_bounds__(kThreads)
 knn_small_kernel(const float* __restrict__ rows, int ld, const float* __restrict__ norms, int N, int C4, int k,
                  int n_sample, unsigned long long* __restrict__ cand, int32_t* __restrict__ idx,
                  int* __restrict__ fb_count, int* __restrict__ fb_rows) {
+  // keys in pairs: Ks[(pair * CP + c) * 2 + slot] so that one FFMA2 (fma.rn.f32x2) scores two keys; Kn holds -|x_j|^2
   __shared__ __align__(16) float Ks[kSmallKeys * CP];
-  __shared__ float Kn[kSmallKeys];
+  __shared__ __align__(8) float Kn[kSmallKeys];
   __shared__ __align__(16) int cntS[kSmallRows * 4];
   __shared__ __align__(16) float tau4[kSmallRows * 4];
   __shared__ unsigned long long stageS[8][kSurvivors];
@@ -552,31 +553,38 @@ knn_small_kernel(const float* __restrict__ rows, int ld, const float* __restrict
       __syncthreads();
       for (int i = tid; i < kSmallKeys * (CP / 4); i += kThreads) {
         const int r = i / (CP / 4), c4 = i % (CP / 4), j = t0 + r;
-        *reinterpret_cast<float4*>(Ks + r * CP + 4 * c4) = (j < nkeys && 4 * c4 < C4)
-            ? *reinterpret_cast<const float4*>(rows + (base + j) * ld + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 v = (j < nkeys && 4 * c4 < C4) ? *reinterpret_cast<const float4*>(rows + (base + j) * ld + 4 * c4)
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        float* dst = Ks + ((r >> 1) * CP + 4 * c4) * 2 + (r & 1);
+        dst[0] = v.x; dst[2] = v.y; dst[4] = v.z; dst[6] = v.w;
       }
-      for (int r = tid; r < kSmallKeys; r += kThreads) Kn[r] = t0 + r < nkeys ? norms[base + t0 + r] : 0.f;
+      for (int r = tid; r < kSmallKeys; r += kThreads) Kn[r] = t0 + r < nkeys ? -norms[base + t0 + r] : 0.f;
       __syncthreads();
       const int r0 = kq * (kSmallKeys / 4);
       const int lim = min(kSmallKeys / 4, nkeys - t0 - r0);
-#pragma unroll 4
-      for (int i = 0; i < lim; ++i) {
+      const float2 two = make_float2(2.0f, 2.0f), mnq = make_float2(-nq, -nq);
+#pragma unroll 2
+      for (int i = 0; i < lim; i += 2) {
         const int r = r0 + i;
-        float d = 0.f;
+        float2 d = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < CP; c += 4) {
-          const float4 kv = *reinterpret_cast<const float4*>(Ks + r * CP + c);
-          d = __fmaf_rn(xq[c], kv.x, d);
-          d = __fmaf_rn(xq[c + 1], kv.y, d);
-          d = __fmaf_rn(xq[c + 2], kv.z, d);
-          d = __fmaf_rn(xq[c + 3], kv.w, d);
+        for (int c = 0; c < CP; c += 2) {
+          const float4 kv = *reinterpret_cast<const float4*>(Ks + ((r >> 1) * CP + c) * 2);      // channels c, c+1 of both keys
+          d = __ffma2_rn(make_float2(xq[c], xq[c]), make_float2(kv.x, kv.y), d);
+          d = __ffma2_rn(make_float2(xq[c + 1], xq[c + 1]), make_float2(kv.z, kv.w), d);
         }
-        const float pd = __fsub_rn(__fmaf_rn(d, 2.0f, -Kn[r]), nq);      // model.py:37, one rounding per step
-        if (pass == 0) {
-          if (pd > top[7]) top8_insert(top, pd);
-        } else if (pd > tau && row_ok) {
-          if (n < kSubCands) mycand[n] = make_key(pd, t0 + r);
-          ++n;
+        // model.py:37, one rounding per step: fl(fl(2 d - |x_j|^2) - |x_i|^2); the FMA chain order is the scalar one
+        const float2 pd2 = __fadd2_rn(__ffma2_rn(d, two, *reinterpret_cast<const float2*>(Kn + r)), mnq);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float pd = h ? pd2.y : pd2.x;
+          if (h && i + 1 >= lim) break;
+          if (pass == 0) {
+            if (pd > top[7]) top8_insert(top, pd);
+          } else if (pd > tau && row_ok) {
+            if (n < kSubCands) mycand[n] = make_key(pd, t0 + r + h);
+            ++n;
+          }
         }
       }
     }
