@@ -372,6 +372,7 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         if (c >= want) lo = mid; else hi = mid;
+        if (c >= want && c <= kSurvivors - 12) break;        // any cut that keeps [k+4, ~52] candidates will do
       }
       const float norm_i = norms[g];                 // reference |x_i|^2 (exact scores)
       const float nci = normc[g];                    // centred |y_i|^2: approx score of the row = exact pd + nci
@@ -409,22 +410,13 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
         }
       }
       __syncwarp();
-      int rank0 = 0, rank1 = 0;
-#pragma unroll 4
-      for (int s2 = 0; s2 < 32; ++s2) {
-        const unsigned long long o0 = __shfl_sync(0xffffffffu, ex[0], s2);
-        const unsigned long long o1 = __shfl_sync(0xffffffffu, ex[1], s2);
-        rank0 += (o0 > ex[0]) + (o1 > ex[0]);
-        rank1 += (o0 > ex[1]) + (o1 > ex[1]);
-      }
-      if (ex[0] != 0ull && rank0 < k) idx[g * k + rank0] = key_index(ex[0]);
-      if (ex[1] != 0ull && rank1 < k) idx[g * k + rank1] = key_index(ex[1]);
+      // bitonic sort of the (<= 64, distinct) exact keys, best first: element lane in ex[0], lane + 32 in ex[1]
+      sel::sort64_desc(ex[0], ex[1], lane);
+      if (ex[0] != 0ull && lane < k) idx[g * k + lane] = key_index(ex[0]);
+      if (ex[1] != 0ull && lane + 32 < k) idx[g * k + lane + 32] = key_index(ex[1]);
       // certificate: no key outside the candidate set can reach the k-th exact score found
-      float pdk = -INFINITY;
-      if (ex[0] != 0ull && rank0 == k - 1) pdk = sel::key_score(ex[0]);
-      if (ex[1] != 0ull && rank1 == k - 1) pdk = sel::key_score(ex[1]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) pdk = fmaxf(pdk, __shfl_xor_sync(0xffffffffu, pdk, o));
+      const unsigned long long kth = sel::list_at(ex[0], ex[1], k - 1);
+      const float pdk = kth != 0ull ? sel::key_score(kth) : -INFINITY;
       const bool cert = (tau_r - nci) + eps < pdk;
       if (lane == 0) {     // diagnostics: fb_count[1..4] count the reasons (overflow, too few, too many near-ties, certificate)
         if (max(max(c4.x, c4.y), max(c4.z, c4.w)) > kSubCands) atomicAdd(fb_count + 1, 1);
@@ -643,6 +635,7 @@ knn_small_kernel(const float* __restrict__ rows, int ld, const float* __restrict
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
       if (c >= want) lo = mid; else hi = mid;
+      if (c >= want && c <= kSurvivors) break;             // any cut that keeps [k+4, 64] candidates will do
     }
     int nb = 0;
 #pragma unroll
@@ -656,19 +649,12 @@ knn_small_kernel(const float* __restrict__ rows, int ld, const float* __restrict
     bad = bad || nb > kSurvivors;                 // > 64 exact ties around the k-th score
     const int ns = min(nb, kSurvivors);
     __syncwarp();
-    const unsigned long long e0 = lane < ns ? stg[lane] : 0ull;
-    const unsigned long long e1 = lane + 32 < ns ? stg[lane + 32] : 0ull;
+    unsigned long long e0 = lane < ns ? stg[lane] : 0ull;
+    unsigned long long e1 = lane + 32 < ns ? stg[lane + 32] : 0ull;
     __syncwarp();
-    int rank0 = 0, rank1 = 0;
-#pragma unroll 4
-    for (int s2 = 0; s2 < 32; ++s2) {
-      const unsigned long long o0 = __shfl_sync(0xffffffffu, e0, s2);
-      const unsigned long long o1 = __shfl_sync(0xffffffffu, e1, s2);
-      rank0 += (o0 > e0) + (o1 > e0);
-      rank1 += (o0 > e1) + (o1 > e1);
-    }
-    if (e0 != 0ull && rank0 < k) idx[g * k + rank0] = key_index(e0);
-    if (e1 != 0ull && rank1 < k) idx[g * k + rank1] = key_index(e1);
+    sel::sort64_desc(e0, e1, lane);                         // distinct keys, best first
+    if (e0 != 0ull && lane < k) idx[g * k + lane] = key_index(e0);
+    if (e1 != 0ull && lane + 32 < k) idx[g * k + lane + 32] = key_index(e1);
     if (bad && lane == 0) fb_rows[atomicAdd(fb_count, 1)] = static_cast<int>(g);
   }
 }
