@@ -24,7 +24,7 @@
 namespace dg {
 
 constexpr int kTcKeyTile = 64;          // keys per MMA tile (UMMA N)
-constexpr uint32_t kTileBytes = 2 * tc::kUnitBytes + kTcKeyTile * 4;   // plane0 | plane1 | 64 key norms
+constexpr uint32_t kTileBytes = 2 * tc::kUnitBytes + kTcKeyTile * 4;   // plane0 | plane1 | 64 negated key norms
 constexpr uint32_t kStageBytes = 17 * 1024;                             // smem slot (planes stay 1024-aligned)
 constexpr int kTcStages = 6;
 // error model of the filter (see DESIGN.md "kNN filter bound")
@@ -94,7 +94,7 @@ __global__ void knn_tc_prep_kernel(const float* __restrict__ rows, int ld, int N
       *reinterpret_cast<uint4*>(tile + p * tc::kUnitBytes + off) = *reinterpret_cast<const uint4*>(h);
     }
     if (ch == 0) {
-      reinterpret_cast<float*>(tile + 2 * tc::kUnitBytes)[rl] = sq;       // centred squared norm (0 for padding rows)
+      reinterpret_cast<float*>(tile + 2 * tc::kUnitBytes)[rl] = -sq;      // MINUS the centred squared norm (0 for padding rows)
       if (n < N) {
         normc[static_cast<size_t>(b) * N + n] = sq;
         atomicMax(maxnormc_bits + b, __float_as_uint(sq));
@@ -278,9 +278,12 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
       const float* kn = reinterpret_cast<const float*>(Bs + s * kStageBytes + 2 * tc::kUnitBytes) + cq * 16;
       const int jn = N - (i * kTcKeyTile + cq * 16);
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const float sc = __fmaf_rn(v[c], 2.0f, -kn[c]);
-        if (sc > top[7] && c < jn) top8_insert(top, sc);
+      for (int c = 0; c < 16; c += 2) {
+        // two keys per FFMA2 (same roundings as the scalar form)
+        const float2 kk = *reinterpret_cast<const float2*>(kn + c);
+        const float2 sc2 = __ffma2_rn(make_float2(v[c], v[c + 1]), make_float2(2.0f, 2.0f), kk);
+        if (sc2.x > top[7] && c < jn) top8_insert(top, sc2.x);
+        if (sc2.y > top[7] && c + 1 < jn) top8_insert(top, sc2.y);
       }
       tc::fence_before_sync();
       __syncwarp();
@@ -308,10 +311,16 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
       const int j0 = (i - T1) * kTcKeyTile + cq * 16;
       const int jn = row_ok ? N - j0 : 0;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const float sc = __fmaf_rn(v[c], 2.0f, -kn[c]);    // approx of 2 x_i.x_j - |x_j|^2 (|x_i|^2 is constant per row)
-        if (sc > tau && c < jn) {
-          if (n < kSubCands) mycand[n] = make_key(sc, j0 + c);
+      for (int c = 0; c < 16; c += 2) {
+        // approx of 2 x_i.x_j - |x_j|^2 (|x_i|^2 is constant per row), two keys per FFMA2
+        const float2 kk = *reinterpret_cast<const float2*>(kn + c);
+        const float2 sc2 = __ffma2_rn(make_float2(v[c], v[c + 1]), make_float2(2.0f, 2.0f), kk);
+        if (sc2.x > tau && c < jn) {
+          if (n < kSubCands) mycand[n] = make_key(sc2.x, j0 + c);
+          ++n;
+        }
+        if (sc2.y > tau && c + 1 < jn) {
+          if (n < kSubCands) mycand[n] = make_key(sc2.y, j0 + c + 1);
           ++n;
         }
       }
