@@ -55,6 +55,12 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&v)[32], int lane) 
   }
 }
 
+// 8 consecutive floats (32-byte aligned in shared memory) as two 16-byte loads
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
 // ---- small synchronisation helpers of the warp-specialised kernels -----------------------------------------
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

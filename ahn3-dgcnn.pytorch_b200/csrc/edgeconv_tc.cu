@@ -470,15 +470,23 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
       }
     }
     __syncthreads();  // S0b: gs / args staged
+    // per-column constants and the point's (g, arg) come in as 16-byte / 8-byte shared loads: scalar loads here made
+    // the kernel MIO-bound (ncu: mio_throttle was the top stall)
 #pragma unroll
     for (int c8 = 0; c8 < 4; ++c8) {
+      const int c0 = half * 32 + c8 * 8;
+      float pm[8], ps[8], pb[8], kA[8], kB[8], gg[8];
+      ld8(aff + c0, pm); ld8(aff + 64 + c0, ps); ld8(aff + 128 + c0, pb);
+      ld8(cb + c0, kA); ld8(cb + 64 + c0, kB);
+      ld8(gs + erp * kCout + c0, gg);
+      const uint2 a8 = *reinterpret_cast<const uint2*>(args + erp * kCout + c0);
       float h[8], d[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const int c = half * 32 + c8 * 8 + e;
-        h[e] = valid ? lrelu(bn_apply(ya[c8 * 8 + e], aff[c], aff[64 + c], aff[128 + c])) : 0.f;
-        const float dz = (args[erp * kCout + c] == ers) ? gs[erp * kCout + c] : 0.f;
-        d[e] = valid ? __fmaf_rn(cb[c], dz, -cb[64 + c]) : 0.f;                    // D' = cA dz - cB
+        h[e] = valid ? lrelu(bn_apply(ya[c8 * 8 + e], pm[e], ps[e], pb[e])) : 0.f;
+        const int ab = static_cast<int>(((e < 4 ? a8.x : a8.y) >> (8 * (e & 3))) & 0xffu);
+        const float dz = (ab == ers) ? gg[e] : 0.f;
+        d[e] = valid ? __fmaf_rn(kA[e], dz, -kB[e]) : 0.f;                          // D' = cA dz - cB
       }
       store_split<2>(Hp, kPlA, erow, half * 4 + c8, h);
       store_split<2>(DYp, kPlA, erow, half * 4 + c8, d);
@@ -531,10 +539,13 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           float o[4];
+          const float4 pm = *reinterpret_cast<const float4*>(aff + half * 32 + i);
+          const float4 ps = *reinterpret_cast<const float4*>(aff + 64 + half * 32 + i);
+          const float4 pb = *reinterpret_cast<const float4*>(aff + 128 + half * 32 + i);
+          const float pmv[4] = {pm.x, pm.y, pm.z, pm.w}, psv[4] = {ps.x, ps.y, ps.z, ps.w}, pbv[4] = {pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int col = half * 32 + i + e;
-            const float z = bn_apply(ya[i + e], aff[col], aff[64 + col], aff[128 + col]);
+            const float z = bn_apply(ya[i + e], pmv[e], psv[e], pbv[e]);
             o[e] = v[i + e] * (z > 0.f ? 1.f : kSlope);
             v[i + e] = o[e];
             w[i + e] = o[e] * ya[i + e];
