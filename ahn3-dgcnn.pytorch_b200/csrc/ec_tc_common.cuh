@@ -8,7 +8,8 @@ namespace dg {
 
 constexpr uint32_t kPlA = 128 * 128;   // bytes of one A plane (128 rows x 64 bf16)
 constexpr uint32_t kPlW = 64 * 128;    // bytes of one weight plane
-constexpr int kYs = 65;                // row stride of the FP32 tile parked over the A planes
+constexpr int kYs = 68;                // row stride of the FP32 tile parked over the A planes: 16-byte row accesses
+                                       // (thread = row) and 4-byte column accesses (thread = column) are both conflict-free
 
 // 8 consecutive channels (chunk ch) of tile row r -> NP bf16 planes (x = x1 + x2 (+ x3)), swizzled.
 // Packed conversions: one cvt.rn.bf16x2 per pair and plane; the residual is exact in FP32.
@@ -55,6 +56,10 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&v)[32], int lane) 
   }
 }
 
+__device__ __forceinline__ void ld4v(const float* p, float* v) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
 // 8 consecutive floats (32-byte aligned in shared memory) as two 16-byte loads
 __device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);

@@ -196,11 +196,10 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
             v[4] -= d.x; v[5] -= d.y; v[6] -= d.z; v[7] -= d.w;
           }
         } else if (ok[it]) {
+          float pm[8], ps[8], pb[8];
+          ld8(aff + ch * 8, pm); ld8(aff + 64 + ch * 8, ps); ld8(aff + 128 + ch * 8, pb);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = ch * 8 + e;
-            v[e] = lrelu(bn_apply(v[e], aff[c], aff[64 + c], aff[128 + c]));             // h = LReLU(BN_a(y_a))
-          }
+          for (int e = 0; e < 8; ++e) v[e] = lrelu(bn_apply(v[e], pm[e], ps[e], pb[e]));      // h = LReLU(BN_a(y_a))
         }
         store_split3(Ap, kPlA, row, ch, v);
       }
@@ -224,9 +223,11 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
       const float* vr = Vs + erp * kCout + half * 32;
       const bool valid = erow < nvalid;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int col = half * 32 + i;
-        v[i] = valid ? lrelu(bn_apply(v[i] + vr[i], aff[col], aff[64 + col], aff[128 + col])) : 0.f;
+      for (int i = 0; i < 32; i += 4) {
+        float c4[4], pm[4], ps[4], pb[4];
+        ld4v(vr + i, c4); ld4v(aff + half * 32 + i, pm); ld4v(aff + 64 + half * 32 + i, ps); ld4v(aff + 128 + half * 32 + i, pb);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[i + e] = valid ? lrelu(bn_apply(v[i + e] + c4[e], pm[e], ps[e], pb[e])) : 0.f;
       }
       if (p.two) {
         tc::fence_before_sync();
@@ -251,25 +252,30 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
         tc::fence_after_sync();
         tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + half * 32, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = half * 32 + i;
-          v[i] = lrelu(bn_apply(v[i], affB[col], affB[64 + col], affB[128 + col]));
+        for (int i = 0; i < 32; i += 4) {
+          float pm[4], ps[4], pb[4];
+          ld4v(affB + half * 32 + i, pm); ld4v(affB + 64 + half * 32 + i, ps); ld4v(affB + 128 + half * 32 + i, pb);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[i + e] = lrelu(bn_apply(v[i + e], pm[e], ps[e], pb[e]));
         }
       }
-      float* dst = Ys + erow * kYs + half * 32;
+      float4* dst = reinterpret_cast<float4*>(Ys + erow * kYs + half * 32);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) dst[i] = v[i];
+      for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     } else {
       float v[32];
       tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + half * 32, v);
-      float* dst = Ys + erow * kYs + half * 32;
+      float4* dst = reinterpret_cast<float4*>(Ys + erow * kYs + half * 32);
       if (MODE == MODE_TRAIN_A) {
-        const float* vr = Vs + erp * kCout + half * 32;
+        const float4* vr = reinterpret_cast<const float4*>(Vs + erp * kCout + half * 32);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) dst[i] = v[i] + vr[i];
+        for (int i = 0; i < 8; ++i) {
+          const float4 c = vr[i];
+          dst[i] = make_float4(v[4 * i] + c.x, v[4 * i + 1] + c.y, v[4 * i + 2] + c.z, v[4 * i + 3] + c.w);
+        }
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) dst[i] = v[i];
+        for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
     }
     tc::fence_before_sync();
@@ -288,17 +294,28 @@ __global__ void __launch_bounds__(kThreads, 2) ec_tc_fwd_kernel(const EcK p) {
     // ---- batch statistics of the raw conv output (valid rows only) ----------------------------------------------
     {
       const int r_lo = sg * 32, r_hi = min(r_lo + 32, nvalid);
-      for (int r = r_lo; r < r_hi; ++r) {
-        const float y = Ys[r * kYs + sc];
-        t1 += y;
-        t2 = __fmaf_rn(y, y, t2);
+      float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};      // four chains: the loop is latency-bound otherwise
+      int r = r_lo;
+      for (; r + 3 < r_hi; r += 4) {
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float y = Ys[(r + c4) * kYs + sc];
+          a1[c4] += y;
+          a2[c4] = __fmaf_rn(y, y, a2[c4]);
+        }
       }
+      for (; r < r_hi; ++r) {
+        const float y = Ys[r * kYs + sc];
+        a1[0] += y;
+        a2[0] = __fmaf_rn(y, y, a2[0]);
+      }
+      t1 += (a1[0] + a1[1]) + (a1[2] + a1[3]);
+      t2 += (a2[0] + a2[1]) + (a2[2] + a2[3]);
     }
     if (MODE == MODE_TRAIN_A) {
       for (int i = tid; i < nvalid * 16; i += kThreads) {
         const int row = i >> 4, c4 = i & 15;
-        const float* s = Ys + row * kYs + 4 * c4;
-        *reinterpret_cast<float4*>(p.y_a_out + (e0 + row) * kCout + 4 * c4) = make_float4(s[0], s[1], s[2], s[3]);
+        *reinterpret_cast<float4*>(p.y_a_out + (e0 + row) * kCout + 4 * c4) = *reinterpret_cast<const float4*>(Ys + row * kYs + 4 * c4);
       }
     }
     if (MODE == MODE_TRAIN_B || !p.two) {
