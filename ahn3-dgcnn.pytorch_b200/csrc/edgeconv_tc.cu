@@ -607,14 +607,23 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
   if (warp == 0) tc::tmem_dealloc(taddr, 128);
 }
 
-// T[128][64] = sum over the CTAs of their partials (FP64, fixed order) -> scratch behind the partials
+// T[128][64] = sum over the CTAs of their partials (FP64, fixed order) -> scratch behind the partials.
+// 32 outputs x 8 part-groups per CTA: group g adds parts g, g+8, ... (coalesced 128-byte rows), then the 8 group sums
+// are added in order.
 __global__ void __launch_bounds__(256) ec_tc_dw_sum_kernel(const float* __restrict__ dw_partials, int nparts, float* __restrict__ T) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * kCout * kCout) return;
+  __shared__ double red[8][32];
+  const int o = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
   double s = 0.0;
-#pragma unroll 8
-  for (int c = 0; c < nparts; ++c) s += dw_partials[static_cast<size_t>(c) * 2 * kCout * kCout + i];
-  T[i] = static_cast<float>(s);
+#pragma unroll 4
+  for (int c = g; c < nparts; c += 8) s += dw_partials[static_cast<size_t>(c) * 2 * kCout * kCout + o];
+  red[g][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (g == 0) {
+    double a = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a += red[q][threadIdx.x];
+    T[o] = static_cast<float>(a);
+  }
 }
 // dW_b[c][j] = T[c][j] - cC_c * sum_i W_b[c][i] T[64 + i][j]
 __global__ void __launch_bounds__(256) ec_tc_dw_finish_kernel(const float* __restrict__ T, const float* __restrict__ w_b,
@@ -632,7 +641,7 @@ int launch_ec_tc_bwd_b(const EcK& p, const float* g, const uint8_t* arg, const f
   DG_CUDA(cudaFuncSetAttribute(ec_tc_bwd_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcTcBwdSmem::bytes)));
   ec_tc_bwd_b_kernel<<<grid, kThreads, EcTcBwdSmem::bytes, st>>>(p, g, arg, coef_b, dz_a, dw_partials);
   float* T = dw_partials + static_cast<size_t>(kMaxPartialCtas) * 2 * kCout * kCout;
-  ec_tc_dw_sum_kernel<<<(2 * kCout * kCout + 255) / 256, 256, 0, st>>>(dw_partials, grid, T);
+  ec_tc_dw_sum_kernel<<<2 * kCout * kCout / 32, 256, 0, st>>>(dw_partials, grid, T);
   ec_tc_dw_finish_kernel<<<(kCout * kCout + 255) / 256, 256, 0, st>>>(T, p.w_b, coef_b, dw_b);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;

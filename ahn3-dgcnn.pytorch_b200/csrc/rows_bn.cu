@@ -182,6 +182,44 @@ __global__ void __launch_bounds__(kRbThreads) rows_bn_apply_kernel(RowsBn p, con
   }
 }
 
+// out[seg][c] = sum over the N rows of segment seg of x[row][c]  (per-block bias gradient of conv7, colsum(feat)).
+// grid (parts, segments): CTA (p, seg) sums a contiguous slice of the segment's rows -> FP64 partial; a second pass adds
+// the parts in order.  Same thread mapping as the BN reductions.
+__global__ void __launch_bounds__(kRbThreads) rows_colsum_partial_kernel(const float* __restrict__ x, int C, int N, int rows_per_cta,
+                                                                        double* __restrict__ partials) {
+  __shared__ float4 red[kRbThreads];
+  const int c4n = C >> 2, RL = kRbThreads / c4n;
+  const int cg = threadIdx.x % c4n, rl = threadIdx.x / c4n;
+  const int seg = blockIdx.y;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
+  const float* base = x + static_cast<size_t>(seg) * N * C;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = r0 + rl; r < r1; r += RL) {
+    const float4 v = ld4(base + static_cast<size_t>(r) * C + 4 * cg);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < c4n) {
+    double acc[4] = {0, 0, 0, 0};
+    for (int l = 0; l < RL; ++l) {
+      const float4 a = red[l * c4n + cg];
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    }
+    double* dst = partials + (static_cast<size_t>(seg) * gridDim.x + blockIdx.x) * C + 4 * cg;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dst[e] = acc[e];
+  }
+}
+__global__ void rows_colsum_finish_kernel(const double* __restrict__ partials, int nparts, int C, int nseg, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nseg * C) return;
+  const int seg = i / C, c = i - seg * C;
+  double s = 0.0;
+  for (int q = 0; q < nparts; ++q) s += partials[(static_cast<size_t>(seg) * nparts + q) * C + c];
+  out[i] = static_cast<float>(s);
+}
+
 static bool rows_bn_shape_ok(int C) { return C == 64 || C == 128 || C == 256 || C == 512 || C == 1024; }
 
 static int rows_bn_grid(int M, int* rows_per_cta) {
@@ -251,6 +289,29 @@ extern "C" int dgcnn_rows_bn_lrelu_bwd(const float* dh, const float* y, int M, i
   rows_bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partials, grid, C, static_cast<double>(M), gamma, rstd, dgamma, dbeta, coef);
   const int blocks = rows_bn_apply_grid(M, C);
   rows_bn_apply_kernel<true><<<blocks, kRbThreads, 0, st>>>(p, dh, coef, dy);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}
+
+extern "C" size_t dgcnn_rows_colsum_workspace_bytes(int M, int C, int N) {
+  if (M <= 0 || C <= 0 || N <= 0) return 0;
+  return static_cast<size_t>(M / N) * 64 * C * sizeof(double);
+}
+
+extern "C" int dgcnn_rows_colsum_f32(const float* x, int M, int C, int N, float* out, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+  DG_REQUIRE(x && out && workspace, DGCNN_E_INVALID, "rows_colsum: null pointer");
+  DG_REQUIRE(rows_bn_shape_ok(C), DGCNN_E_UNSUPPORTED, "rows_colsum: C must be 64, 128, 256, 512 or 1024");
+  DG_REQUIRE(M > 0 && N > 0 && M % N == 0, DGCNN_E_INVALID, "rows_colsum: M must be a multiple of N");
+  DG_REQUIRE(workspace_bytes >= dgcnn_rows_colsum_workspace_bytes(M, C, N), DGCNN_E_INVALID, "rows_colsum: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nseg = M / N;
+  const int sms = std::max(1, num_sms());
+  const int parts = std::max(1, std::min(64, std::min(N, (sms * 4 + nseg - 1) / nseg)));
+  const int rpc = (N + parts - 1) / parts;
+  const int nparts = (N + rpc - 1) / rpc;
+  rows_colsum_partial_kernel<<<dim3(nparts, nseg), kRbThreads, 0, st>>>(x, C, N, rpc, static_cast<double*>(workspace));
+  rows_colsum_finish_kernel<<<(nseg * C + 255) / 256, 256, 0, st>>>(static_cast<const double*>(workspace), nparts, C, nseg, out);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
 }

@@ -269,6 +269,19 @@ class GlobalFeature(torch.autograd.Function):
         return dfeat, dw, s2, s1, None, None, None, None
 
 
+def rows_colsum(x: torch.Tensor, N: int) -> torch.Tensor:
+    """x[M,C] -> [M/N, C]: column sums of every block of N rows (deterministic FP64 two-pass reduction)."""
+    lib = _lib.load()
+    M, Cn = x.shape
+    if not lib.dgcnn_rows_bn_supported(Cn) or M % N:
+        return x.view(-1, N, Cn).sum(1)
+    x = x.contiguous()
+    out = torch.empty(M // N, Cn, dtype=torch.float32, device=x.device)
+    ws = torch.empty(lib.dgcnn_rows_colsum_workspace_bytes(M, Cn, N), dtype=torch.uint8, device=x.device)
+    _call("dgcnn_rows_colsum_f32", _ptr(x), M, Cn, N, _ptr(out), _ptr(ws), ws.numel(), _stream())
+    return out
+
+
 class RowsBnLrelu(torch.autograd.Function):
     """h = LeakyReLU(BatchNorm1d(y + bias[block])) on point-major rows y[M,C] (model.py:131-139,179-184), two fused
     passes forward and two backward instead of the library's five and eight."""
@@ -303,7 +316,7 @@ class RowsBnLrelu(torch.autograd.Function):
         dbeta = torch.empty_like(dgamma)
         _call("dgcnn_rows_bn_lrelu_bwd", _ptr(dh), _ptr(y), M, Cn, _ptr(bias), ctx.N, _ptr(gamma), _ptr(stat[1]), _ptr(aff),
               _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(ctx.ws), ctx.ws.numel(), _stream())
-        dbias = None if bias is None else dy.view(-1, ctx.N, Cn).sum(1)
+        dbias = None if bias is None else rows_colsum(dy, ctx.N)
         return dy, dbias, dgamma, dbeta, None, None, None
 
 

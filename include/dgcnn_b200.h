@@ -195,6 +195,12 @@ int dgcnn_rows_bn_lrelu_bwd(const float* dh, const float* y, int M, int C, const
                             const float* rstd, const float* aff, float* dy, float* dgamma, float* dbeta,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* out[s][c] = sum_{n < N} x[s*N + n][c] for the M/N segments of x[M,C] (the per-block bias gradient `dy.view(B,N,C).sum(1)`
+ * of the conv7 split, column sums of the features); deterministic two-pass FP64 reduction.                            */
+size_t dgcnn_rows_colsum_workspace_bytes(int M, int C, int N);
+int dgcnn_rows_colsum_f32(const float* x, int M, int C, int N, float* out, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
 /* debug: exercises MN-major tcgen05 operand descriptors on one 128x64 tile pair (tests only) */
 int dgcnn_debug_mn_lab(const float* X, const float* Y, float* D, int lbo_a, int sbo_a, int lbo_b, int sbo_b,
                        int kstep, int a_major, int b_major, void* stream);

@@ -82,3 +82,14 @@ def test_rows_bn_lrelu_inference_uses_running_stats(pkg):
 def test_rows_bn_rejects_unsupported_width(pkg):
     lib = pkg._lib.load()
     assert lib.dgcnn_rows_bn_supported(512) == 1 and lib.dgcnn_rows_bn_supported(100) == 0
+
+
+@pytest.mark.parametrize("B,N,C", [(8, 7000, 512), (3, 101, 64), (1, 5000, 256)])
+def test_rows_colsum_matches_fp64(pkg, B, N, C):
+    g = torch.Generator().manual_seed(B + N + C)
+    x = torch.randn(B * N, C, generator=g).to(DEV)
+    out = pkg.ops.rows_colsum(x, N)
+    ref = x.double().view(B, N, C).sum(1)
+    assert out.shape == (B, C)
+    assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 1e-6
+    assert torch.equal(out, pkg.ops.rows_colsum(x, N))          # deterministic
