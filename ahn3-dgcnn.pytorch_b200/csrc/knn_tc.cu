@@ -94,7 +94,9 @@ __global__ void knn_tc_prep_kernel(const float* __restrict__ rows, int ld, int N
       *reinterpret_cast<uint4*>(tile + p * tc::kUnitBytes + off) = *reinterpret_cast<const uint4*>(h);
     }
     if (ch == 0) {
-      reinterpret_cast<float*>(tile + 2 * tc::kUnitBytes)[rl] = -sq;      // MINUS the centred squared norm (0 for padding rows)
+      // MINUS the centred squared norm; -inf for padding keys: their score 2*0 - inf never passes a threshold, so the
+      // scans need no per-key bounds check
+      reinterpret_cast<float*>(tile + 2 * tc::kUnitBytes)[rl] = n < N ? -sq : -INFINITY;
       if (n < N) {
         normc[static_cast<size_t>(b) * N + n] = sq;
         atomicMax(maxnormc_bits + b, __float_as_uint(sq));
@@ -276,14 +278,13 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
       float v[16];
       tc::tmem_ld16(taddr + tlane + a * kTcKeyTile + cq * 16, v);
       const float* kn = reinterpret_cast<const float*>(Bs + s * kStageBytes + 2 * tc::kUnitBytes) + cq * 16;
-      const int jn = N - (i * kTcKeyTile + cq * 16);
 #pragma unroll
       for (int c = 0; c < 16; c += 2) {
-        // two keys per FFMA2 (same roundings as the scalar form)
+        // two keys per FFMA2 (same roundings as the scalar form); padding keys score -inf
         const float2 kk = *reinterpret_cast<const float2*>(kn + c);
         const float2 sc2 = __ffma2_rn(make_float2(v[c], v[c + 1]), make_float2(2.0f, 2.0f), kk);
-        if (sc2.x > top[7] && c < jn) top8_insert(top, sc2.x);
-        if (sc2.y > top[7] && c + 1 < jn) top8_insert(top, sc2.y);
+        if (sc2.x > top[7]) top8_insert(top, sc2.x);
+        if (sc2.y > top[7]) top8_insert(top, sc2.y);
       }
       tc::fence_before_sync();
       __syncwarp();
@@ -301,6 +302,7 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
     // ---- pass 2: collect every key above tau ------------------------------------------------------------------------
     unsigned long long* mycand = cand + ((static_cast<size_t>(b) * N + q0 + erow) * 4 + cq) * kSubCands;
     int n = 0;
+    const float tau_eff = row_ok ? tau : INFINITY;       // rows past the end of the block collect nothing
     for (int i = T1; i < TT; ++i) {
       const int s = i % kTcStages, a = i % kAccs;
       tc::mbar_wait(accfull + a, (i / kAccs) & 1);
@@ -309,19 +311,22 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
       tc::tmem_ld16(taddr + tlane + a * kTcKeyTile + cq * 16, v);
       const float* kn = reinterpret_cast<const float*>(Bs + s * kStageBytes + 2 * tc::kUnitBytes) + cq * 16;
       const int j0 = (i - T1) * kTcKeyTile + cq * 16;
-      const int jn = row_ok ? N - j0 : 0;
 #pragma unroll
       for (int c = 0; c < 16; c += 2) {
-        // approx of 2 x_i.x_j - |x_j|^2 (|x_i|^2 is constant per row), two keys per FFMA2
+        // approx of 2 x_i.x_j - |x_j|^2 (|x_i|^2 is constant per row), two keys per FFMA2.  The warp-uniform vote keeps
+        // the common case (no lane has a candidate) free of divergence bookkeeping.
         const float2 kk = *reinterpret_cast<const float2*>(kn + c);
         const float2 sc2 = __ffma2_rn(make_float2(v[c], v[c + 1]), make_float2(2.0f, 2.0f), kk);
-        if (sc2.x > tau && c < jn) {
-          if (n < kSubCands) mycand[n] = make_key(sc2.x, j0 + c);
-          ++n;
-        }
-        if (sc2.y > tau && c + 1 < jn) {
-          if (n < kSubCands) mycand[n] = make_key(sc2.y, j0 + c + 1);
-          ++n;
+        const bool h0 = sc2.x > tau_eff, h1 = sc2.y > tau_eff;
+        if (__any_sync(0xffffffffu, h0 || h1)) {
+          if (h0) {
+            if (n < kSubCands) mycand[n] = make_key(sc2.x, j0 + c);
+            ++n;
+          }
+          if (h1) {
+            if (n < kSubCands) mycand[n] = make_key(sc2.y, j0 + c + 1);
+            ++n;
+          }
         }
       }
       tc::fence_before_sync();
