@@ -152,20 +152,29 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 
 // Issue the split-precision product of one 64-wide K atom: A planes at a_s (+ p*a_plane bytes), B likewise.
 // Pairs are issued smallest-magnitude first.  `first` = true overwrites the accumulator with the first MMA.
+// Descriptor of an address `byte_off` bytes after the one `base_lo` was built for: only the 14-bit start-address field
+// changes (shared memory < 256 KB, so no carry leaves the field) — one integer add per MMA instead of rebuilding the
+// descriptor.  The MMA-issuing thread is a single in-order instruction stream on the critical path of every tile.
+__device__ __forceinline__ uint64_t desc_at(uint32_t base_lo, uint32_t hi, uint32_t byte_off) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(base_lo + (byte_off >> 4)), "r"(hi));
+  return d;
+}
 template <int NS>
 __device__ __forceinline__ void mma_split_katom(uint32_t taddr, uint32_t a_s, uint32_t a_plane, uint32_t b_s,
                                                 uint32_t b_plane, uint32_t idesc, bool first) {
   uint32_t acc = first ? 0u : 1u;
+  const uint64_t da = smem_desc_sw128(a_s), db = smem_desc_sw128(b_s);
+  const uint32_t a_lo = static_cast<uint32_t>(da), b_lo = static_cast<uint32_t>(db), hi = static_cast<uint32_t>(da >> 32);
 #pragma unroll
   for (int sum = NS + 1; sum >= 2; --sum) {
 #pragma unroll
     for (int i = 1; i <= NS; ++i) {
       const int j = sum - i;
       if (j < 1 || j > NS) continue;
-      const uint32_t a0 = a_s + (i - 1) * a_plane, b0 = b_s + (j - 1) * b_plane;
 #pragma unroll
       for (int k16 = 0; k16 < kUnitK / 16; ++k16) {
-        mma_bf16(taddr, smem_desc_sw128(a0 + k16 * 32), smem_desc_sw128(b0 + k16 * 32), idesc, acc);
+        mma_bf16(taddr, desc_at(a_lo, hi, (i - 1) * a_plane + k16 * 32), desc_at(b_lo, hi, (j - 1) * b_plane + k16 * 32), idesc, acc);
         acc = 1u;
       }
     }
