@@ -224,7 +224,7 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
 
   if (warp == kScanWarps) {
     // ===== producer + MMA issuer (one thread) =================================================================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::idesc_bf16(128, kTcKeyTile);
       tc::mbar_arrive_expect_tx(abar, KnnTcSmem::a_bytes);
 #pragma unroll
