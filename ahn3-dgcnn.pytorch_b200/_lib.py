@@ -56,6 +56,7 @@ SIGNATURES = {
     "dgcnn_rows_bn_lrelu_bwd": (c_int, [_P, _P, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "dgcnn_rows_colsum_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dgcnn_rows_colsum_f32": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "dgcnn_debug_tmem_a_lab": (c_int, [_P, _P, _P, c_int, _P]),
     "dgcnn_debug_mn_lab": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "dgcnn_tc_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "dgcnn_tc_gemm_f32": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int, c_int, c_int, c_int, c_int,

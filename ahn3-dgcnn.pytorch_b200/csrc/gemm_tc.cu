@@ -589,6 +589,70 @@ tc_mn_lab_kernel(const float* __restrict__ X, const float* __restrict__ Y, float
 }
 }  // namespace dg
 
+// debug: A operand in tensor memory.  D[128x64] = X[128x64] Y[64x64]^T with bf16-rounded inputs; X goes registers ->
+// TMEM (tcgen05.st, thread = row, 32-bit column j = K elements 2j (low half unless `swap`) and 2j+1), Y -> smem planes.
+namespace dg {
+__global__ void __launch_bounds__(128, 1)
+tc_tmem_a_lab_kernel(const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ D, int swap) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  unsigned char* Ys = sm;            // [64 rows][128 B] bf16, SWIZZLE_128B K-major
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 8192);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_barrier_init(); }
+  if (warp == 0) tc::tmem_alloc(slot, 128);          // columns 0-63: D, 64-95: A (32 words = 64 bf16 per row)
+  for (int i = tid; i < 64 * 8; i += 128) {
+    const int r = i >> 3, ch = i & 7;
+    __nv_bfloat16 hy[8];
+    for (int e = 0; e < 8; ++e) hy[e] = __float2bfloat16_rn(Y[r * 64 + ch * 8 + e]);
+    *reinterpret_cast<uint4*>(Ys + r * 128 + (((ch ^ (r & 7)) & 7) << 4)) = *reinterpret_cast<const uint4*>(hy);
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t taddr = *slot;
+  {
+    uint32_t w[32];
+    const float* xr = X + (warp * 32 + lane) * 64;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const __nv_bfloat162 h = swap ? __floats2bfloat162_rn(xr[2 * j + 1], xr[2 * j]) : __floats2bfloat162_rn(xr[2 * j], xr[2 * j + 1]);
+      w[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    tc::tmem_st32(taddr + (static_cast<uint32_t>(warp * 32) << 16) + 64, w);
+    tc::tmem_st_wait();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (tid == 0) {
+    tc::fence_after_sync();
+    constexpr uint32_t idesc = tc::idesc_bf16(128, 64);
+    for (int k16 = 0; k16 < 4; ++k16)
+      tc::mma_bf16_ts(taddr, taddr + 64 + k16 * 8, tc::smem_desc_sw128(tc::smem_u32(Ys) + k16 * 32), idesc, k16 > 0);
+    tc::mma_commit(bar);
+  }
+  __syncwarp();
+  tc::mbar_wait(bar, 0);
+  tc::fence_after_sync();
+  for (int c0 = 0; c0 < 64; c0 += 32) {
+    float v[32];
+    tc::tmem_ld32(taddr + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+    for (int i = 0; i < 32; ++i) D[(warp * 32 + lane) * 64 + c0 + i] = v[i];
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(taddr, 128);
+}
+}  // namespace dg
+
+extern "C" int dgcnn_debug_tmem_a_lab(const float* X, const float* Y, float* D, int swap, void* stream) {
+  DG_CUDA(cudaFuncSetAttribute(dg::tc_tmem_a_lab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384));
+  dg::tc_tmem_a_lab_kernel<<<1, 128, 16384, static_cast<cudaStream_t>(stream)>>>(X, Y, D, swap);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}
+
 extern "C" int dgcnn_debug_mn_lab(const float* X, const float* Y, float* D, int lbo_a, int sbo_a, int lbo_b, int sbo_b,
                                   int kstep, int a_major, int b_major, void* stream) {
   DG_CUDA(cudaFuncSetAttribute(dg::tc_mn_lab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));

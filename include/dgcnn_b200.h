@@ -205,6 +205,9 @@ int dgcnn_rows_colsum_f32(const float* x, int M, int C, int N, float* out, void*
 int dgcnn_debug_mn_lab(const float* X, const float* Y, float* D, int lbo_a, int sbo_a, int lbo_b, int sbo_b,
                        int kstep, int a_major, int b_major, void* stream);
 
+/* debug: tcgen05.mma with the A operand in tensor memory on one 128x64x64 tile (tests only) */
+int dgcnn_debug_tmem_a_lab(const float* X, const float* Y, float* D, int swap, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
