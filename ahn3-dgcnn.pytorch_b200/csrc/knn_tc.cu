@@ -382,7 +382,7 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
         ap[r] = key[r] != 0ull ? sel::key_score(key[r]) : -INFINITY;
       }
       const float tau_r = tauS[row];
-      // bisection: v with at least min(ntot, k+4) candidates strictly above it
+      // bisection: v with at least min(ntot, k) candidates strictly above it
       float lo = tau_r, hi = ap[0];
 #pragma unroll
       for (int r = 1; r < 8; ++r) hi = fmaxf(hi, ap[r]);
@@ -396,7 +396,9 @@ knn_tc_kernel(const unsigned char* __restrict__ tiles, const float* __restrict__
         for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         lo = mn - fabsf(mn) * 1e-6f - 1e-30f;
       }
-      const int want = min(ntot, k + 4);
+      // k candidates above the cut suffice: with |approx - exact - const| <= eps, a key below lo - 2 eps has k keys
+      // strictly above it in exact score.  Every extra survivor costs a 256-byte gather.
+      const int want = min(ntot, k);
       for (int it = 0; it < 10; ++it) {
         const float mid = 0.5f * (lo + hi);
         int c = 0;
