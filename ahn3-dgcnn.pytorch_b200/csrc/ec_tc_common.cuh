@@ -91,6 +91,13 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 20)) __trap();
   }
 }
+// 256-bit global load (sm_100): 8 consecutive floats, 32-byte aligned.  When one lane reads a whole row, 16-byte loads
+// request every 32-byte sector twice; this fetches it once.
+__device__ __forceinline__ void ld_global_v8(const float* src, float* v) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(src));
+}
 // 256-bit global store (sm_100): 8 consecutive floats, 32-byte aligned
 __device__ __forceinline__ void st_global_v8(float* dst, const float* v) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),

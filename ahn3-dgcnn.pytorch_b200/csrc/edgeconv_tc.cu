@@ -481,9 +481,10 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
     {
       const float* src = p.y_a_in + (e0 + (valid ? erow : 0)) * kCout + half * 32;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 y = valid ? *reinterpret_cast<const float4*>(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        ya[i] = y.x; ya[i + 1] = y.y; ya[i + 2] = y.z; ya[i + 3] = y.w;
+      for (int i = 0; i < 32; ++i) ya[i] = 0.f;
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) ld_global_v8(src + i, ya + i);      // y_a rows are 256-byte aligned (cudaMalloc'd [E,64])
       }
     }
     __syncthreads();  // S0b: gs / args staged
@@ -638,6 +639,8 @@ __global__ void __launch_bounds__(256) ec_tc_dw_finish_kernel(const float* __res
 
 int launch_ec_tc_bwd_b(const EcK& p, const float* g, const uint8_t* arg, const float* coef_b, float* dz_a,
                        float* dw_partials, float* dw_b, int grid, cudaStream_t st) {
+  DG_REQUIRE((reinterpret_cast<uintptr_t>(p.y_a_in) & 31) == 0 && (reinterpret_cast<uintptr_t>(dz_a) & 31) == 0, DGCNN_E_INVALID,
+             "edgeconv_bwd_b (tensor-core path): y_a and dz_a must be 32-byte aligned");
   DG_CUDA(cudaFuncSetAttribute(ec_tc_bwd_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcTcBwdSmem::bytes)));
   ec_tc_bwd_b_kernel<<<grid, kThreads, EcTcBwdSmem::bytes, st>>>(p, g, arg, coef_b, dz_a, dw_partials);
   float* T = dw_partials + static_cast<size_t>(kMaxPartialCtas) * 2 * kCout * kCout;
