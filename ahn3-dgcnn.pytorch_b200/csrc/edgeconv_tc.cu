@@ -568,7 +568,7 @@ ec_tc_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __re
             v[i + e] = o[e];
             w[i + e] = o[e] * ya[i + e];
           }
-          *reinterpret_cast<float4*>(dst + i) = make_float4(o[0], o[1], o[2], o[3]);
+          if (i & 4) st_global_v8(dst + i - 4, v + i - 4);      // whole 32-byte sectors of the thread's own row
         }
       } else {
 #pragma unroll
