@@ -217,7 +217,14 @@ tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __rest
         const int n0 = nt * BN + c0;
         if (row < M) {
           float* dst = D + static_cast<size_t>(row) * ldd + n0;
-          if (n0 + 32 <= N && (ldd & 3) == 0) {
+          if (n0 + 32 <= N && (ldd & 7) == 0 && (reinterpret_cast<uintptr_t>(D) & 31) == 0) {
+            // thread = output row: 32-byte stores write whole sectors (16-byte stores would touch every sector twice)
+#pragma unroll
+            for (int i = 0; i < 32; i += 8)
+              asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + i), "f"(v[i]), "f"(v[i + 1]),
+                           "f"(v[i + 2]), "f"(v[i + 3]), "f"(v[i + 4]), "f"(v[i + 5]), "f"(v[i + 6]), "f"(v[i + 7])
+                           : "memory");
+          } else if (n0 + 32 <= N && (ldd & 3) == 0) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           } else {
