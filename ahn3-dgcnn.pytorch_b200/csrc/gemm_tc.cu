@@ -404,19 +404,32 @@ extern "C" int dgcnn_tc_gemm_f32(const float* A, int64_t a_sr, int64_t a_sc, con
 // GEMM + batch statistics + per-block column extrema (conv6 + bn6 + LeakyReLU + max over the points), no D store
 // ---------------------------------------------------------------------------------------------
 namespace dg {
-// one thread per column: reduce the row-tile partials in FP64 (fixed order) and derive the BN scalars
-__global__ void colstats_bn_kernel(const float* __restrict__ stat_partials, int num_mt, int N, double count,
+// 32 columns x 8 row-tile groups per CTA: group g adds the row-tile partials g, g+8, ... in FP64 (coalesced 128-byte
+// reads), the 8 group sums are added in order (deterministic); then the BN scalars.  (One thread per column looping over
+// all 438 row tiles was a 70 us latency chain.)
+__global__ void __launch_bounds__(256) colstats_bn_kernel(const float* __restrict__ stat_partials, int num_mt, int N, double count,
                                    const float* __restrict__ gamma, float eps, float momentum, int use_batch_stats,
                                    float* running_mean, float* running_var, float* mean_out, float* rstd_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
-  double m, rs;
-  if (use_batch_stats) {
-    double s = 0.0, q = 0.0;
-    for (int i = 0; i < num_mt; ++i) {
+  __shared__ double red[2][8][32];
+  const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  double s = 0.0, q = 0.0;
+  if (use_batch_stats && c < N) {
+#pragma unroll 4
+    for (int i = g; i < num_mt; i += 8) {
       s += stat_partials[(static_cast<size_t>(i) * 2 + 0) * N + c];
       q += stat_partials[(static_cast<size_t>(i) * 2 + 1) * N + c];
     }
+  }
+  red[0][g][cl] = s;
+  red[1][g][cl] = q;
+  __syncthreads();
+  if (g != 0 || c >= N) return;
+  double m, rs;
+  if (use_batch_stats) {
+    s = 0.0; q = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s += red[0][j][cl]; q += red[1][j][cl]; }
     m = s / count;
     double var = q / count - m * m;
     if (var < 0.0) var = 0.0;
@@ -526,7 +539,7 @@ extern "C" int dgcnn_tc_gemm_bn_lrelu_segmax_f32(const float* A, int64_t a_sr, i
   GemmEpi epi{seg_len, stats, gext, gamma};
   kern<<<dim3(Np / 128, num_mt, 1), 192, SM::bytes, st>>>(Ap, Bp, nullptr, 0, M, N, KA, KA, 0, epi);
   DG_CUDA(cudaGetLastError());
-  colstats_bn_kernel<<<(N + 127) / 128, 128, 0, st>>>(stats, num_mt, N, static_cast<double>(M), gamma, eps, momentum, use_batch_stats,
+  colstats_bn_kernel<<<(N + 31) / 32, 256, 0, st>>>(stats, num_mt, N, static_cast<double>(M), gamma, eps, momentum, use_batch_stats,
                                                       running_mean, running_var, mean, rstd);
   DG_CUDA(cudaGetLastError());
   const long long items = static_cast<long long>(segments) * N;
