@@ -397,6 +397,10 @@ extern "C" int dgcnn_tc_gemm_f32(const float* A, int64_t a_sr, int64_t a_sc, con
   }
   if ((rc = launch_split<2>(A, a_sr, a_sc, M, K, Mp, KA, Ap, st))) return rc;
   if ((rc = launch_split<2>(B, b_sr, b_sc, N, K, Np, KA, Bp, st))) return rc;
+  // wide tiles where the grid stays full: a 128x256 MMA reads 12 KB of operands for 128 cycles of math (96 B/clk),
+  // a 128x128 one 8 KB for 64 (125 B/clk, at the shared-memory limit)
+  if (Np % 256 == 0 && splitk_factor(M, N, KA) == 1 && static_cast<long long>((M + 127) / 128) * (Np / 256) >= 2 * 148)
+    return launch_gemm<2, 256, 2>(Ap, Bp, D, ldd, M, N, KA, partials, st);
   return launch_gemm<2, 128, 3>(Ap, Bp, D, ldd, M, N, KA, partials, st);
 }
 
