@@ -168,7 +168,7 @@ tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __rest
   const uint32_t taddr = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (tc::elect_one()) {             // one lane, chosen with elect.sync: the issue code stays on the uniform datapath
       for (int ka = ka_lo; ka < ka_hi; ++ka) {
         const int it = ka - ka_lo, s = it % STAGES;
         tc::mbar_wait(empty + s, ((it / STAGES) & 1) ^ 1);
@@ -192,7 +192,7 @@ tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __rest
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::idesc_bf16(128, BN);
       for (int ka = ka_lo; ka < ka_hi; ++ka) {
         const int it = ka - ka_lo, s = it % STAGES;
