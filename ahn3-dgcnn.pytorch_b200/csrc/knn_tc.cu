@@ -585,13 +585,14 @@ knn_small_kernel(const float* __restrict__ rows, int ld, const float* __restrict
         float* dst = Ks + ((r >> 1) * CP + 4 * c4) * 2 + (r & 1);
         dst[0] = v.x; dst[2] = v.y; dst[4] = v.z; dst[6] = v.w;
       }
-      for (int r = tid; r < kSmallKeys; r += kThreads) Kn[r] = t0 + r < nkeys ? -norms[base + t0 + r] : 0.f;
+      // keys past the end score -inf: no per-key bounds check in the scan
+      for (int r = tid; r < kSmallKeys; r += kThreads) Kn[r] = t0 + r < nkeys ? -norms[base + t0 + r] : -INFINITY;
       __syncthreads();
       const int r0 = kq * (kSmallKeys / 4);
-      const int lim = min(kSmallKeys / 4, nkeys - t0 - r0);
       const float2 two = make_float2(2.0f, 2.0f), mnq = make_float2(-nq, -nq);
+      const float thr = pass == 0 ? 0.f : (row_ok ? tau : INFINITY);       // rows past the end of the block collect nothing
 #pragma unroll 2
-      for (int i = 0; i < lim; i += 2) {
+      for (int i = 0; i < kSmallKeys / 4; i += 2) {
         const int r = r0 + i;
         float2 d = make_float2(0.f, 0.f);
 #pragma unroll
@@ -602,15 +603,21 @@ knn_small_kernel(const float* __restrict__ rows, int ld, const float* __restrict
         }
         // model.py:37, one rounding per step: fl(fl(2 d - |x_j|^2) - |x_i|^2); the FMA chain order is the scalar one
         const float2 pd2 = __fadd2_rn(__ffma2_rn(d, two, *reinterpret_cast<const float2*>(Kn + r)), mnq);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float pd = h ? pd2.y : pd2.x;
-          if (h && i + 1 >= lim) break;
-          if (pass == 0) {
-            if (pd > top[7]) top8_insert(top, pd);
-          } else if (pd > tau && row_ok) {
-            if (n < kSubCands) mycand[n] = make_key(pd, t0 + r + h);
-            ++n;
+        if (pass == 0) {
+          if (pd2.x > top[7]) top8_insert(top, pd2.x);
+          if (pd2.y > top[7]) top8_insert(top, pd2.y);
+        } else {
+          // the warp-uniform vote keeps the common case (no lane has a candidate) free of divergence bookkeeping
+          const bool h0 = pd2.x > thr, h1 = pd2.y > thr;
+          if (__any_sync(0xffffffffu, h0 || h1)) {
+            if (h0) {
+              if (n < kSubCands) mycand[n] = make_key(pd2.x, t0 + r);
+              ++n;
+            }
+            if (h1) {
+              if (n < kSubCands) mycand[n] = make_key(pd2.y, t0 + r + 1);
+              ++n;
+            }
           }
         }
       }
