@@ -124,10 +124,12 @@ def test_knn_small_many_duplicates(pkg):
 
 
 # ---------------------------------------------------------------------------------------------- tensor-core EdgeConv
-def test_edgeconv_tc_matches_ffma_path(pkg):
-    """Train-mode forward/backward with the tcgen05 EdgeConv passes vs the FP32-FMA passes (same graphs)."""
+@pytest.mark.parametrize("N,k", [(1003, 30), (517, 20), (300, 48), (260, 7)])
+def test_edgeconv_tc_matches_ffma_path(pkg, N, k):
+    """Train-mode forward/backward with the tcgen05 EdgeConv passes vs the FP32-FMA passes (same graphs); the shapes
+    cover 4, 6, 2 and 16 points per 128-row tile and ragged last tiles."""
     lib = pkg._lib.load()
-    B, Fd, N, k = 2, 4, 1003, 30
+    B, Fd = 2, 4
     x = common.points(51, B, Fd, N, "real").to(DEV)
     w = common.weights(52, 5, Fd, 1024)
     outs = {}
