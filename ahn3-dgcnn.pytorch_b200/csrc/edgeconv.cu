@@ -705,7 +705,8 @@ extern "C" int dgcnn_edgeconv_bwd_prep(int M, const float* dout, int ld_dout, co
                                        float* g, double* partials, void* stream) {
   DG_REQUIRE(dout && ysel && aff && g && partials, DGCNN_E_INVALID, "edgeconv_bwd_prep: null pointer");
   DG_REQUIRE(M > 0 && ld_dout >= kCout, DGCNN_E_INVALID, "edgeconv_bwd_prep: bad shape");
-  const int blocks = std::max(1, std::min((M + 3) / 4, 2 * 148));
+  // a latency-bound streaming pass (each thread walks M / (4 blocks) points with dependent 4-byte loads): many CTAs
+  const int blocks = std::max(1, std::min((M + 3) / 4, 6 * 148));
   bwd_prep_kernel<<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(M, dout, ld_dout, ysel, aff, g, partials);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
