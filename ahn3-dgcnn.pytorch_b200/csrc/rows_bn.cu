@@ -188,13 +188,13 @@ __global__ void __launch_bounds__(kRbThreads) rows_bn_apply_kernel(RowsBn p, con
 __global__ void __launch_bounds__(kRbThreads) rows_colsum_partial_kernel(const float* __restrict__ x, int C, int N, int rows_per_cta,
                                                                         double* __restrict__ partials) {
   __shared__ float4 red[kRbThreads];
-  const int c4n = C >> 2, RL = kRbThreads / c4n;
+  const int c4n = C >> 2, RL = kRbThreads / c4n;            // any C % 4 == 0, C <= 1024: threads >= c4n * RL idle
   const int cg = threadIdx.x % c4n, rl = threadIdx.x / c4n;
   const int seg = blockIdx.y;
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
   const float* base = x + static_cast<size_t>(seg) * N * C;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = r0 + rl; r < r1; r += RL) {
+  for (int r = r0 + rl; r < r1 && rl < RL; r += RL) {
     const float4 v = ld4(base + static_cast<size_t>(r) * C + 4 * cg);
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
@@ -301,7 +301,8 @@ extern "C" size_t dgcnn_rows_colsum_workspace_bytes(int M, int C, int N) {
 extern "C" int dgcnn_rows_colsum_f32(const float* x, int M, int C, int N, float* out, void* workspace, size_t workspace_bytes,
                                      void* stream) {
   DG_REQUIRE(x && out && workspace, DGCNN_E_INVALID, "rows_colsum: null pointer");
-  DG_REQUIRE(rows_bn_shape_ok(C), DGCNN_E_UNSUPPORTED, "rows_colsum: C must be 64, 128, 256, 512 or 1024");
+  DG_REQUIRE(C % 4 == 0 && C <= 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, DGCNN_E_UNSUPPORTED,
+             "rows_colsum: C must be a multiple of 4, at most 1024, x 16-byte aligned");
   DG_REQUIRE(M > 0 && N > 0 && M % N == 0, DGCNN_E_INVALID, "rows_colsum: M must be a multiple of N");
   DG_REQUIRE(workspace_bytes >= dgcnn_rows_colsum_workspace_bytes(M, C, N), DGCNN_E_INVALID, "rows_colsum: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);

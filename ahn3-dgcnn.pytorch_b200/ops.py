@@ -265,7 +265,7 @@ class GlobalFeature(torch.autograd.Function):
         # dW
         t1 = (gdz.unsqueeze(-1) * feat[idx].view(B, E, -1)).sum(0)     # [E,K] = dz^T feat
         f2 = tc_gemm(feat.t(), feat.t(), nsplit=2)                     # [K,K] = feat^T feat (split-K over the points)
-        dw = a[:, None] * t1 - bprime[:, None] * feat.sum(0)[None, :] - kappa[:, None] * (w @ f2)
+        dw = a[:, None] * t1 - bprime[:, None] * rows_colsum(feat, M) - kappa[:, None] * (w @ f2)
         return dfeat, dw, s2, s1, None, None, None, None
 
 
@@ -273,7 +273,7 @@ def rows_colsum(x: torch.Tensor, N: int) -> torch.Tensor:
     """x[M,C] -> [M/N, C]: column sums of every block of N rows (deterministic FP64 two-pass reduction)."""
     lib = _lib.load()
     M, Cn = x.shape
-    if not lib.dgcnn_rows_bn_supported(Cn) or M % N:
+    if Cn % 4 or Cn > 1024 or M % N:
         return x.view(-1, N, Cn).sum(1)
     x = x.contiguous()
     out = torch.empty(M // N, Cn, dtype=torch.float32, device=x.device)

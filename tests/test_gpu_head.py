@@ -84,7 +84,7 @@ def test_rows_bn_rejects_unsupported_width(pkg):
     assert lib.dgcnn_rows_bn_supported(512) == 1 and lib.dgcnn_rows_bn_supported(100) == 0
 
 
-@pytest.mark.parametrize("B,N,C", [(8, 7000, 512), (3, 101, 64), (1, 5000, 256)])
+@pytest.mark.parametrize("B,N,C", [(8, 7000, 512), (3, 101, 64), (1, 5000, 256), (1, 56000, 192), (2, 333, 20)])
 def test_rows_colsum_matches_fp64(pkg, B, N, C):
     g = torch.Generator().manual_seed(B + N + C)
     x = torch.randn(B * N, C, generator=g).to(DEV)
