@@ -173,6 +173,83 @@ def kernel_flops(name: str, calls_per_step: int, B: int):
     return 0.0
 
 
+# ------------------------------------------------------------------------------------------------ extras
+def _event_ms(fn, iters):
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def layer_times(pkg, dev):
+    """kNN + EdgeConv block (train mode) per layer at the bench shape: forward and forward+backward, microseconds."""
+    ops = pkg.ops
+    g = torch.Generator().manual_seed(1)
+    B, N, k = B_PER_GPU, NPTS, KNN
+    M = B * N
+    out = {}
+    for name, Cn, two in (("L1 (C=4, conv1+conv2)", FEAT, True), ("L2 (C=64, conv3+conv4)", 64, True), ("L3 (C=64, conv5)", 64, False)):
+        x = (torch.randn(B, Cn, N, generator=g) if Cn > 4 else make_batch(7, B)[0]).to(dev)
+        rows = ops.pack_rows(x)
+        wa = (torch.randn(64, 2 * Cn, 1, 1, generator=g) * 0.1).to(dev).requires_grad_(True)
+        wb = (torch.randn(64, 64, 1, 1, generator=g) * 0.1).to(dev).requires_grad_(True) if two else None
+        ga = torch.ones(64, device=dev, requires_grad=True)
+        be = torch.zeros(64, device=dev, requires_grad=True)
+
+        def fwd(req=False):
+            r = rows.detach().requires_grad_(req)
+            idx = ops.knn_rows(r.detach(), B, Cn, N, k)
+            return r, ops.EdgeConvTrain.apply(r, idx, (B, Cn, N, k), wa, ga, be, wb, ga if two else None, be if two else None,
+                                              ops.BNState(None, None), ops.BNState(None, None) if two else None)
+
+        def fwd_bwd():
+            r, o = fwd(True)
+            o.sum().backward()
+
+        for _ in range(2):
+            fwd_bwd()
+        out[name] = {"fwd": round(1e3 * _event_ms(lambda: fwd(), 5), 1), "fwd_bwd": round(1e3 * _event_ms(fwd_bwd, 5), 1)}
+    return out
+
+
+def eager_gpu_oracle(dev):
+    """The CPU oracle's torch code run eagerly on this GPU (FP32, TF32 off): the library composition the kernels replace."""
+    from oracle import dgcnn_oracle as O
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        params = {kk: v.to(dev) for kk, v in O.init_params(CLASSES, FEAT, EMB, seed=0).items()}
+        leaves = []
+        for name, v in params.items():
+            if v.is_floating_point() and "running" not in name:
+                v.requires_grad_(True)
+                leaves.append(v)
+        net = O.OracleDGCNN(params, KNN, dropout=0.5, training=True)
+        opt = torch.optim.Adam(leaves, lr=1e-3, weight_decay=1e-4, fused=True)
+        x, y = make_batch(0, B_PER_GPU)
+        x, y = x.to(dev), y.to(dev)
+
+        def step():
+            opt.zero_grad()
+            seg_loss(net(x), y).backward()
+            opt.step()
+
+        step()
+        ms = _event_ms(step, 2)
+        return {"ms_per_step": ms, "value": B_PER_GPU * NPTS / (ms * 1e-3), "unit": UNIT,
+                "what": "oracle/dgcnn_oracle.py (torch ops of reference model.py) on this GPU, eager, FP32, same shape"}
+    except Exception as e:                       # informative only: never fail the bench line on it
+        return {"error": repr(e)[:200]}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+        torch.cuda.empty_cache()
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args, rank: int, local: int, world: int):
     import __graft_entry__ as entry
@@ -285,6 +362,11 @@ def run_ours(args, rank: int, local: int, world: int):
                 "frac": achieved / peak, "traffic": traffic, "peak_kind": kind,
                 "launches_per_step": per_kernel[dom][0] / args.steps, "ms_per_step": dom_ms / args.steps}
 
+    # ---- extras: kNN + EdgeConv per layer, and the oracle run eagerly on this GPU -----------------
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = {"layers_us": layer_times(pkg, dev), "torch_eager_gpu": eager_gpu_oracle(dev)}
+
     # ---- CPU baseline (bounded sample) -------------------------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -305,6 +387,7 @@ def run_ours(args, rank: int, local: int, world: int):
         "roofline": roof,
         "cpu_baseline": cpu,
         "kernels": breakdown,
+        "extras": extras,
     }
     print(json.dumps(line), flush=True)
 
@@ -316,6 +399,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-layer timings and the eager-GPU oracle run")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":

@@ -96,7 +96,7 @@ def graph_feature(x: torch.Tensor, k: int, idx: Optional[torch.Tensor] = None) -
     if idx is None:
         idx = knn(x, k)
     C = x.size(1)
-    flat = (idx + torch.arange(B).view(-1, 1, 1) * N).view(-1)        # model.py:64-69
+    flat = (idx + torch.arange(B, device=idx.device).view(-1, 1, 1) * N).view(-1)   # model.py:64-69
     rows = x.transpose(2, 1).contiguous()                              # [B,N,C]   model.py:73
     nbr = rows.view(B * N, -1)[flat, :].view(B, N, k, C)               # model.py:74-77
     ctr = rows.view(B, N, 1, C).repeat(1, 1, k, 1)                     # model.py:78
