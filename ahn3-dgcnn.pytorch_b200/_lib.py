@@ -29,7 +29,8 @@ SIGNATURES = {
     "dgcnn_knn_f32": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "dgcnn_knn_tc_supported": (c_int, [c_int, c_int, c_int]),
     "dgcnn_knn_tc_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "dgcnn_knn_tc_f32": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "dgcnn_knn_tc_f32": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "dgcnn_knn_tc_fallback_stats": (c_int, [_P, c_int, c_int, c_int, C.POINTER(c_int), _P]),
     "dgcnn_knn_small_supported": (c_int, [c_int, c_int, c_int]),
     "dgcnn_knn_small_workspace_bytes": (c_size_t, [c_int, c_int]),
     "dgcnn_knn_small_f32": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),

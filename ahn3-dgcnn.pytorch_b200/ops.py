@@ -17,6 +17,7 @@ import torch
 from . import _lib
 
 COUT = 64
+TC_KNN_MIN_N = 512       # below this the key loop is too short for the threshold pass to pay off
 BN_EPS_DEFAULT = 1e-5
 
 
@@ -61,7 +62,7 @@ class KernelLog:
 LOG = KernelLog()
 
 # kernels launched by each entry point
-_LAUNCHES = {"dgcnn_knn_f32": 2, "dgcnn_knn_tc_f32": 5, "dgcnn_knn_small_f32": 3, "dgcnn_edgeconv_bwd_b": 2, "dgcnn_tc_gemm_f32": 3, "dgcnn_tc_gemm_bn_lrelu_segmax_f32": 5}
+_LAUNCHES = {"dgcnn_knn_f32": 2, "dgcnn_knn_tc_f32": 6, "dgcnn_knn_small_f32": 3, "dgcnn_edgeconv_bwd_b": 2, "dgcnn_tc_gemm_f32": 3, "dgcnn_tc_gemm_bn_lrelu_segmax_f32": 5}
 
 
 def _call(name: str, *args) -> None:
@@ -129,12 +130,14 @@ def unpack_rows(rows: torch.Tensor, B: int, Cn: int, N: int) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # kNN / graph feature
 # ------------------------------------------------------------------------------------------------
-def knn_rows(rows: torch.Tensor, B: int, Cn: int, N: int, k: int, method: str = "auto") -> torch.Tensor:
+def knn_rows(rows: torch.Tensor, B: int, Cn: int, N: int, k: int, method: str = "auto",
+             stats: Optional[list] = None, ordered: bool = True) -> torch.Tensor:
     """Neighbour table int32 [B*N, k] of point-major rows (model.py:25-40).
 
     method: "exact" = FP32-FMA tile kernel (any C <= 128, any k <= 128); "tc" = tcgen05 filter + exact re-score
-    (16 < C <= 64, k <= 48); "small" = thread-per-query kernel (C <= 16, k <= 48, N >= 512); all three give the
-    identical table; "auto" picks the fastest supported one."""
+    (C <= 128, k <= 48, N >= 128); "small" = thread-per-query kernel (C <= 16, k <= 48, N >= 512); all three give the
+    identical table; "auto" picks the fastest supported one.  `stats` (tc only): receives the 5 fallback counters.
+    ordered=False (tc only): the same neighbour sets in unspecified order — all the EdgeConv blocks need, and faster."""
     _need_cuda(rows, "knn")
     rows, ld = _rows_view(rows)
     lib = _lib.load()
@@ -142,14 +145,21 @@ def knn_rows(rows: torch.Tensor, B: int, Cn: int, N: int, k: int, method: str = 
     if method == "auto":
         method = "exact"
         if k <= N:
-            if N >= 1024 and lib.dgcnn_knn_tc_supported(Cn, N, k):       # small blocks: pass 1 does not pay off
+            if N >= TC_KNN_MIN_N and lib.dgcnn_knn_tc_supported(Cn, N, k):
                 method = "tc"
             elif lib.dgcnn_knn_small_supported(Cn, N, k):
                 method = "small"
     if method in ("tc", "small"):
         nbytes = getattr(lib, f"dgcnn_knn_{method}_workspace_bytes")(B, N)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=rows.device)
-        _call(f"dgcnn_knn_{method}_f32", _ptr(rows), ld, B, Cn, N, k, _ptr(idx), _ptr(ws), nbytes, _stream())
+        if method == "tc":
+            _call("dgcnn_knn_tc_f32", _ptr(rows), ld, B, Cn, N, k, 1 if ordered else 0, _ptr(idx), _ptr(ws), nbytes, _stream())
+        else:
+            _call("dgcnn_knn_small_f32", _ptr(rows), ld, B, Cn, N, k, _ptr(idx), _ptr(ws), nbytes, _stream())
+        if stats is not None and method == "tc":
+            out5 = (C.c_int * 5)()
+            _lib.check(lib.dgcnn_knn_tc_fallback_stats(_ptr(ws), B, N, Cn, out5, _stream()))
+            stats[:] = list(out5)
     else:
         norms = torch.empty(B * N, dtype=torch.float32, device=rows.device)
         _call("dgcnn_knn_f32", _ptr(rows), ld, B, Cn, N, k, _ptr(idx), _ptr(norms), _stream())

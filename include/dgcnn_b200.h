@@ -51,14 +51,21 @@ int dgcnn_unpack_rows_f32(const float* rows, int ld, int B, int C, int N, float*
 int dgcnn_knn_f32(const float* rows, int ld, int B, int C, int N, int k,
                   int32_t* idx, float* norms, void* stream);
 
-/* ---- tensor-core kNN (model.py:25-40 for the 64-channel feature-space graphs) ---------------------------------
- * Same result as dgcnn_knn_f32, bit for bit: tcgen05 Gram tiles on a 2-plane bf16 split act as a filter
- * (64 candidates per query + a rigorous error bound), survivors are re-scored with the exact FP32 expression,
- * rows that cannot be certified are redone by brute force.  Needs 16 < C <= 64, k <= 48, N >= 128.         */
+/* ---- tensor-core kNN (model.py:25-40; every graph of the model: C = 3..4 input graph, C = 64 feature graphs, C <= 128) ---
+ * Same result as dgcnn_knn_f32, bit for bit: tcgen05 Gram tiles on a 2-plane bf16 split of the block-centred features act
+ * as a filter (threshold from a sample of the keys, ~100 candidates per query, a rigorous error bound), the survivors are
+ * re-scored with the exact FP32 expression, rows that cannot be certified are redone by brute force.
+ * ordered != 0: rows best-first like the reference's topk (knn(), get_graph_feature()); ordered == 0: the same k
+ * neighbours in unspecified order (all the EdgeConv blocks need; only the few keys whose approximate score is within
+ * the error bound of the k-th are re-scored, 10x less gather traffic).
+ * Needs C <= 128, k <= 48, N >= 128.  workspace: dgcnn_knn_tc_workspace_bytes(B, N) bytes (about 2.1 KB per point).   */
 int dgcnn_knn_tc_supported(int C, int N, int k);
 size_t dgcnn_knn_tc_workspace_bytes(int B, int N);
-int dgcnn_knn_tc_f32(const float* rows, int ld, int B, int C, int N, int k, int32_t* idx,
+int dgcnn_knn_tc_f32(const float* rows, int ld, int B, int C, int N, int k, int ordered, int32_t* idx,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* Diagnostics of the last dgcnn_knn_tc_f32 call that used `workspace` (same B, N, C): out5 (HOST int[5]) = rows redone by
+ * brute force | sub-buffer overflows | too few candidates | too many near-ties | certificate failures.  Synchronises.  */
+int dgcnn_knn_tc_fallback_stats(const void* workspace, int B, int N, int C, int* out5, void* stream);
 
 /* ---- low-dimensional kNN (C <= 16: the xyz/agl input graph), thread per query, exact FP32 scores, threshold-collect-
  * select; same result as dgcnn_knn_f32 (rows that cannot be resolved in the fast path are redone by brute force).
