@@ -147,25 +147,44 @@ __global__ void knn_tc_prep_kernel(const float* __restrict__ rows, int ld, int N
   }
 }
 
-__global__ void knn_norms_max_kernel(const float* __restrict__ rows, int ld, int N, int C, float* __restrict__ norms,
-                                     unsigned int* __restrict__ maxnorm_bits) {
-  // same summation order as norms_kernel in knn.cu; per-block max via atomicMax on the (non-negative) float bits
-  const int b = blockIdx.y;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) knn_norms_max_kernel(const float* __restrict__ rows, int ld, int N, int C,
+                                                            float* __restrict__ norms, unsigned int* __restrict__ maxnorm_bits) {
+  // |x|^2 in torch.sum's order (sequential in blocks of 16 channels, block sums added sequentially: the same order as
+  // norms_kernel in knn.cu); per-block max via atomicMax on the (non-negative) float bits.
+  // 128 rows per CTA: 64-channel slabs are staged through shared memory with coalesced 16-byte loads (a thread reading
+  // its own 256-byte row touched 32 different lines per warp load), then thread = row sums its slab row by row.
+  __shared__ float tile[128 * 65];
+  const int b = blockIdx.y, n0 = blockIdx.x * 128, tid = threadIdx.x;
+  const int n = n0 + tid;
+  const int C4 = (C + 3) & ~3;
+  float lvl1 = 0.f, tail = 0.f;
+  for (int h = 0; h < C; h += 64) {
+    const int cw = min(64, C - h), cw4 = min(64, C4 - h);
+    __syncthreads();
+    for (int i = tid; i < 128 * 16; i += 128) {
+      const int r = i >> 4, c4 = i & 15;
+      if (n0 + r < N && 4 * c4 < cw4) {
+        const float4 v = *reinterpret_cast<const float4*>(rows + (static_cast<size_t>(b) * N + n0 + r) * ld + h + 4 * c4);
+        float* t = tile + r * 65 + 4 * c4;
+        t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+      }
+    }
+    __syncthreads();
+    if (n < N) {
+      const float* r = tile + tid * 65;
+      int c = 0;
+      for (; c + 16 <= cw; c += 16) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a = __fadd_rn(a, __fmul_rn(r[c + j], r[c + j]));
+        lvl1 = __fadd_rn(lvl1, a);
+      }
+      for (; c < cw; ++c) tail = __fadd_rn(tail, __fmul_rn(r[c], r[c]));
+    }
+  }
   float val = 0.f;
   if (n < N) {
-    const float* r = rows + (static_cast<size_t>(b) * N + n) * ld;
-    float lvl1 = 0.f;
-    int c = 0;
-    for (; c + 16 <= C; c += 16) {
-      float a = 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) a = __fadd_rn(a, __fmul_rn(r[c + j], r[c + j]));
-      lvl1 = __fadd_rn(lvl1, a);
-    }
-    float a = 0.f;
-    for (; c < C; ++c) a = __fadd_rn(a, __fmul_rn(r[c], r[c]));
-    val = __fadd_rn(a, lvl1);
+    val = __fadd_rn(tail, lvl1);
     norms[static_cast<size_t>(b) * N + n] = val;
   }
   unsigned int m = __float_as_uint(val);
@@ -177,29 +196,33 @@ __global__ void knn_norms_max_kernel(const float* __restrict__ rows, int ld, int
 // exact reference score of (query row xi, key row xj): FMA chain over channels, then the two rounded subtractions.
 // The key row is a gather from L2: all 16-byte loads of a 64-channel half are issued before the first use — with a rolled
 // loop every 4 channels paid a full L2 round trip.
+template <int NB = 16>
 __device__ __forceinline__ float exact_score(const float* __restrict__ xi, const float* __restrict__ xj, int C4,
                                              float norm_i, float norm_j) {
+  // NB float4 chunks (4 NB channels) of the key row are in flight at a time: 16 for the passes that re-score two keys per
+  // lane anyway, 8 where register pressure decides the occupancy
+  constexpr int W = 4 * NB;
   float d = 0.f;
-  for (int h = 0; h < C4; h += 64) {
-    const int cw = min(64, C4 - h);
+  for (int h = 0; h < C4; h += W) {
+    const int cw = min(W, C4 - h);
     const float* xjh = xj + h;
-    float4 b[16];
-    if (cw == 64 && (reinterpret_cast<uintptr_t>(xjh) & 31) == 0) {
+    float4 b[NB];
+    if (cw == W && (reinterpret_cast<uintptr_t>(xjh) & 31) == 0) {
       // one lane reads one whole key row: 32-byte loads fetch every sector once (16-byte loads request each sector twice,
       // and with many rows in flight the second request usually misses L1 again)
 #pragma unroll
-      for (int q = 0; q < 16; q += 2)
+      for (int q = 0; q < NB; q += 2)
         asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                      : "=f"(b[q].x), "=f"(b[q].y), "=f"(b[q].z), "=f"(b[q].w), "=f"(b[q + 1].x), "=f"(b[q + 1].y), "=f"(b[q + 1].z),
                        "=f"(b[q + 1].w)
                      : "l"(xjh + 4 * q));
     } else {
 #pragma unroll
-      for (int q = 0; q < 16; ++q)
+      for (int q = 0; q < NB; ++q)
         b[q] = 4 * q < cw ? *reinterpret_cast<const float4*>(xjh + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
+    for (int q = 0; q < NB; ++q) {
       if (4 * q < cw) {                 // the chain order is the reference's (channel by channel)
         const float4 a = *reinterpret_cast<const float4*>(xi + h + 4 * q);
         d = __fmaf_rn(a.x, b[q].x, d);
@@ -484,7 +507,7 @@ knn_tc_scan_kernel(const unsigned char* __restrict__ tiles, int N, int T, int nk
 // by construction (a_k > tau_i), the selected band keys are checked with their exact scores.
 // ---------------------------------------------------------------------------------------------
 template <bool ORDERED>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, ORDERED ? 2 : 4)
 knn_tc_select_kernel(const float* __restrict__ rows, int ld, const float* __restrict__ norms,
                      const unsigned int* __restrict__ maxnorm_bits, const float* __restrict__ normc,
                      const unsigned int* __restrict__ maxnormc_bits, int N, int C4, int k,
@@ -571,7 +594,14 @@ knn_tc_select_kernel(const float* __restrict__ rows, int ld, const float* __rest
   const float cut = lo - 2.0f * eps;
   const float* xi = rows + g * ld;
 
-  if (!ORDERED && !bad && cl <= k + 3) {
+  if (!ORDERED) {
+    if (bad || cl > k + 3) {          // overflow / too few candidates / a run of > 4 equal approximate scores at the cut
+      if (lane == 0) {
+        atomicAdd(fb_count + (overflow ? 1 : (ntot < k ? 2 : 3)), 1);
+        fb_rows[atomicAdd(fb_count, 1)] = static_cast<int>(g);
+      }
+      return;
+    }
     // ---- neighbour SET: a_k by peeling the cl - k smallest values above lo (groups of equal values at once) --------
     float ak = lo;
     int above = cl;                               // candidates strictly above ak
@@ -614,7 +644,7 @@ knn_tc_select_kernel(const float* __restrict__ rows, int ld, const float* __rest
       if (e < ns) {
         const int j = key_index(stg[e]);
         const size_t gj = static_cast<size_t>(b) * N + j;
-        ex[r] = make_key(exact_score(xi, rows + gj * ld, C4, norm_i, norms[gj]), j);
+        ex[r] = make_key(exact_score<8>(xi, rows + gj * ld, C4, norm_i, norms[gj]), j);
       }
     }
     __syncwarp();
@@ -1049,7 +1079,7 @@ extern "C" int dgcnn_knn_tc_f32(const float* rows, int ld, int B, int C, int N, 
   // maxnorm + fallback counters, then centred max norm + channel sums
   DG_CUDA(cudaMemsetAsync(ws + L.maxn, 0, L.fbrows - L.maxn, st));
   DG_CUDA(cudaMemsetAsync(ws + L.mu, 0, L.tau - L.mu, st));
-  knn_norms_max_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(rows, ld, N, C, reinterpret_cast<float*>(ws + L.norms),
+  knn_norms_max_kernel<<<dim3((N + 127) / 128, B), 128, 0, st>>>(rows, ld, N, C, reinterpret_cast<float*>(ws + L.norms),
                                                                  reinterpret_cast<unsigned int*>(ws + L.maxn));
   DG_CUDA(cudaGetLastError());
   if (C > 64) return launch_knn_tc<2, 64>(rows, ld, B, C4, N, k, ordered, idx, ws, L, st);
@@ -1109,7 +1139,7 @@ extern "C" int dgcnn_knn_small_f32(const float* rows, int ld, int B, int C, int 
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(ws + o_cand);
   DG_CUDA(cudaMemsetAsync(fb_count, 0, 4 + static_cast<size_t>(B) * 4, st));
   // norms in torch.sum's order (rows beyond C are zero padded, so the padded chain is exact as well)
-  knn_norms_max_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(rows, ld, N, C, norms, reinterpret_cast<unsigned int*>(fb_count + 1));
+  knn_norms_max_kernel<<<dim3((N + 127) / 128, B), 128, 0, st>>>(rows, ld, N, C, norms, reinterpret_cast<unsigned int*>(fb_count + 1));
   DG_CUDA(cudaGetLastError());
   // sample size: a thread's 8th best of its n_sample/4 keys has expected global rank 32 N / n_sample; aim at max(100, 3k)
   const int target = std::max(100, 3 * k);
