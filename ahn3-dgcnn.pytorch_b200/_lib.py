@@ -14,7 +14,8 @@ class EdgeConvArgs(C.Structure):
     """mirror of `dgcnn_edgeconv_args`"""
     _fields_ = [("rows", c_void_p), ("ld", c_int), ("idx", c_void_p),
                 ("B", c_int), ("C", c_int), ("N", c_int), ("k", c_int),
-                ("w_a", c_void_p), ("w_b", c_void_p), ("out", c_void_p), ("ld_out", c_int), ("v_scratch", c_void_p)]
+                ("w_a", c_void_p), ("w_b", c_void_p), ("out", c_void_p), ("ld_out", c_int), ("v_scratch", c_void_p),
+                ("impl", c_int)]
 
 
 _P = c_void_p
@@ -41,7 +42,6 @@ SIGNATURES = {
     "dgcnn_edgeconv_conv_b_train": (c_int, [_ARGS, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dgcnn_bn_finalize": (c_int, [_P, c_int, c_double, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P]),
     "dgcnn_edgeconv_select": (c_int, [c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
-    "dgcnn_set_edgeconv_tc": (c_int, [c_int]),
     "dgcnn_edgeconv_bwd_prep": (c_int, [c_int, _P, c_int, _P, _P, _P, _P, _P]),
     "dgcnn_bn_bwd_reduce": (c_int, [_P, c_int, c_double, _P, _P, _P, _P, _P, _P, _P]),
     "dgcnn_edgeconv_dw_partials_bytes": (c_size_t, []),
@@ -57,8 +57,10 @@ SIGNATURES = {
     "dgcnn_rows_bn_lrelu_bwd": (c_int, [_P, _P, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "dgcnn_rows_colsum_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dgcnn_rows_colsum_f32": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
-    "dgcnn_debug_tmem_a_lab": (c_int, [_P, _P, _P, c_int, _P]),
-    "dgcnn_debug_mn_lab": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "dgcnn_seg_loss_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "dgcnn_seg_loss_f32": (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, c_int, _P, _P, c_float, c_float, _P,
+                                   _P, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
+    "dgcnn_seg_predict_f32": (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float, c_int64, _P, _P, _P]),
     "dgcnn_tc_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "dgcnn_tc_gemm_f32": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int, c_int, c_int, c_int, c_int,
                                   _P, c_size_t, _P]),

@@ -589,6 +589,8 @@ static int fill_common(const dgcnn_edgeconv_args* a, EcK& p, const char* who) {
   p.w_a = a->w_a; p.w_b = a->w_b; p.two = a->w_b != nullptr;
   p.out = a->out; p.ld_out = a->ld_out;
   p.v_center = a->v_scratch;
+  DG_REQUIRE(a->impl >= 0 && a->impl <= 2, DGCNN_E_INVALID, "%s: impl must be 0 (default), 1 (FP32 FMA) or 2 (serial tcgen05)", who);
+  p.tc = a->impl == 0 ? 2 : (a->impl == 1 ? 0 : 1);
   return DGCNN_OK;
 }
 
@@ -641,7 +643,7 @@ extern "C" int dgcnn_edgeconv_fwd_eval(const dgcnn_edgeconv_args* a, const float
   if ((rc = check_rows(a, "edgeconv_fwd_eval"))) return rc;
   DG_REQUIRE(a->out && aff_a && (!p.two || aff_b), DGCNN_E_INVALID, "edgeconv_fwd_eval: null pointer");
   p.aff_a = aff_a; p.aff_b = aff_b;
-  if (p.C == 64 && p.v_center && edgeconv_tc_enabled())
+  if (p.C == 64 && p.v_center && p.tc)
     return launch_ec_tc_fwd(p, MODE_EVAL, persistent_grid(p.num_tiles), static_cast<cudaStream_t>(stream));
   return dispatch_cp<MODE_EVAL>(p, static_cast<cudaStream_t>(stream));
 }
@@ -657,7 +659,7 @@ extern "C" int dgcnn_edgeconv_conv_a_train(const dgcnn_edgeconv_args* a, float* 
              "edgeconv_conv_a_train: single-conv block needs the extrema outputs");
   p.y_a_out = y_a; p.partials = partials;
   p.ymax = ymax; p.ymin = ymin; p.amax = amax; p.amin = amin;
-  if (p.C == 64 && p.v_center && edgeconv_tc_enabled())
+  if (p.C == 64 && p.v_center && p.tc)
     return launch_ec_tc_fwd(p, MODE_TRAIN_A, persistent_grid(p.num_tiles), static_cast<cudaStream_t>(stream));
   return dispatch_cp<MODE_TRAIN_A>(p, static_cast<cudaStream_t>(stream));
 }
@@ -672,7 +674,7 @@ extern "C" int dgcnn_edgeconv_conv_b_train(const dgcnn_edgeconv_args* a, const f
              "edgeconv_conv_b_train: null pointer");
   p.y_a_in = y_a; p.aff_a = aff_a; p.partials = partials;
   p.ymax = ymax; p.ymin = ymin; p.amax = amax; p.amin = amin;
-  if (edgeconv_tc_enabled())
+  if (p.tc)
     return launch_ec_tc_fwd(p, MODE_TRAIN_B, persistent_grid(p.num_tiles), static_cast<cudaStream_t>(stream));
   return launch_fwd<64, MODE_TRAIN_B>(p, static_cast<cudaStream_t>(stream));
 }
@@ -731,7 +733,7 @@ extern "C" int dgcnn_edgeconv_bwd_b(const dgcnn_edgeconv_args* a, const float* y
              "edgeconv_bwd_b: null pointer");
   p.y_a_in = y_a; p.aff_a = aff_a; p.partials = partials;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (edgeconv_tc_enabled()) {
+  if (p.tc) {
     // two CTAs per SM; every CTA gets at least one tile so that its dW partial is defined
     const int grid = std::max(1, std::min(p.num_tiles, 2 * std::max(1, num_sms())));
     return launch_ec_tc_bwd_b(p, g, arg, coef_b, dz_a, dw_partials, dw_b, grid, st);

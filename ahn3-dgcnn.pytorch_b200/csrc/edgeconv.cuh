@@ -18,6 +18,7 @@ struct EcK {
   const float* aff_a; const float* aff_b;     // float[192]: mean | scale | beta
   float* y_a_out; const float* y_a_in;
   float* v_center;                            // [M,64] scratch: hoisted centre term Wa2 x_i (tensor-core kernels)
+  int tc;                                     // 0 = FFMA kernels, 1 = serial tensor-core kernels, 2 = 1 + pipelined conv_b (default)
   double* partials;
   float* ymax; float* ymin; uint8_t* amax; uint8_t* amin;
 };
@@ -30,8 +31,6 @@ __device__ __forceinline__ float bn_apply(float y, float mean, float scale, floa
 int launch_ec_tc_fwd(const EcK& p, int mode, int grid, cudaStream_t st);
 int launch_ec_tc_bwd_b(const EcK& p, const float* g, const uint8_t* arg, const float* coef_b, float* dz_a,
                        float* dw_partials, float* dw_b, int grid, cudaStream_t st);
-bool edgeconv_tc_enabled();
-int edgeconv_tc_mode();       // 0 = FFMA kernels, 1 = serial tensor-core kernels, 2 = 1 + warp-specialised pipelined conv_b (default)
 // pipelined conv_b training pass (edgeconv_pipe.cu); one CTA per SM
 int launch_ec_pipe_conv_b(const EcK& p, int sms, cudaStream_t st);
 

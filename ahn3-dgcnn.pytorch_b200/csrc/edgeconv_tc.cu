@@ -16,10 +16,6 @@
 
 namespace dg {
 
-static int g_edgeconv_tc = 2;
-bool edgeconv_tc_enabled() { return g_edgeconv_tc != 0; }
-int edgeconv_tc_mode() { return g_edgeconv_tc; }
-
 struct EcTcSmem {
   static constexpr uint32_t a_off = 0;                       // 3 A planes, later the FP32 Y tile
   static constexpr uint32_t w_off = 3 * kPlA;                // 3 weight planes (conv_a: Wa1, conv_b: W_b)
@@ -657,7 +653,7 @@ int launch_ec_tc_fwd(const EcK& p, int mode, int grid, cudaStream_t st) {
   }
   // conv_b streams a contiguous tile: the warp-specialised pipeline wins there.  conv_a is bound by the L2 gather and
   // shared-memory bandwidth either way and runs faster as two serial CTAs per SM.
-  if (mode == MODE_TRAIN_B && g_edgeconv_tc >= 2) return launch_ec_pipe_conv_b(p, (grid + 1) / 2, st);
+  if (mode == MODE_TRAIN_B && p.tc >= 2) return launch_ec_pipe_conv_b(p, (grid + 1) / 2, st);
   if (mode == MODE_TRAIN_A) {
     DG_CUDA(cudaFuncSetAttribute(ec_tc_fwd_kernel<MODE_TRAIN_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcTcSmem::bytes)));
     ec_tc_fwd_kernel<MODE_TRAIN_A><<<grid, kThreads, EcTcSmem::bytes, st>>>(p);
@@ -673,9 +669,3 @@ int launch_ec_tc_fwd(const EcK& p, int mode, int grid, cudaStream_t st) {
 }
 
 }  // namespace dg
-
-extern "C" int dgcnn_set_edgeconv_tc(int enabled) {
-  const int old = dg::g_edgeconv_tc;
-  dg::g_edgeconv_tc = enabled;
-  return old;
-}

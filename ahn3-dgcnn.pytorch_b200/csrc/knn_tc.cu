@@ -36,7 +36,6 @@ constexpr float kC1 = 2.0e-5f * 2.0f;     // 2 * (split + accumulation + chain e
 constexpr float kC1Wide = 3.0e-5f * 2.0f; // 64 < C <= 128
 constexpr float kC2 = 6.0e-7f;            // final roundings (incl. fl(tau - score)), relative to (|x_i|+|x_j|)^2
 
-constexpr int kAccs = 4;                 // TMEM accumulators
 constexpr int kScanWarps = 16;
 constexpr int kTcThreads = (kScanWarps + 1) * 32;   // + 1 producer / MMA-issue warp
 constexpr int kSubCands = 64;            // candidate slots per (row, column quarter)
@@ -252,6 +251,12 @@ template <int KA, int KEYS>
 struct KnnScan {
   using Tile = KnnTile<KA, KEYS>;
   static constexpr int kStages = KA == 1 ? 4 : 3;
+  // TMEM accumulators = shared-memory stages.  The producer tests `sfree` of a slot by phase PARITY, which is only
+  // unambiguous while the barrier is at most one phase behind: with A accumulators the MMA issue (and so the prefetch
+  // test) runs up to A tiles ahead of the slowest scan warp, and a slot that is two releases behind reads as "free"
+  // (seen on B200 with 4 accumulators over 3 stages: a tile was overwritten under its MMA).  A == stages, together with
+  // the scan warps arriving on `sfree` BEFORE `accfree`, bounds the lag at one phase.
+  static constexpr int kAccs = kStages;
   static constexpr int CH = KEYS / 64;                                      // 16-column chunks per thread and tile
   static constexpr int QC = KEYS / 4;                                       // columns per column quarter
   static constexpr uint32_t stage_bytes = (Tile::bytes + 1023u) & ~1023u;
@@ -264,7 +269,7 @@ struct KnnScan {
   static constexpr uint32_t tau_off = scr_off + scr_bytes;
   static constexpr uint32_t bar_off = tau_off + 128 * 4;
   static constexpr uint32_t bytes = bar_off + 256;
-  static constexpr uint32_t tmem_cols = kAccs * KEYS;
+  static constexpr uint32_t tmem_cols = kAccs * KEYS <= 256 ? 256 : 512;        // power of two >= kAccs * KEYS
   static_assert(128 * 68 * 4 <= scr_bytes, "group maxima must fit in the score park");
 };
 
@@ -274,7 +279,7 @@ knn_tc_scan_kernel(const unsigned char* __restrict__ tiles, int N, int T, int nk
                    unsigned long long* __restrict__ cand, int* __restrict__ cnt4, float* __restrict__ tau_out) {
   using S = KnnScan<KA, KEYS>;
   using Tile = KnnTile<KA, KEYS>;
-  constexpr int kStages = S::kStages, CH = S::CH, QC = S::QC;
+  constexpr int kStages = S::kStages, kAccs = S::kAccs, CH = S::CH, QC = S::QC;
   // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (checked below)
   extern __shared__ __align__(1024) unsigned char sm[];
   unsigned char* As = sm;
@@ -411,8 +416,8 @@ knn_tc_scan_kernel(const unsigned char* __restrict__ tiles, int N, int T, int nk
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) {
+        tc::mbar_arrive(sfree + s);            // slot first: an observed `accfree` phase implies the slot's release
         tc::mbar_arrive(accfree + a);
-        tc::mbar_arrive(sfree + s);
       }
     };
 

@@ -19,11 +19,35 @@ Deliberate compatibility extensions:
 """
 from __future__ import annotations
 
+import os
+import sys
 from typing import List, Optional, Sequence
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+_PKG = "ahn3_dgcnn_pytorch_b200"
+if not __package__:
+    # Imported the way the reference's drivers import it: this directory is on sys.path and they say
+    # `from model import DGCNN` (train.py:12, test.py:11, visualisation.py).  Load the real package (its directory name is
+    # not an identifier, so it is registered under _PKG) and make `model` an alias of its `model` submodule: one set of
+    # classes, one loaded library.  The rest of this file then runs as a discarded duplicate with relative imports bound
+    # to the package.
+    if _PKG not in sys.modules:
+        import importlib.util as _ilu
+        _dir = os.path.dirname(os.path.abspath(__file__))
+        _spec = _ilu.spec_from_file_location(_PKG, os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+        _mod = _ilu.module_from_spec(_spec)
+        sys.modules[_PKG] = _mod
+        try:
+            _spec.loader.exec_module(_mod)
+        except BaseException:
+            sys.modules.pop(_PKG, None)
+            raise
+    sys.modules[__name__] = sys.modules[_PKG + ".model"]
+    __package__ = _PKG
+    __spec__ = sys.modules[_PKG + ".model"].__spec__
 
 from . import ops
 
@@ -46,6 +70,15 @@ def get_graph_feature(x: torch.Tensor, k: int = 20, use_cuda: bool = True, **_co
     rows = ops.pack_rows(x)
     idx = ops.knn_rows(rows, B, Cn, N, k)
     return ops.graph_feature_rows(rows, idx, B, Cn, N, k).permute(0, 3, 1, 2)
+
+
+def _bn_state(bn: nn.Module) -> "ops.BNState":
+    """Running statistics + (eps, momentum) of a BatchNorm module; momentum=None is nn.BatchNorm's cumulative moving
+    average, i.e. an update factor of 1 / (batches seen including this one)."""
+    mom = bn.momentum
+    if mom is None:
+        mom = 1.0 / float(int(bn.num_batches_tracked) + 1) if bn.track_running_stats else 0.0
+    return ops.BNState(bn.running_mean, bn.running_var, bn.eps, mom)
 
 
 def _conv_bn_act(conv: nn.Module, bn: nn.Module) -> nn.Sequential:
@@ -94,8 +127,8 @@ class DGCNN(nn.Module):
         conv_b = bn_b = None
         if second is not None:
             conv_b, bn_b = getattr(self, f"conv{second}")[0], getattr(self, f"bn{second}")
-        st_a = ops.BNState(bn_a.running_mean, bn_a.running_var, bn_a.eps, bn_a.momentum)
-        st_b = None if bn_b is None else ops.BNState(bn_b.running_mean, bn_b.running_var, bn_b.eps, bn_b.momentum)
+        st_a = _bn_state(bn_a)
+        st_b = None if bn_b is None else _bn_state(bn_b)
         if self.training:
             out = ops.EdgeConvTrain.apply(rows, idx, (B, Cn, N, self.k), conv_a.weight, bn_a.weight, bn_a.bias,
                                           None if conv_b is None else conv_b.weight,
@@ -161,11 +194,13 @@ class DGCNN(nn.Module):
             return self._bcn(self._dense(feat, 6), B, N)                   # [M,emb] only materialised on request
         # conv6 + bn6 + LeakyReLU + max over the points fused: the [B,emb,N] activation is never formed
         bn6 = self.bn6
-        g = ops.GlobalFeature.apply(feat, self.conv6[0].weight.squeeze(-1), bn6.weight, bn6.bias,
-                                    ops.BNState(bn6.running_mean, bn6.running_var, bn6.eps, bn6.momentum),
-                                    self.training, B, N)                   # [B,emb] global feature
-        if self.training:
-            bn6.num_batches_tracked.add_(1)
+        if N >= 32:
+            g = ops.GlobalFeature.apply(feat, self.conv6[0].weight.squeeze(-1), bn6.weight, bn6.bias, _bn_state(bn6),
+                                        self.training, B, N)               # [B,emb] global feature
+            if self.training:
+                bn6.num_batches_tracked.add_(1)
+        else:                            # blocks shorter than one epilogue row group: materialise [M,emb] (tiny)
+            g = self._dense(feat, 6).view(B, N, -1).max(dim=1)[0]
         if depth == 6:
             return g.unsqueeze(-1)
         if depth == 7:

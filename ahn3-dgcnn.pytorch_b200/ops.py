@@ -8,7 +8,9 @@ int32 [B*N, k] with block-local indices.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -17,7 +19,11 @@ import torch
 from . import _lib
 
 COUT = 64
-TC_KNN_MIN_N = 512       # below this the key loop is too short for the threshold pass to pay off
+TC_KNN_MIN_N = 256       # below this every key is a candidate anyway and the exact tile kernel is as fast
+EDGECONV_IMPL = 0        # dgcnn_edgeconv_args.impl: 0 = default (pipelined tcgen05), 1 = FP32 FMA, 2 = serial tcgen05 (A/B checks)
+# bf16 planes per operand in the GRADIENT GEMMs (forward GEMMs always use 3 = FP32-accurate).  2 = 3 MMAs per product,
+# relative error ~2^-17; 3 = 6 MMAs, ~2^-24 like the forward.  DGCNN_GRAD_NSPLIT overrides; bench.py reports both.
+GRAD_NSPLIT = int(os.environ.get("DGCNN_GRAD_NSPLIT", "2"))
 BN_EPS_DEFAULT = 1e-5
 
 
@@ -25,8 +31,8 @@ def _ptr(t: Optional[torch.Tensor]):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _dev_index(dev: torch.device) -> int:
+    return torch.cuda.current_device() if dev.index is None else dev.index
 
 
 def _need_cuda(t: torch.Tensor, what: str) -> None:
@@ -65,18 +71,26 @@ LOG = KernelLog()
 _LAUNCHES = {"dgcnn_knn_f32": 2, "dgcnn_knn_tc_f32": 6, "dgcnn_knn_small_f32": 3, "dgcnn_edgeconv_bwd_b": 2, "dgcnn_tc_gemm_f32": 3, "dgcnn_tc_gemm_bn_lrelu_segmax_f32": 5}
 
 
-def _call(name: str, *args) -> None:
+def _call(name: str, dev: torch.device, *args) -> None:
+    """Enqueue one C-ABI entry point on `dev`'s current stream (appended as the last argument).
+
+    The library launches on the CURRENT device, so a tensor living on another device than the caller's current one
+    (`model.to('cuda:1')` without `set_device`) needs the guard; PyTorch's own ops behave the same way."""
     fn = getattr(_lib.load(), name)
     LOG.launches += _LAUNCHES.get(name, 1)
-    if LOG.timing:
-        a = torch.cuda.Event(enable_timing=True)
-        b = torch.cuda.Event(enable_timing=True)
-        a.record()
-        rc = fn(*args)
-        b.record()
-        LOG.events.append((name, a, b))
-    else:
-        rc = fn(*args)
+    index = _dev_index(dev)
+    guard = torch.cuda.device(index) if index != torch.cuda.current_device() else contextlib.nullcontext()
+    with guard:
+        st = C.c_void_p(torch.cuda.current_stream(index).cuda_stream)
+        if LOG.timing:
+            a = torch.cuda.Event(enable_timing=True)
+            b = torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = fn(*args, st)
+            b.record()
+            LOG.events.append((name, a, b))
+        else:
+            rc = fn(*args, st)
     _lib.check(rc)
 
 
@@ -85,7 +99,8 @@ _scratch = {}
 
 
 def _partials(dev: torch.device) -> Tuple[torch.Tensor, torch.Tensor]:
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    # one buffer per (device, stream): kernels of different streams never share scratch
+    key = (_dev_index(dev), torch.cuda.current_stream(_dev_index(dev)).cuda_stream)
     if key not in _scratch:
         lib = _lib.load()
         _scratch[key] = (
@@ -108,22 +123,41 @@ def _rows_view(rows: torch.Tensor) -> Tuple[torch.Tensor, int]:
 # ------------------------------------------------------------------------------------------------
 # layout
 # ------------------------------------------------------------------------------------------------
-def pack_rows(x: torch.Tensor) -> torch.Tensor:
-    """x [B,C,N] (any strides) -> rows [B*N, round4(C)], padding columns zero (model.py:73)."""
+def _pack_rows(x: torch.Tensor) -> torch.Tensor:
     _need_cuda(x, "pack_rows")
     B, Cn, N = x.shape
     c4 = (Cn + 3) // 4 * 4
     rows = torch.empty(B * N, c4, dtype=torch.float32, device=x.device)
-    _call("dgcnn_pack_rows_f32", _ptr(x), x.stride(0), x.stride(1), x.stride(2), B, Cn, N,
-                                               _ptr(rows), c4, _stream())
+    _call("dgcnn_pack_rows_f32", x.device, _ptr(x), x.stride(0), x.stride(1), x.stride(2), B, Cn, N, _ptr(rows), c4)
     return rows
+
+
+class PackRows(torch.autograd.Function):
+    """pack_rows with its adjoint, so that gradients reach the input point cloud like in the reference."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = tuple(x.shape)
+        return _pack_rows(x)
+
+    @staticmethod
+    def backward(ctx, drows):
+        B, Cn, N = ctx.shape
+        return unpack_rows(drows, B, Cn, N)
+
+
+def pack_rows(x: torch.Tensor) -> torch.Tensor:
+    """x [B,C,N] (any strides) -> rows [B*N, round4(C)], padding columns zero (model.py:73)."""
+    if x.requires_grad and torch.is_grad_enabled():
+        return PackRows.apply(x)
+    return _pack_rows(x)
 
 
 def unpack_rows(rows: torch.Tensor, B: int, Cn: int, N: int) -> torch.Tensor:
     """rows [B*N, >=C] -> contiguous [B,C,N]."""
     rows, ld = _rows_view(rows)
     y = torch.empty(B, Cn, N, dtype=torch.float32, device=rows.device)
-    _call("dgcnn_unpack_rows_f32", _ptr(rows), ld, B, Cn, N, _ptr(y), _stream())
+    _call("dgcnn_unpack_rows_f32", rows.device, _ptr(rows), ld, B, Cn, N, _ptr(y))
     return y
 
 
@@ -153,16 +187,17 @@ def knn_rows(rows: torch.Tensor, B: int, Cn: int, N: int, k: int, method: str = 
         nbytes = getattr(lib, f"dgcnn_knn_{method}_workspace_bytes")(B, N)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=rows.device)
         if method == "tc":
-            _call("dgcnn_knn_tc_f32", _ptr(rows), ld, B, Cn, N, k, 1 if ordered else 0, _ptr(idx), _ptr(ws), nbytes, _stream())
+            _call("dgcnn_knn_tc_f32", rows.device, _ptr(rows), ld, B, Cn, N, k, 1 if ordered else 0, _ptr(idx), _ptr(ws), nbytes)
         else:
-            _call("dgcnn_knn_small_f32", _ptr(rows), ld, B, Cn, N, k, _ptr(idx), _ptr(ws), nbytes, _stream())
+            _call("dgcnn_knn_small_f32", rows.device, _ptr(rows), ld, B, Cn, N, k, _ptr(idx), _ptr(ws), nbytes)
         if stats is not None and method == "tc":
             out5 = (C.c_int * 5)()
-            _lib.check(lib.dgcnn_knn_tc_fallback_stats(_ptr(ws), B, N, Cn, out5, _stream()))
+            _lib.check(lib.dgcnn_knn_tc_fallback_stats(_ptr(ws), B, N, Cn, out5,
+                                                       C.c_void_p(torch.cuda.current_stream(_dev_index(rows.device)).cuda_stream)))
             stats[:] = list(out5)
     else:
         norms = torch.empty(B * N, dtype=torch.float32, device=rows.device)
-        _call("dgcnn_knn_f32", _ptr(rows), ld, B, Cn, N, k, _ptr(idx), _ptr(norms), _stream())
+        _call("dgcnn_knn_f32", rows.device, _ptr(rows), ld, B, Cn, N, k, _ptr(idx), _ptr(norms))
     return idx
 
 
@@ -170,7 +205,7 @@ def graph_feature_rows(rows: torch.Tensor, idx: torch.Tensor, B: int, Cn: int, N
     """[B,N,k,2C] edge-feature buffer (model.py:74-81); API-parity path, not used by DGCNN.forward."""
     rows, ld = _rows_view(rows)
     out = torch.empty(B, N, k, 2 * Cn, dtype=torch.float32, device=rows.device)
-    _call("dgcnn_graph_feature_f32", _ptr(rows), ld, _ptr(idx), B, Cn, N, k, _ptr(out), _stream())
+    _call("dgcnn_graph_feature_f32", rows.device, _ptr(rows), ld, _ptr(idx), B, Cn, N, k, _ptr(out))
     return out
 
 
@@ -180,20 +215,25 @@ def graph_feature_rows(rows: torch.Tensor, idx: torch.Tensor, B: int, Cn: int, N
 _gemm_ws = {}
 
 
+def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    """Grow-only GEMM workspace per (device, stream)."""
+    key = (_dev_index(dev), torch.cuda.current_stream(_dev_index(dev)).cuda_stream)
+    ws = _gemm_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.25), dtype=torch.uint8, device=dev)
+        _gemm_ws[key] = ws
+    return ws
+
+
 def tc_gemm(a: torch.Tensor, b: torch.Tensor, nsplit: int = 3) -> torch.Tensor:
     """D[M,N] = a[M,K] @ b[N,K]^T in FP32 via dgcnn_tc_gemm_f32; a and b may be arbitrary 2-D strided views."""
     M, K = a.shape
     N = b.shape[0]
     lib = _lib.load()
-    nbytes = lib.dgcnn_tc_gemm_workspace_bytes(M, N, K, nsplit)
-    key = (a.device.index, nbytes)
-    ws = _gemm_ws.get(a.device.index)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(int(nbytes * 1.25), dtype=torch.uint8, device=a.device)
-        _gemm_ws[a.device.index] = ws
+    ws = _workspace(a.device, lib.dgcnn_tc_gemm_workspace_bytes(M, N, K, nsplit))
     d = torch.empty(M, N, dtype=torch.float32, device=a.device)
-    _call("dgcnn_tc_gemm_f32", _ptr(a), a.stride(0), a.stride(1), _ptr(b), b.stride(0), b.stride(1), _ptr(d), N, M, N, K,
-          nsplit, _ptr(ws), ws.numel(), _stream())
+    _call("dgcnn_tc_gemm_f32", a.device, _ptr(a), a.stride(0), a.stride(1), _ptr(b), b.stride(0), b.stride(1), _ptr(d), N, M, N, K,
+          nsplit, _ptr(ws), ws.numel())
     return d
 
 
@@ -209,11 +249,11 @@ class TcLinear(torch.autograd.Function):
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         dx = dw = None
-        # gradient GEMMs use the 2-plane split (relative error 2^-17: two orders below the gradient noise floor)
+        # gradient GEMMs: GRAD_NSPLIT planes (2: relative error 2^-17, two orders below the gradient noise floor; 3: FP32-accurate)
         if ctx.needs_input_grad[0]:
-            dx = tc_gemm(dy, w.t(), nsplit=2)       # [M,K] = dy[M,N] @ w[N,K]
+            dx = tc_gemm(dy, w.t(), nsplit=GRAD_NSPLIT)       # [M,K] = dy[M,N] @ w[N,K]
         if ctx.needs_input_grad[1]:
-            dw = tc_gemm(dy.t(), x.t(), nsplit=2)   # [N,K] = dy^T[N,M] @ x[M,K]   (split-K over the points)
+            dw = tc_gemm(dy.t(), x.t(), nsplit=GRAD_NSPLIT)   # [N,K] = dy^T[N,M] @ x[M,K]   (split-K over the points)
         return dx, dw
 
 
@@ -233,20 +273,16 @@ class GlobalFeature(torch.autograd.Function):
         E = w.shape[0]
         dev = feat.device
         f32 = dict(dtype=torch.float32, device=dev)
-        nbytes = lib.dgcnn_tc_gemm_colstats_workspace_bytes(M, E, K, B)
-        ws = _gemm_ws.get(dev.index)
-        if ws is None or ws.numel() < nbytes:
-            ws = torch.empty(int(nbytes * 1.25), dtype=torch.uint8, device=dev)
-            _gemm_ws[dev.index] = ws
+        ws = _workspace(dev, lib.dgcnn_tc_gemm_colstats_workspace_bytes(M, E, K, B))
         g = torch.empty(B, E, **f32)
         ysel = torch.empty(B, E, **f32)
         nstar = torch.empty(B, E, dtype=torch.int32, device=dev)
         stat = torch.empty(2, E, **f32)
         fd, wd = feat.detach(), w.detach()
-        _call("dgcnn_tc_gemm_bn_lrelu_segmax_f32", _ptr(fd), fd.stride(0), fd.stride(1), _ptr(wd), wd.stride(0), wd.stride(1),
+        _call("dgcnn_tc_gemm_bn_lrelu_segmax_f32", dev, _ptr(fd), fd.stride(0), fd.stride(1), _ptr(wd), wd.stride(0), wd.stride(1),
               M, E, K, N, _ptr(gamma.detach()), _ptr(beta.detach()), bn.eps, bn.momentum, 1 if training else 0,
               _ptr(bn.running_mean), _ptr(bn.running_var), _ptr(stat[0]), _ptr(stat[1]), _ptr(g), _ptr(ysel), _ptr(nstar),
-              _ptr(ws), ws.numel(), _stream())
+              _ptr(ws), ws.numel())
         ctx.save_for_backward(fd, wd, gamma.detach(), beta.detach(), stat, ysel, nstar)
         ctx.training = training
         return g
@@ -269,12 +305,12 @@ class GlobalFeature(torch.autograd.Function):
         idx = nstar.reshape(-1).long()
         # dfeat
         gram_w = (w * kappa[:, None]).t() @ w                          # [K,K] = W^T diag(kappa) W (symmetric)
-        dfeat = tc_gemm(feat, gram_w, nsplit=2)
+        dfeat = tc_gemm(feat, gram_w, nsplit=GRAD_NSPLIT)
         dfeat.neg_().sub_(bprime @ w)
         dfeat.index_add_(0, idx, (a * gdz).reshape(-1, 1) * w.repeat(B, 1))
         # dW
         t1 = (gdz.unsqueeze(-1) * feat[idx].view(B, E, -1)).sum(0)     # [E,K] = dz^T feat
-        f2 = tc_gemm(feat.t(), feat.t(), nsplit=2)                     # [K,K] = feat^T feat (split-K over the points)
+        f2 = tc_gemm(feat.t(), feat.t(), nsplit=GRAD_NSPLIT)                     # [K,K] = feat^T feat (split-K over the points)
         dw = a[:, None] * t1 - bprime[:, None] * rows_colsum(feat, M) - kappa[:, None] * (w @ f2)
         return dfeat, dw, s2, s1, None, None, None, None
 
@@ -288,7 +324,7 @@ def rows_colsum(x: torch.Tensor, N: int) -> torch.Tensor:
     x = x.contiguous()
     out = torch.empty(M // N, Cn, dtype=torch.float32, device=x.device)
     ws = torch.empty(lib.dgcnn_rows_colsum_workspace_bytes(M, Cn, N), dtype=torch.uint8, device=x.device)
-    _call("dgcnn_rows_colsum_f32", _ptr(x), M, Cn, N, _ptr(out), _ptr(ws), ws.numel(), _stream())
+    _call("dgcnn_rows_colsum_f32", x.device, _ptr(x), M, Cn, N, _ptr(out), _ptr(ws), ws.numel())
     return out
 
 
@@ -307,9 +343,9 @@ class RowsBnLrelu(torch.autograd.Function):
         stat = torch.empty(2, Cn, dtype=torch.float32, device=dev)
         aff = torch.empty(3 * Cn, dtype=torch.float32, device=dev)
         h = torch.empty_like(y)
-        _call("dgcnn_rows_bn_lrelu_fwd", _ptr(y.detach()), M, Cn, _ptr(bias_c), N, _ptr(gamma.detach()), _ptr(beta.detach()),
+        _call("dgcnn_rows_bn_lrelu_fwd", dev, _ptr(y.detach()), M, Cn, _ptr(bias_c), N, _ptr(gamma.detach()), _ptr(beta.detach()),
               bn.eps, bn.momentum, 1 if training else 0, _ptr(bn.running_mean), _ptr(bn.running_var), _ptr(stat[0]),
-              _ptr(stat[1]), _ptr(aff), _ptr(h), _ptr(ws), ws.numel(), _stream())
+              _ptr(stat[1]), _ptr(aff), _ptr(h), _ptr(ws), ws.numel())
         ctx.save_for_backward(y.detach(), bias_c, gamma.detach(), stat, aff)
         ctx.training, ctx.N, ctx.ws = training, N, ws
         return h
@@ -324,15 +360,18 @@ class RowsBnLrelu(torch.autograd.Function):
         dy = torch.empty_like(y)
         dgamma = torch.empty(Cn, dtype=torch.float32, device=y.device)
         dbeta = torch.empty_like(dgamma)
-        _call("dgcnn_rows_bn_lrelu_bwd", _ptr(dh), _ptr(y), M, Cn, _ptr(bias), ctx.N, _ptr(gamma), _ptr(stat[1]), _ptr(aff),
-              _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(ctx.ws), ctx.ws.numel(), _stream())
+        _call("dgcnn_rows_bn_lrelu_bwd", y.device, _ptr(dh), _ptr(y), M, Cn, _ptr(bias), ctx.N, _ptr(gamma), _ptr(stat[1]), _ptr(aff),
+              _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(ctx.ws), ctx.ws.numel())
         dbias = None if bias is None else rows_colsum(dy, ctx.N)
         return dy, dbias, dgamma, dbeta, None, None, None
 
 
 def bn_lrelu_rows(y: torch.Tensor, bn_mod, training: bool, N: int, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """LeakyReLU(bn_mod(y + bias[block])) for y[M,C]; `bn_mod` is the reference's nn.BatchNorm1d (state and parameters)."""
-    st = BNState(bn_mod.running_mean, bn_mod.running_var, bn_mod.eps, bn_mod.momentum)
+    mom = bn_mod.momentum
+    if mom is None:                      # cumulative moving average (nn.BatchNorm with momentum=None)
+        mom = 1.0 / float(int(bn_mod.num_batches_tracked) + 1)
+    st = BNState(bn_mod.running_mean, bn_mod.running_var, bn_mod.eps, mom)
     h = RowsBnLrelu.apply(y, bias, bn_mod.weight, bn_mod.bias, st, training, N)
     if training:
         bn_mod.num_batches_tracked.add_(1)
@@ -360,10 +399,10 @@ class BNState:
     momentum: float = 0.1
 
 
-def _args(rows, ld, idx, B, Cn, N, k, w_a, w_b, out, ld_out, v_scratch=None):
+def _args(rows, ld, idx, B, Cn, N, k, w_a, w_b, out, ld_out, v_scratch=None, impl=None):
     return _lib.EdgeConvArgs(rows.data_ptr(), ld, idx.data_ptr(), B, Cn, N, k, w_a.data_ptr(),
                              0 if w_b is None else w_b.data_ptr(), 0 if out is None else out.data_ptr(), ld_out,
-                             0 if v_scratch is None else v_scratch.data_ptr())
+                             0 if v_scratch is None else v_scratch.data_ptr(), EDGECONV_IMPL if impl is None else impl)
 
 
 def _v_scratch(B: int, Cn: int, N: int, dev) -> Optional[torch.Tensor]:
@@ -387,7 +426,7 @@ def edgeconv_eval(rows: torch.Tensor, idx: torch.Tensor, B: int, Cn: int, N: int
     wb = None if w_b is None else w_b.detach().reshape(COUT, COUT).contiguous()
     vs = _v_scratch(B, Cn, N, rows.device)
     a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, out, COUT, vs)
-    _call("dgcnn_edgeconv_fwd_eval", C.byref(a), _ptr(aff_a), _ptr(aff_b), _stream())
+    _call("dgcnn_edgeconv_fwd_eval", rows.device, C.byref(a), _ptr(aff_a), _ptr(aff_b))
     return out
 
 
@@ -408,7 +447,6 @@ class EdgeConvTrain(torch.autograd.Function):
         wa = w_a.detach().reshape(COUT, 2 * Cn).contiguous()
         wb = w_b.detach().reshape(COUT, COUT).contiguous() if two else None
         partials, _ = _partials(dev)
-        st = _stream()
 
         f32 = dict(dtype=torch.float32, device=dev)
         y_a = torch.empty(E, COUT, **f32)
@@ -423,22 +461,22 @@ class EdgeConvTrain(torch.autograd.Function):
         vs = _v_scratch(B, Cn, N, dev)
         a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, None, COUT, vs)
 
-        _call("dgcnn_edgeconv_conv_a_train", C.byref(a), _ptr(y_a), _ptr(partials), _ptr(ymax), _ptr(ymin),
-                                                   _ptr(amax), _ptr(amin), st)
-        _call("dgcnn_bn_finalize", _ptr(partials), COUT, float(E), _ptr(gamma_a.detach()), _ptr(beta_a.detach()),
+        _call("dgcnn_edgeconv_conv_a_train", dev, C.byref(a), _ptr(y_a), _ptr(partials), _ptr(ymax), _ptr(ymin),
+                                                   _ptr(amax), _ptr(amin))
+        _call("dgcnn_bn_finalize", dev, _ptr(partials), COUT, float(E), _ptr(gamma_a.detach()), _ptr(beta_a.detach()),
                                          bn_a.eps, bn_a.momentum, _ptr(bn_a.running_mean), _ptr(bn_a.running_var),
-                                         _ptr(stat_a[0]), _ptr(stat_a[1]), _ptr(stat_a[2:]), st)
+                                         _ptr(stat_a[0]), _ptr(stat_a[1]), _ptr(stat_a[2:]))
         stat_b = None
         if two:
             stat_b = torch.empty(2 + 3, COUT, **f32)
-            _call("dgcnn_edgeconv_conv_b_train", C.byref(a), _ptr(y_a), _ptr(stat_a[2:]), _ptr(partials),
-                                                       _ptr(ymax), _ptr(ymin), _ptr(amax), _ptr(amin), st)
-            _call("dgcnn_bn_finalize", _ptr(partials), COUT, float(E), _ptr(gamma_b.detach()), _ptr(beta_b.detach()),
+            _call("dgcnn_edgeconv_conv_b_train", dev, C.byref(a), _ptr(y_a), _ptr(stat_a[2:]), _ptr(partials),
+                                                       _ptr(ymax), _ptr(ymin), _ptr(amax), _ptr(amin))
+            _call("dgcnn_bn_finalize", dev, _ptr(partials), COUT, float(E), _ptr(gamma_b.detach()), _ptr(beta_b.detach()),
                                              bn_b.eps, bn_b.momentum, _ptr(bn_b.running_mean), _ptr(bn_b.running_var),
-                                             _ptr(stat_b[0]), _ptr(stat_b[1]), _ptr(stat_b[2:]), st)
+                                             _ptr(stat_b[0]), _ptr(stat_b[1]), _ptr(stat_b[2:]))
         last = stat_b if two else stat_a
-        _call("dgcnn_edgeconv_select", M, _ptr(ymax), _ptr(ymin), _ptr(amax), _ptr(amin), _ptr(last[2:]),
-                                             _ptr(out), COUT, _ptr(ysel), _ptr(arg), st)
+        _call("dgcnn_edgeconv_select", dev, M, _ptr(ymax), _ptr(ymin), _ptr(amax), _ptr(amin), _ptr(last[2:]),
+                                             _ptr(out), COUT, _ptr(ysel), _ptr(arg))
         ctx.meta = meta
         ctx.two = two
         ctx.save_for_backward(rows, idx, wa, wb if two else wa, gamma_a.detach(), gamma_b.detach() if two else gamma_a.detach(),
@@ -455,7 +493,6 @@ class EdgeConvTrain(torch.autograd.Function):
         two = ctx.two
         M, E = B * N, B * N * k
         dev = dout.device
-        st = _stream()
         partials, dw_partials = _partials(dev)
         f32 = dict(dtype=torch.float32, device=dev)
         if dout.stride(1) != 1:
@@ -465,28 +502,30 @@ class EdgeConvTrain(torch.autograd.Function):
         g = torch.empty(M, COUT, **f32)
         last = stat_b if two else stat_a
         gamma_last = gamma_b if two else gamma_a
-        _call("dgcnn_edgeconv_bwd_prep", M, _ptr(dout), dout.stride(0), _ptr(ysel), _ptr(last[2:]), _ptr(g),
-                                               _ptr(partials), st)
+        _call("dgcnn_edgeconv_bwd_prep", dev, M, _ptr(dout), dout.stride(0), _ptr(ysel), _ptr(last[2:]), _ptr(g),
+                                               _ptr(partials))
         dgl = torch.empty(2, COUT, **f32)      # dgamma, dbeta of the last BN
         coef_l = torch.empty(3, COUT, **f32)
-        _call("dgcnn_bn_bwd_reduce", _ptr(partials), COUT, float(E), _ptr(gamma_last), _ptr(last[0]), _ptr(last[1]),
-                                           _ptr(dgl[0]), _ptr(dgl[1]), _ptr(coef_l), st)
+        _call("dgcnn_bn_bwd_reduce", dev, _ptr(partials), COUT, float(E), _ptr(gamma_last), _ptr(last[0]), _ptr(last[1]),
+                                           _ptr(dgl[0]), _ptr(dgl[1]), _ptr(coef_l))
         dw_b = dga = None
         if two:
             dz_a = torch.empty(E, COUT, **f32)
             dw_b = torch.empty(COUT, COUT, **f32)
-            _call("dgcnn_edgeconv_bwd_b", C.byref(a), _ptr(y_a), _ptr(stat_a[2:]), _ptr(g), _ptr(arg), _ptr(coef_l),
-                                                _ptr(dz_a), _ptr(dw_b), _ptr(partials), _ptr(dw_partials), st)
+            # the tensor-core conv_b backward is a 2-plane (2^-17) kernel: the FP32-accurate setting takes the FP32-FMA one
+            ab = a if GRAD_NSPLIT == 2 else _args(rows, ctx.ld, idx, B, Cn, N, k, wa, wb, None, COUT, impl=1)
+            _call("dgcnn_edgeconv_bwd_b", dev, C.byref(ab), _ptr(y_a), _ptr(stat_a[2:]), _ptr(g), _ptr(arg), _ptr(coef_l),
+                                                _ptr(dz_a), _ptr(dw_b), _ptr(partials), _ptr(dw_partials))
             dga = torch.empty(2, COUT, **f32)
             coef_a = torch.empty(3, COUT, **f32)
-            _call("dgcnn_bn_bwd_reduce", _ptr(partials), COUT, float(E), _ptr(gamma_a), _ptr(stat_a[0]), _ptr(stat_a[1]),
-                                               _ptr(dga[0]), _ptr(dga[1]), _ptr(coef_a), st)
+            _call("dgcnn_bn_bwd_reduce", dev, _ptr(partials), COUT, float(E), _ptr(gamma_a), _ptr(stat_a[0]), _ptr(stat_a[1]),
+                                               _ptr(dga[0]), _ptr(dga[1]), _ptr(coef_a))
         else:
             dz_a, coef_a, dga = None, coef_l, dgl
         rs = torch.zeros(M, 2 * COUT, **f32)            # [ r | s ]: scatter target and per-point sums, one GEMM operand
         r, s = rs[:, :COUT], rs[:, COUT:]
-        _call("dgcnn_edgeconv_bwd_a", C.byref(a), _ptr(y_a), _ptr(dz_a), _ptr(g), _ptr(arg), _ptr(coef_a),
-              _ptr(s), _ptr(r), 2 * COUT, st)
+        _call("dgcnn_edgeconv_bwd_a", dev, C.byref(a), _ptr(y_a), _ptr(dz_a), _ptr(g), _ptr(arg), _ptr(coef_a),
+              _ptr(s), _ptr(r), 2 * COUT)
         # point-level GEMMs on the tensor cores (bf16x2 split: gradient path):
         #   dX  = r Wa1 + s (Wa2 - Wa1)            = [r|s] @ [Wa1 ; Wa2-Wa1]
         #   dWa = [(r - s)^T X | s^T X]            from G = [r|s]^T X  (contraction over the points, split-K)
@@ -495,13 +534,79 @@ class EdgeConvTrain(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             wcat = torch.cat((wa1, wa2 - wa1), dim=0)                   # [128, C]
-            dx = tc_gemm(rs, wcat.t(), nsplit=2) if Cn >= 16 else rs @ wcat
-            if dx.shape != ctx.x_shape:
-                dx = dx.reshape(ctx.x_shape)
-        G = tc_gemm(rs.t(), X.t(), nsplit=2)                            # [128, C]
+            dx = tc_gemm(rs, wcat.t(), nsplit=GRAD_NSPLIT) if Cn >= 16 else rs @ wcat
+            if dx.shape != ctx.x_shape:                                 # rows padded to a multiple of 4 channels
+                dx = torch.nn.functional.pad(dx, (0, ctx.x_shape[1] - dx.shape[1]))
+        G = tc_gemm(rs.t(), X.t(), nsplit=GRAD_NSPLIT)                            # [128, C]
         dwa = torch.cat((G[:COUT] - G[COUT:], G[COUT:]), dim=1)
         # returns: x, idx, meta, w_a, gamma_a, beta_a, w_b, gamma_b, beta_b, bn_a, bn_b
         if two:
             return (dx, None, None, dwa.view(COUT, 2 * Cn, 1, 1), dga[0], dga[1], dw_b.view(COUT, COUT, 1, 1),
                     dgl[0], dgl[1], None, None)
         return dx, None, None, dwa.view(COUT, 2 * Cn, 1, 1), dga[0], dga[1], None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# the drivers' per-point passes on device: training criterion (train.py:180-197, util.py:17-34) and the
+# tile-inference epilogue (test.py:123-127)
+# ------------------------------------------------------------------------------------------------
+UNCLASSIFIED = 31          # test.py:15
+
+
+class SegLoss(torch.autograd.Function):
+    """loss = cal_loss(focus(softmax(logits), mask), focus(labels, mask)) — forward and backward in ONE kernel pass."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, mask, smoothing: float, want_pred: bool):
+        lib = _lib.load()
+        _need_cuda(logits, "seg_loss")
+        if logits.dim() != 3:
+            raise RuntimeError(f"seg_loss: expected logits [B, classes, N], got {tuple(logits.shape)}")
+        B, Cn, N = logits.shape
+        dev = logits.device
+        labels = labels.to(device=dev, dtype=torch.int64).reshape(B, N).contiguous()
+        if mask is not None:
+            mask = mask.to(device=dev).reshape(B, N).ne(0).to(torch.uint8).contiguous()
+        z = logits.detach()
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        need_grad = logits.requires_grad
+        dz = torch.empty_like(z, memory_format=torch.contiguous_format) if need_grad else None
+        pred = torch.empty(B, N, dtype=torch.int32, device=dev) if want_pred else None
+        nbytes = lib.dgcnn_seg_loss_workspace_bytes(B, N)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ds = dz.stride() if need_grad else (0, 0, 0)
+        _call("dgcnn_seg_loss_f32", dev, _ptr(z), z.stride(0), z.stride(1), z.stride(2), B, Cn, N, _ptr(labels), _ptr(mask),
+              float(smoothing), 1.0, _ptr(loss), _ptr(dz), ds[0], ds[1], ds[2], _ptr(pred), _ptr(ws), nbytes)
+        ctx.save_for_backward(dz)
+        ctx.mark_non_differentiable(*([pred] if want_pred else []))
+        return (loss, pred) if want_pred else loss
+
+    @staticmethod
+    def backward(ctx, dloss, *_unused):
+        (dz,) = ctx.saved_tensors
+        return (None if dz is None else dz * dloss), None, None, None, None
+
+
+def seg_loss(logits: torch.Tensor, labels: torch.Tensor, mask: Optional[torch.Tensor] = None, smoothing: float = 0.2,
+             return_pred: bool = False):
+    """The reference's training criterion in one device pass.
+
+    logits [B, classes, N] (the model's output), labels [B, N] (any integer/float dtype, as the reference's loaders
+    deliver them), mask [B, N] or None.  With a mask: train.py:180-197 (softmax, focus class for unmasked points,
+    cal_loss over classes + 1).  Without: the validation form train.py:265-270.  return_pred=True also returns the
+    arg-max channel per point (`labels_pred.max(dim=2)[1]`, int32 [B, N])."""
+    return SegLoss.apply(logits, labels, mask, smoothing, return_pred)
+
+
+def seg_predict(logits: torch.Tensor, min_class_confidence: float = 0.8, unclassified: int = UNCLASSIFIED,
+                return_conf: bool = False):
+    """test.py:119-127 on device: softmax over the classes, (max probability, arg-max) per point, arg-max replaced by
+    `unclassified` where the max probability is below min_class_confidence.  logits [B, classes, N] -> int64 [B, N]."""
+    _need_cuda(logits, "seg_predict")
+    B, Cn, N = logits.shape
+    z = logits.detach()
+    pred = torch.empty(B, N, dtype=torch.int64, device=z.device)
+    conf = torch.empty(B, N, dtype=torch.float32, device=z.device) if return_conf else None
+    _call("dgcnn_seg_predict_f32", z.device, _ptr(z), z.stride(0), z.stride(1), z.stride(2), B, Cn, N,
+          float(min_class_confidence), int(unclassified), _ptr(pred), _ptr(conf))
+    return (pred, conf) if return_conf else pred

@@ -96,6 +96,9 @@ typedef struct dgcnn_edgeconv_args {
   int ld_out;
   float* v_scratch;       /* optional float[B*N*64] scratch: enables the tensor-core kernels for C == 64
                              (holds the per-point centre term Wa2 x_i); NULL selects the FP32-FMA kernels   */
+  int impl;               /* kernel family of the 64-channel passes: 0 = default (tcgen05, warp-specialised pipelined
+                             conv_b), 1 = FP32-FMA kernels, 2 = serial tcgen05 kernels only.  Per call (no process-wide
+                             state); 1 and 2 exist for A/B checks.  The tensor-core paths are FP32-accurate (bf16x3).   */
 } dgcnn_edgeconv_args;
 
 /* BN "affine" vectors are float[192] = mean[64] | scale[64] | beta[64]; the kernels apply
@@ -128,11 +131,6 @@ int dgcnn_bn_finalize(const double* partials, int C, double count, const float* 
  * ysel float[B*N,64] and arg uint8[B*N,64] (slot of sel) are saved for backward.                       */
 int dgcnn_edgeconv_select(int M, const float* ymax, const float* ymin, const uint8_t* amax, const uint8_t* amin,
                           const float* affine, float* out, int ld_out, float* ysel, uint8_t* arg, void* stream);
-
-/* Select the implementation of the 64-channel EdgeConv passes: 2 (default) = tcgen05 kernels with the warp-specialised,
- * pipelined conv_b training pass, 1 = serial tcgen05 kernels only, 0 = FP32 FMA.
- * The tensor-core paths use the FP32-accurate bf16x3 split.  Returns the previous setting.  Process-wide; for A/B checks. */
-int dgcnn_set_edgeconv_tc(int enabled);
 
 /* Training backward (dense because of batch-stat BN; SURVEY.md §7 hard part 3).  Sequence:
  *   bwd_prep -> bn_bwd_reduce(last BN) -> [bwd_b -> bn_bwd_reduce(BN a)] -> bwd_a
@@ -208,12 +206,26 @@ size_t dgcnn_rows_colsum_workspace_bytes(int M, int C, int N);
 int dgcnn_rows_colsum_f32(const float* x, int M, int C, int N, float* out, void* workspace, size_t workspace_bytes,
                           void* stream);
 
-/* debug: exercises MN-major tcgen05 operand descriptors on one 128x64 tile pair (tests only) */
-int dgcnn_debug_mn_lab(const float* X, const float* Y, float* D, int lbo_a, int sbo_a, int lbo_b, int sbo_b,
-                       int kstep, int a_major, int b_major, void* stream);
+/* ---- training criterion on device (train.py:180-197 + util.py:17-34; the validation form train.py:265-270) -----------
+ * loss = mean over the B*N points of the label-smoothed (eps = `smoothing`, 0.2 upstream) cross entropy that the reference
+ * applies to softmax(logits) — i.e. log_softmax of PROBABILITIES, quirk kept.  mask != NULL (uint8 [B*N], 1 = point takes
+ * part): the training form with num_classes + 1 channels — a masked point contributes [p_0..p_{C-1}, 0] with its label,
+ * an unmasked one [0,..,0,1] with label C (constant, no gradient), replacing the per-point Python loops of train.py:183-192.
+ * mask == NULL: the validation form (C channels).  logits / dlogits are addressed with element strides, so both the
+ * model's [B,C,N] output and point-major rows work.  Forward and backward are one pass: dlogits (may be NULL) receives
+ * grad_scale * d(loss)/d(logits); pred (may be NULL, int32 [B*N]) the arg-max channel the drivers log as prediction.
+ * labels: int64 [B*N].  workspace: dgcnn_seg_loss_workspace_bytes(B, N).  Deterministic (fixed-order FP64 reduction). */
+size_t dgcnn_seg_loss_workspace_bytes(int B, int N);
+int dgcnn_seg_loss_f32(const float* logits, int64_t stride_b, int64_t stride_c, int64_t stride_n, int B, int C, int N,
+                       const int64_t* labels, const uint8_t* mask, float smoothing, float grad_scale, float* loss,
+                       float* dlogits, int64_t dstride_b, int64_t dstride_c, int64_t dstride_n, int32_t* pred,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
-/* debug: tcgen05.mma with the A operand in tensor memory on one 128x64x64 tile (tests only) */
-int dgcnn_debug_tmem_a_lab(const float* X, const float* Y, float* D, int swap, void* stream);
+/* ---- tile-inference epilogue (test.py:123-127, 305-308): softmax over the classes, (max probability, arg-max) per point,
+ * pred = arg-max, or `unclassified` (31 upstream) where the max probability is below min_conf.  pred: int64 [B*N] like
+ * the reference's tensor; conf (may be NULL): float [B*N] max probability.                                          */
+int dgcnn_seg_predict_f32(const float* logits, int64_t stride_b, int64_t stride_c, int64_t stride_n, int B, int C, int N,
+                          float min_conf, int64_t unclassified, int64_t* pred, float* conf, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,8 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
+# the package directory goes on sys.path the way a user of the reference's drivers would put it there (`from model import DGCNN`)
+for p in (ROOT, os.path.join(ROOT, "tests", "golden"), os.path.join(ROOT, "ahn3-dgcnn.pytorch_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 

@@ -83,4 +83,24 @@ MODEL_CASES = (
     ("eval_small", 2, 4, 96, 8, 5, 1024, "real", 31, False),
     ("eval_readme", 1, 4, 200, 20, 5, 1024, "unit", 32, False),
     ("train_small", 2, 4, 80, 6, 5, 1024, "real", 33, True),
+    # BASELINE.json configs[0] exactly: README example, B=1 F=4 N=1000 k=20 emb 1024 (README.md:71-86)
+    ("eval_cfg1", 1, 4, 1000, 20, 5, 1024, "unit", 34, False),
 )
+
+
+# (name, B, classes, N, masked fraction, seed) — the drivers' per-point passes (train.py:180-197, test.py:119-127)
+DRIVER_CASES = (
+    ("loss_small", 2, 5, 64, 0.5, 41),
+    ("loss_cfg", 3, 5, 700, 0.3, 42),
+    ("loss_allmasked", 1, 5, 33, 1.0, 43),
+    ("loss_nomask", 2, 7, 40, 0.0, 44),
+)
+
+
+def driver_inputs(seed: int, B: int, classes: int, N: int, frac: float):
+    """logits [B,classes,N] fp32, labels [B,N] fp64 (the loaders deliver float64, data.py:181), mask [B,N] fp64 0/1."""
+    rs = np.random.RandomState(seed)
+    logits = torch.from_numpy((rs.randn(B, classes, N) * 2.5).astype(np.float32))
+    labels = torch.from_numpy(rs.randint(0, classes, size=(B, N)).astype(np.float64))
+    mask = torch.from_numpy((rs.rand(B, N) < frac).astype(np.float64))
+    return logits, labels, mask

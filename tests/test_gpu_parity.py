@@ -91,9 +91,10 @@ def test_knn_errors(pkg):
 
 
 def test_knn_large_properties(pkg):
-    """cfg2 / cfg4-sized inputs: size-independent properties + sampled rows against the oracle."""
-    for (B, C, N, k) in ((8, 4, 7000, 30), (2, 64, 7000, 30), (1, 4, 32768, 30)):
-        x = common.points(5, B, C, N, "real" if C == 4 else "randn")
+    """cfg2 / cfg4-sized input graphs: size-independent properties + sampled rows against the oracle (bit-exact for C=4).
+    The feature-space graphs (C=64) at these sizes are compared row by row in test_gpu_baseline_shapes.py."""
+    for (B, C, N, k) in ((8, 4, 7000, 30), (1, 4, 32768, 30), (1, 4, 65536, 20)):
+        x = common.points(5, B, C, N, "real")
         got = pkg.knn(x.to(DEV), k).cpu()
         assert int(got.min()) >= 0 and int(got.max()) < N
         assert (torch.sort(got, -1)[0].diff(dim=-1) > 0).all()
@@ -102,11 +103,7 @@ def test_knn_large_properties(pkg):
         pd = O.score_rows(x, B - 1, rows)
         ref = pd.topk(k, dim=-1)[1]
         a, b = torch.sort(ref, -1)[0], torch.sort(got[B - 1, rows], -1)[0]
-        bad = (a != b).any(-1)
-        if C == 4:
-            assert not bad.any()
-        else:
-            assert bad.float().mean() < 0.05
+        assert torch.equal(a, b)
 
 
 def test_knn_permutation_equivariance(pkg):

@@ -71,11 +71,16 @@ def _knn_both(pkg, x, k):
 
 
 @pytest.mark.parametrize("B,C,N,k,kind", [(2, 64, 1500, 30, "randn"), (1, 64, 7000, 30, "unit"), (3, 64, 333, 20, "randn"),
-                                          (1, 32, 1000, 40, "randn"), (2, 64, 128, 48, "unit"), (1, 20, 640, 5, "randn")])
+                                          (1, 32, 1000, 40, "randn"), (2, 64, 128, 48, "unit"), (1, 20, 640, 5, "randn"),
+                                          (2, 4, 2000, 30, "real"), (1, 3, 700, 16, "unit"), (1, 4, 3000, 20, "dup"),
+                                          (2, 128, 900, 20, "randn"), (1, 100, 257, 33, "randn"), (1, 9, 200, 48, "unit")])
 def test_knn_tc_equals_exact_kernel(pkg, B, C, N, k, kind):
     x = common.points(2000 + N + C, B, C, N, kind)
     exact, tcv = _knn_both(pkg, x, k)
     assert torch.equal(exact, tcv)                     # identical table, identical order
+    rows = pkg.ops.pack_rows(x.to(DEV))
+    tset = pkg.ops.knn_rows(rows, B, C, N, k, method="tc", ordered=False)       # set mode: same neighbours, any order
+    assert torch.equal(torch.sort(tset, -1)[0], torch.sort(exact, -1)[0])
     if N <= 2000:
         rep = O.compare_neighbour_sets(x, O.knn(x, k), tcv.view(B, N, k).cpu().long(), tol_ulps=4.0)
         assert rep["hard"] == 0, rep
@@ -128,13 +133,13 @@ def test_knn_small_many_duplicates(pkg):
 def test_edgeconv_tc_matches_ffma_path(pkg, N, k):
     """Train-mode forward/backward with the tcgen05 EdgeConv passes vs the FP32-FMA passes (same graphs); the shapes
     cover 4, 6, 2 and 16 points per 128-row tile and ragged last tiles."""
-    lib = pkg._lib.load()
     B, Fd = 2, 4
     x = common.points(51, B, Fd, N, "real").to(DEV)
     w = common.weights(52, 5, Fd, 1024)
     outs = {}
-    for tcflag in (0, 1, 2):                  # FP32 FMA, serial tcgen05 kernels, warp-specialised pipelined kernels
-        old = lib.dgcnn_set_edgeconv_tc(tcflag)
+    for tcflag, impl in ((0, 1), (1, 2), (2, 0)):   # FP32 FMA, serial tcgen05 kernels, default (pipelined) — dgcnn_edgeconv_args.impl
+        old = pkg.ops.EDGECONV_IMPL
+        pkg.ops.EDGECONV_IMPL = impl
         try:
             net = pkg.DGCNN(5, Fd, k, dropout=0.0, cuda=True)
             net.load_state_dict(w, strict=False)
@@ -146,7 +151,7 @@ def test_edgeconv_tc_matches_ffma_path(pkg, N, k):
             outs[tcflag] = (y.detach(), [p.grad.clone() for p in net.parameters()],
                             [getattr(net, f"bn{i}").running_var.clone() for i in range(1, 6)])
         finally:
-            lib.dgcnn_set_edgeconv_tc(old)
+            pkg.ops.EDGECONV_IMPL = old
     y0, g0, rv0 = outs[0]
     for flag in (1, 2):
         y1, g1, rv1 = outs[flag]

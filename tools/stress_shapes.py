@@ -13,8 +13,9 @@ for (B, N, k) in [(1, 130, 5), (3, 515, 16), (1, 2049, 33), (2, 128, 48), (5, 30
     x = common.points(B * N + k, B, 4, N, "real").cuda()
     w = common.weights(7 + k, 5, 4, 1024)
     outs = {}
-    for flag in (0, 2):
-        old = lib.dgcnn_set_edgeconv_tc(flag)
+    for flag, impl in ((0, 1), (2, 0)):          # FP32 FMA vs the default tensor-core kernels (dgcnn_edgeconv_args.impl)
+        old = pkg.ops.EDGECONV_IMPL
+        pkg.ops.EDGECONV_IMPL = impl
         try:
             net = pkg.DGCNN(5, 4, k, dropout=0.0, cuda=True); net.load_state_dict(w, strict=False); net.train()
             y = net(x, forced_idx=outs.get("idx"))
@@ -22,7 +23,7 @@ for (B, N, k) in [(1, 130, 5), (3, 515, 16), (1, 2049, 33), (2, 128, 48), (5, 30
             outs.setdefault("idx", [i.view(B, N, k).long() for i in net.last_idx])
             outs[flag] = (y.detach(), [p.grad.clone() for p in net.parameters()])
         finally:
-            lib.dgcnn_set_edgeconv_tc(old)
+            pkg.ops.EDGECONV_IMPL = old
     ey = ((outs[0][0] - outs[2][0]).abs().max() / outs[0][0].abs().max()).item()
     # gradients that are analytically zero (e.g. the global-feature half of conv7 when B == 1: BatchNorm removes a
     # per-block constant) are pure rounding noise in both paths: measure against the largest gradient norm as well
