@@ -1,11 +1,14 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the DGCNN EdgeConv hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train|infer]
 
 Workload (BASELINE.json configs[1]/[2]): AHN3 training shape, B=8 blocks per GPU of N=7000 points, F=4, k=30,
-5 classes, emb 1024.  One step = forward + loss (softmax -> label-smoothed CE, reference train.py:180-197 /
-util.py:17-34) + backward + gradient all-reduce (N>1) + Adam update (reference train.py:118).  Synthetic
+5 classes, emb 1024.  One step = forward + the reference's masked criterion (softmax -> focus class for unmasked points
+-> label-smoothed CE on the probabilities, train.py:180-197 / util.py:17-34; class-balanced masks as data.py:80-105
+makes them) + backward + gradient all-reduce (N>1) + Adam update (reference train.py:118).  `--workload infer` is
+BASELINE configs[3]: tile inference, batches of 16 blocks of N=32768 points, k=30, blocks sharded over the GPUs with no
+collective (test.py:281-330), softmax/max/threshold on device; metric inference points/s.  Synthetic
 "real-like" blocks (xy in [0,30) m, z in [100,130) m, agl in [0,20) m), random-init weights.
 Metric: training points/s, whole job (all GPUs).
 
@@ -41,17 +44,16 @@ def make_batch(seed: int, B: int):
     x = torch.cat((torch.rand(B, 2, NPTS, generator=g) * 30, 100 + torch.rand(B, 1, NPTS, generator=g) * 30,
                    torch.rand(B, 1, NPTS, generator=g) * 20), dim=1)
     y = torch.randint(0, CLASSES, (B, NPTS), generator=g)
+    # class-balanced training mask of every block, as the loader side builds it (data.py:80-105): n = min(smallest class
+    # count, N // classes) random points per class
+    n_per = min(int(torch.stack([(y == c).sum(1) for c in range(CLASSES)]).min()), NPTS // CLASSES)
+    keys = torch.rand(B, NPTS, generator=g)
+    mask = torch.zeros(B, NPTS, dtype=torch.uint8)
+    for c in range(CLASSES):
+        kc = torch.where(y == c, keys, torch.full_like(keys, 2.0))
+        mask.scatter_(1, kc.argsort(dim=1)[:, :n_per], 1)
     # the reference's loaders produce [B,N,F]; the model sees the permute(0,2,1) view (train.py:176)
-    return x.permute(0, 2, 1).contiguous().permute(0, 2, 1), y
-
-
-def seg_loss(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
-    """The reference's training loss: label-smoothed CE (eps 0.2) applied to softmax(logits) (train.py:180,197)."""
-    p = torch.softmax(logits, dim=1).permute(0, 2, 1).reshape(-1, CLASSES)
-    gold = labels.reshape(-1)
-    one_hot = torch.zeros_like(p).scatter(1, gold.view(-1, 1), 1)
-    one_hot = one_hot * 0.8 + (1 - one_hot) * 0.2 / (CLASSES - 1)
-    return -(one_hot * torch.log_softmax(p, dim=1)).sum(dim=1).mean()
+    return x.permute(0, 2, 1).contiguous().permute(0, 2, 1), y, mask
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -96,9 +98,20 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_model_name() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def cpu_reference_steps(steps: int, warmup: int, sample_blocks: int):
-    """Time the CPU oracle's training step (fwd + loss + bwd + Adam) on `sample_blocks` blocks of the workload."""
+    """Time the CPU oracle's training step (fwd + masked criterion + bwd + Adam) on `sample_blocks` blocks of the workload."""
     from oracle import dgcnn_oracle as O
+    from oracle import drivers_oracle as D
     torch.set_num_threads(os.cpu_count() or 1)
     params = O.init_params(CLASSES, FEAT, EMB, seed=0)
     leaves = []
@@ -108,13 +121,12 @@ def cpu_reference_steps(steps: int, warmup: int, sample_blocks: int):
             leaves.append(v)
     net = O.OracleDGCNN(params, KNN, dropout=0.5, training=True)
     opt = torch.optim.Adam(leaves, lr=1e-3, weight_decay=1e-4)
-    x, y = make_batch(0, sample_blocks)
-    xin = x
+    x, y, mask = make_batch(0, sample_blocks)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad()
-        loss = seg_loss(net(xin), y)
+        loss, _ = D.train_criterion(net(x), y, mask.numpy(), CLASSES)      # vectorised form of train.py:180-197
         loss.backward()
         opt.step()
         if i >= warmup:
@@ -122,9 +134,41 @@ def cpu_reference_steps(steps: int, warmup: int, sample_blocks: int):
     return times, torch.get_num_threads()
 
 
-def workload_config(world: int) -> dict:
+def cpu_reference_infer(steps: int, warmup: int, n_points: int):
+    """The reference's predict() loop body (test.py:291-306, B=1) on one block of `n_points` points."""
+    from oracle import dgcnn_oracle as O
+    from oracle import drivers_oracle as D
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = O.init_params(CLASSES, FEAT, EMB, seed=0)
+    net = O.OracleDGCNN(params, KNN, training=False)
+    x = make_blocks(0, 1, n_points).permute(0, 2, 1).float()
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            D.predict_labels(net(x), 0.8)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return times, torch.get_num_threads()
+
+
+def make_blocks(seed: int, nb: int, n: int) -> torch.Tensor:
+    """[nb, n, F] float32 blocks in the reference's block layout (test.py:276-299)."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.cat((torch.rand(nb, n, 2, generator=g) * 30, 100 + torch.rand(nb, n, 1, generator=g) * 30,
+                      torch.rand(nb, n, 1, generator=g) * 20), dim=2)
+
+
+INFER_B, INFER_N = 16, 32768
+
+
+def workload_config(world: int, workload: str = "train") -> dict:
     """`config` of the JSON line: identical for our arm and for the reference arm."""
-    return {"workload": f"AHN3 train step (fwd+loss+bwd+allreduce+Adam) B={B_PER_GPU}/GPU F={FEAT} N={NPTS} k={KNN} classes={CLASSES} emb={EMB}",
+    if workload == "infer":
+        return {"workload": f"AHN3 tile inference (predict(): fwd + softmax/max/threshold) {INFER_B} blocks/GPU/batch F={FEAT} N={INFER_N} k={KNN} classes={CLASSES} emb={EMB}",
+                "parallelism": f"blocks sharded over {world} GPU(s), no collective", "global_batch": INFER_B * world,
+                "l2": "inputs larger than L2: a batch streams > 8 GB of per-edge work; 2 rotating block sets"}
+    return {"workload": f"AHN3 train step (fwd+masked criterion+bwd+allreduce+Adam) B={B_PER_GPU}/GPU F={FEAT} N={NPTS} k={KNN} classes={CLASSES} emb={EMB}",
             "parallelism": f"dp{world}", "global_batch": B_PER_GPU * world,
             "l2": "no explicit flush: each step streams >1.5 GB of per-edge intermediates (L2 is 126 MB); 4 rotating input batches"}
 
@@ -132,17 +176,27 @@ def workload_config(world: int) -> dict:
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    sample_blocks = 2
-    times, cores = cpu_reference_steps(args.steps, args.warmup, sample_blocks)
-    total = sum(times)
-    value = sample_blocks * NPTS * len(times) / total
-    sample = f"{sample_blocks} of {B_PER_GPU} blocks (N={NPTS}) per step, {args.warmup} warm-up + {args.steps} timed steps"
+    if args.workload == "infer":
+        sample_n = 8192                      # the reference's B x N x N matrices: 32768^2 floats x 3 per layer do not fit the step budget
+        times, cores = cpu_reference_infer(args.steps, args.warmup, sample_n)
+        total = sum(times)
+        value = sample_n * len(times) / total
+        sample = (f"one block of N={sample_n} points per step (B=1 like test.py:291-306; N={INFER_N} needs 3 x 4.3 GB distance "
+                  f"matrices per layer and ~16x the time), {args.warmup} warm-up + {args.steps} timed steps")
+        metric = INFER_METRIC
+    else:
+        sample_blocks = B_PER_GPU
+        times, cores = cpu_reference_steps(args.steps, args.warmup, sample_blocks)
+        total = sum(times)
+        value = sample_blocks * NPTS * len(times) / total
+        sample = f"the full batch: {sample_blocks} blocks (N={NPTS}) per step, {args.warmup} warm-up + {args.steps} timed steps"
+        metric = METRIC
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args.gpus, args.workload),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "cpu": cpu_model_name()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -150,19 +204,17 @@ def run_reference(args, rank: int):
 
 
 # ------------------------------------------------------------------------------------------------ roofline bookkeeping
-def kernel_flops(name: str, calls_per_step: int, B: int):
-    """Algorithmic FLOPs of ALL launches of one entry point in one step (DESIGN.md §kernels)."""
-    M = B * NPTS
+def kernel_flops(name: str, B: int, N: int = NPTS):
+    """Algorithmic FLOPs of ALL launches of one entry point in one step (DESIGN.md §kernels; SURVEY §8d)."""
+    M = B * N
     E = M * KNN
-    if name == "dgcnn_knn_f32":                       # xyz/agl graph (C=4): 2*B*N^2*C
-        return 2.0 * B * NPTS * NPTS * FEAT
-    if name == "dgcnn_knn_tc_f32":                    # two feature-space graphs (C=64)
-        return 2.0 * B * NPTS * NPTS * (64 + 64)
+    if name == "dgcnn_knn_tc_f32":                    # all three graphs: C = 4 (input), 64, 64 (feature space): 2*B*N^2*C
+        return 2.0 * B * N * N * (FEAT + 64 + 64)
     if name == "dgcnn_edgeconv_conv_a_train":         # conv1 (2F->64), conv3, conv5 (128->64)
         return 2.0 * E * 64 * (2 * FEAT + 128 + 128)
     if name == "dgcnn_edgeconv_conv_b_train":         # conv2, conv4 (64->64)
         return 2.0 * E * 64 * 64 * 2
-    if name == "dgcnn_edgeconv_bwd_b":                # per block: dW_b and dh GEMMs (recompute of y_b not counted)
+    if name == "dgcnn_edgeconv_bwd_b":                # per block: dW_b and dh GEMMs
         return 2.0 * E * 64 * 64 * 2 * 2
     if name == "dgcnn_tc_gemm_f32":                   # conv6/7/8 forward + dgrad + wgrad, and the EdgeConv point-level GEMMs
         head = 2.0 * M * (192 * EMB + 192 * 512 + 512 * 256) * 3
@@ -171,6 +223,33 @@ def kernel_flops(name: str, calls_per_step: int, B: int):
     if name == "dgcnn_edgeconv_fwd_eval":
         return 2.0 * E * 64 * (2 * FEAT + 64 + 128 + 64 + 128)
     return 0.0
+
+
+TENSOR_KERNELS = ("dgcnn_tc_gemm_f32", "dgcnn_knn_tc_f32", "dgcnn_edgeconv_bwd_b", "dgcnn_edgeconv_conv_b_train",
+                  "dgcnn_edgeconv_conv_a_train", "dgcnn_edgeconv_fwd_eval")
+
+
+def roofline_of(per_kernel: dict, steps: int, B: int, N: int, peaks: dict, sm_mhz: float):
+    """Roofline entry of the entry point with the largest device time among those with an algorithmic FLOP count."""
+    dom, dom_ms = None, 0.0
+    for name, (calls, tot) in per_kernel.items():
+        if kernel_flops(name, B, N) > 0 and tot > dom_ms:
+            dom, dom_ms = name, tot
+    if not dom:
+        return None
+    fl = kernel_flops(dom, B, N)
+    achieved = fl / (dom_ms / steps * 1e-3) / 1e12
+    tensor_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+    kind = ("measured sustained dense bf16 tensor peak (MEASURED_PEAKS.json); the kernels issue 3 (bf16x2 split) or 6 (bf16x3) "
+            "kind::f16 MMAs per algorithmic product for FP32-level accuracy, so the ceiling for ALGORITHMIC flops is peak/3 .. peak/6")
+    traffic = None
+    try:        # measured DRAM bytes per launch from the committed `ncu --set full` capture (not a live number)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(dom, {}).get("bytes_per_launch")
+    except Exception:
+        pass
+    return {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+            "frac": achieved / tensor_peak, "traffic": traffic, "peak_kind": kind,
+            "launches_per_step": per_kernel[dom][0] / steps, "ms_per_step": dom_ms / steps}
 
 
 # ------------------------------------------------------------------------------------------------ extras
@@ -186,11 +265,12 @@ def _event_ms(fn, iters):
 
 
 def layer_times(pkg, dev):
-    """kNN + EdgeConv block (train mode) per layer at the bench shape: forward and forward+backward, microseconds."""
+    """kNN + EdgeConv block (train mode) per layer at the bench shape: forward and forward+backward, microseconds, with the
+    achieved algorithmic TFLOP/s of the fused layer (kNN Gram + EdgeConv convs, fwd+bwd = 3x the conv FLOPs)."""
     ops = pkg.ops
     g = torch.Generator().manual_seed(1)
     B, N, k = B_PER_GPU, NPTS, KNN
-    M = B * N
+    E = B * N * k
     out = {}
     for name, Cn, two in (("L1 (C=4, conv1+conv2)", FEAT, True), ("L2 (C=64, conv3+conv4)", 64, True), ("L3 (C=64, conv5)", 64, False)):
         x = (torch.randn(B, Cn, N, generator=g) if Cn > 4 else make_batch(7, B)[0]).to(dev)
@@ -202,7 +282,7 @@ def layer_times(pkg, dev):
 
         def fwd(req=False):
             r = rows.detach().requires_grad_(req)
-            idx = ops.knn_rows(r.detach(), B, Cn, N, k)
+            idx = ops.knn_rows(r.detach(), B, Cn, N, k, ordered=False)
             return r, ops.EdgeConvTrain.apply(r, idx, (B, Cn, N, k), wa, ga, be, wb, ga if two else None, be if two else None,
                                               ops.BNState(None, None), ops.BNState(None, None) if two else None)
 
@@ -212,13 +292,18 @@ def layer_times(pkg, dev):
 
         for _ in range(2):
             fwd_bwd()
-        out[name] = {"fwd": round(1e3 * _event_ms(lambda: fwd(), 5), 1), "fwd_bwd": round(1e3 * _event_ms(fwd_bwd, 5), 1)}
+        t_f, t_fb = _event_ms(lambda: fwd(), 5), _event_ms(fwd_bwd, 5)
+        gram = 2.0 * B * N * N * Cn
+        conv = 2.0 * E * 64 * (2 * Cn + (64 if two else 0))
+        out[name] = {"fwd": round(1e3 * t_f, 1), "fwd_bwd": round(1e3 * t_fb, 1),
+                     "fwd_tflops": round((gram + conv) / t_f / 1e9, 1), "fwd_bwd_tflops": round((gram + 3 * conv) / t_fb / 1e9, 1)}
     return out
 
 
 def eager_gpu_oracle(dev):
     """The CPU oracle's torch code run eagerly on this GPU (FP32, TF32 off): the library composition the kernels replace."""
     from oracle import dgcnn_oracle as O
+    from oracle import drivers_oracle as D
     old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
@@ -231,12 +316,12 @@ def eager_gpu_oracle(dev):
                 leaves.append(v)
         net = O.OracleDGCNN(params, KNN, dropout=0.5, training=True)
         opt = torch.optim.Adam(leaves, lr=1e-3, weight_decay=1e-4, fused=True)
-        x, y = make_batch(0, B_PER_GPU)
+        x, y, _ = make_batch(0, B_PER_GPU)
         x, y = x.to(dev), y.to(dev)
 
         def step():
             opt.zero_grad()
-            seg_loss(net(x), y).backward()
+            D.validation_criterion(net(x), y, CLASSES)[0].backward()       # (the masked form's host loops would only add to it)
             opt.step()
 
         step()
@@ -250,7 +335,14 @@ def eager_gpu_oracle(dev):
         torch.cuda.empty_cache()
 
 
-# ------------------------------------------------------------------------------------------------ our arm
+def load_peaks() -> dict:
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+# ------------------------------------------------------------------------------------------------ our arm: training
 def run_ours(args, rank: int, local: int, world: int):
     import __graft_entry__ as entry
     import torch.distributed as dist
@@ -267,17 +359,18 @@ def run_ours(args, rank: int, local: int, world: int):
 
     nbuf = 4
     host = [make_batch(1000 * rank + i, B_PER_GPU) for i in range(nbuf)]
-    host = [(x.pin_memory(), y.pin_memory()) for x, y in host]
-    resident = [(x.to(dev), y.to(dev)) for x, y in host]
-    h2d = host[0][0].numel() * 4 + host[0][1].numel() * 8
+    host = [(x.pin_memory(), y.pin_memory(), m.pin_memory()) for x, y, m in host]
+    resident = [(x.to(dev), y.to(dev), m.to(dev)) for x, y, m in host]
+    h2d = host[0][0].numel() * 4 + host[0][1].numel() * 8 + host[0][2].numel()
 
-    def step(x, y):
+    def step(x, y, m, update=True):
         bucket.zero()
-        # callers hand the model the [B,N,F] -> permute(0,2,1) view (train.py:176)
-        loss = seg_loss(model(x), y)
+        # callers hand the model the [B,N,F] -> permute(0,2,1) view (train.py:176); criterion = train.py:180-197 on device
+        loss = ops.seg_loss(model(x), y, m)
         loss.backward()
         bucket.all_reduce_mean()
-        opt.step()
+        if update:
+            opt.step()
         return loss
 
     def barrier():
@@ -300,85 +393,77 @@ def run_ours(args, rank: int, local: int, world: int):
 
     for i in range(max(args.warmup, 3)):
         step(*resident[i % nbuf])
-    # ---- device-resident throughput --------------------------------------------------------------
+    # ---- device-resident throughput: no per-call instrumentation inside this region ---------------------------------
     sampler = ClockSampler(local)
     sampler.start()
-    ops.LOG.reset(timing=True)
+    ops.LOG.reset(timing=False)
     ms = timed(lambda i: step(*resident[i % nbuf]), args.steps)
     launches = ops.LOG.launches
-    per_kernel = ops.LOG.summary()
     clocks = sampler.stop()
-    ops.LOG.reset(timing=False)
     points = B_PER_GPU * NPTS * world * args.steps
     value = points / (ms * 1e-3)
 
     # ---- end-to-end through the public API with host buffers ------------------------------------------
     def e2e_step(i):
-        xh, yh = host[i % nbuf]
+        xh, yh, mh = host[i % nbuf]
         x = xh.to(dev, non_blocking=True)
         y = yh.to(dev, non_blocking=True)
-        loss = step(x, y)
+        m = mh.to(dev, non_blocking=True)
+        loss = step(x, y, m)
         return float(loss.item())            # D2H read of the step's result
 
     e2e_step(0)
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = points / (ms_e2e * 1e-3)
 
+    # ---- separate instrumented pass: per-entry-point device time (CUDA event pairs around every C-ABI call) ------------
+    ops.LOG.reset(timing=True)
+    ms_instr = timed(lambda i: step(*resident[i % nbuf]), args.steps)
+    per_kernel = ops.LOG.summary()
+    ops.LOG.reset(timing=False)
+    # ---- optimizer alone (SURVEY §8d metric i): the same step without the Adam update --------------------------------
+    ms_noopt = timed(lambda i: step(*resident[i % nbuf], update=False), args.steps)
+
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel -----------------------------------------------------------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    # all of our GEMM-shaped kernels run on the FP32 FMA pipe in this round: peak = 148 SM x 128 lanes x 2 x clock
+    peaks = load_peaks()
     sm_mhz = clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
-    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    dom, dom_ms = None, 0.0
     breakdown = {}
     for name, (calls, tot) in sorted(per_kernel.items(), key=lambda kv: -kv[1][1]):
         breakdown[name] = {"calls_per_step": calls / args.steps, "ms_per_step": tot / args.steps}
-        if kernel_flops(name, 0, B_PER_GPU) > 0 and tot > dom_ms:
-            dom, dom_ms = name, tot
-    roof = None
-    if dom:
-        fl = kernel_flops(dom, 0, B_PER_GPU)
-        achieved = fl / (dom_ms / args.steps * 1e-3) / 1e12
-        on_tensor = dom in ("dgcnn_tc_gemm_f32", "dgcnn_knn_tc_f32", "dgcnn_edgeconv_bwd_b", "dgcnn_edgeconv_conv_b_train")
-        tensor_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
-        peak = tensor_peak if on_tensor else fp32_peak
-        kind = ("measured sustained dense bf16 tensor peak (MEASURED_PEAKS.json); the kernel issues 3 (bf16x2) or 6 (bf16x3) "
-                "kind::f16 MMAs per algorithmic product for FP32-level accuracy, so the ceiling for ALGORITHMIC flops is "
-                "peak/3 .. peak/6" if on_tensor else
-                f"FP32 FMA pipe at the median SM clock under load ({sm_mhz:.0f} MHz); kernel is FFMA-based")
-        # measured DRAM bytes per launch of that entry point from the committed `ncu --set full` capture (not a live number)
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(dom, {}).get("bytes_per_launch")
-        except Exception:
-            pass
-        roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_kind": kind,
-                "launches_per_step": per_kernel[dom][0] / args.steps, "ms_per_step": dom_ms / args.steps}
+    roof = roofline_of(per_kernel, args.steps, B_PER_GPU, NPTS, peaks, sm_mhz)
 
-    # ---- extras: kNN + EdgeConv per layer, and the oracle run eagerly on this GPU -----------------
+    # ---- extras: kNN + EdgeConv per layer, the FP32-accurate gradient setting, eager oracle on this GPU ----
     extras = None
     if world == 1 and not args.no_extras:
-        extras = {"layers_us": layer_times(pkg, dev), "torch_eager_gpu": eager_gpu_oracle(dev)}
+        extras = {"layers_us": layer_times(pkg, dev)}
+        old = ops.GRAD_NSPLIT
+        try:
+            ops.GRAD_NSPLIT = 3
+            for i in range(3):
+                step(*resident[i % nbuf])
+            ms3 = timed(lambda i: step(*resident[i % nbuf]), args.steps)
+            extras["grad_nsplit3"] = {"ms_per_step": ms3 / args.steps, "value": points / (ms3 * 1e-3), "unit": UNIT,
+                                      "what": "same step with every gradient GEMM on 3 bf16 planes (FP32-accurate, 6 MMAs per product) "
+                                              "and the conv_b backward on the FP32-FMA kernel; the headline uses 2 planes (2^-17) there"}
+        finally:
+            ops.GRAD_NSPLIT = old
+        extras["torch_eager_gpu"] = eager_gpu_oracle(dev)
 
     # ---- CPU baseline (bounded sample) -------------------------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        sb = 2
-        times, cores = cpu_reference_steps(1, 1, sb)
-        cpu = {"value": sb * NPTS * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{sb} of {B_PER_GPU} blocks (N={NPTS}), 1 warm-up + 1 timed training step of the CPU oracle"}
+        times, cores = cpu_reference_steps(2, 1, B_PER_GPU)
+        cpu = {"value": B_PER_GPU * NPTS * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model_name(),
+               "sample": f"the full batch of {B_PER_GPU} blocks (N={NPTS}), 1 warm-up + 2 timed training steps of the CPU oracle"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
+        "precision": ("FP32 I/O; forward GEMMs/Gram tiles as bf16x3 split MMAs (FP32-accurate, ~2^-24) or exact FP32 FMA re-scores; "
+                      f"gradient GEMMs on {ops.GRAD_NSPLIT} bf16 planes ({'2^-17 relative' if ops.GRAD_NSPLIT == 2 else 'FP32-accurate'}), "
+                      "see extras.grad_nsplit3 for the all-FP32-accurate step"),
         "config": workload_config(world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
@@ -386,8 +471,94 @@ def run_ours(args, rank: int, local: int, world: int):
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "optimizer": {"ms_per_step": max(ms - ms_noopt, 0.0) / args.steps, "what": "fused Adam (train.py:118): step time minus the same step without opt.step()",
+                      "ms_per_step_without": ms_noopt / args.steps},
         "kernels": breakdown,
+        "kernels_pass_ms_per_step": ms_instr / args.steps,
         "extras": extras,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm: tile inference
+INFER_METRIC = "inference points/sec (N=32768,k=30, 16 blocks/batch)"
+
+
+def run_infer(args, rank: int, local: int, world: int):
+    import __graft_entry__ as entry
+    import torch.distributed as dist
+    pkg = entry.load_package()
+    ops = pkg.ops
+    inference = __import__(entry.PKG_NAME + ".inference", fromlist=["x"])
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)
+    model = pkg.DGCNN(CLASSES, FEAT, KNN, dropout=0.5, emb_dims=EMB, cuda=True).eval()
+    nb = INFER_B * world                                           # one batch per GPU and step; the tile's blocks are shared by all ranks
+    host_sets = [make_blocks(10 + i, nb, INFER_N).pin_memory() for i in range(2)]
+    dev_sets = [h.to(dev) for h in host_sets]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            fn(i)
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def resident_step(i):
+        blocks = dev_sets[i % 2][rank::world]                      # this rank's shard, already in HBM
+        x = inference.shift_to_block_origin(blocks.permute(0, 2, 1)).float()
+        with torch.no_grad():
+            return ops.seg_predict(model(x), 0.8)
+
+    def e2e_step(i):
+        return inference.predict_blocks(model, host_sets[i % 2], batch_size=INFER_B, min_class_confidence=0.8, rank=rank, world=world)
+
+    for i in range(max(args.warmup, 3)):
+        resident_step(i)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.LOG.reset(timing=False)
+    ms = timed(resident_step, args.steps)
+    launches = ops.LOG.launches
+    clocks = sampler.stop()
+    points = INFER_B * INFER_N * world * args.steps
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, args.steps)
+    ops.LOG.reset(timing=True)
+    timed(resident_step, args.steps)
+    per_kernel = ops.LOG.summary()
+    ops.LOG.reset(timing=False)
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    breakdown = {name: {"calls_per_step": calls / args.steps, "ms_per_step": tot / args.steps}
+                 for name, (calls, tot) in sorted(per_kernel.items(), key=lambda kv: -kv[1][1])}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        times, cores = cpu_reference_infer(1, 1, 8192)
+        cpu = {"value": 8192 * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model_name(),
+               "sample": "one block of N=8192 points (B=1, the reference's predict() loop body), 1 warm-up + 1 timed forward"}
+    line = {
+        "metric": INFER_METRIC, "value": points / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(world, "infer"),
+        "e2e": {"value": points / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": INFER_B * INFER_N * FEAT * 4,
+                "d2h_bytes_per_step": INFER_B * INFER_N * 8, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": roofline_of(per_kernel, args.steps, INFER_B, INFER_N, peaks, clocks["sm_mhz"] or 1965.0),
+        "cpu_baseline": cpu, "kernels": breakdown,
     }
     print(json.dumps(line), flush=True)
 
@@ -398,20 +569,22 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "infer"],
+                    help="train = BASELINE configs[1]/[2] (the headline metric); infer = configs[3], sharded tile inference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the per-layer timings and the eager-GPU oracle run")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-layer timings, the nsplit=3 step and the eager-GPU oracle run")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
         return
     import __graft_entry__ as entry
-    pkg = entry.load_package()
+    entry.load_package()
     parallel = __import__(entry.PKG_NAME + ".parallel", fromlist=["x"])
     rank, local, world = parallel.init_from_env("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
-    run_ours(args, rank, local, world)
+    (run_infer if args.workload == "infer" else run_ours)(args, rank, local, world)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

@@ -1,6 +1,6 @@
 """tcgen05.mma with A in tensor memory: checks the TMEM operand layout on one 128x64x64 tile."""
 import os, sys, ctypes as C
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
 import __graft_entry__ as entry

@@ -12,11 +12,11 @@ pkg = entry.load_package()
 torch.manual_seed(0)
 model = pkg.DGCNN(bench.CLASSES, bench.FEAT, bench.KNN, dropout=0.5, emb_dims=bench.EMB, cuda=True).train()
 opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
-x, y = bench.make_batch(0, B)
-x, y = x.cuda(), y.cuda()
+x, y, m = bench.make_batch(0, B)
+x, y, m = x.cuda(), y.cuda(), m.cuda()
 for i in range(1 + steps):
     opt.zero_grad()
-    loss = bench.seg_loss(model(x), y)
+    loss = pkg.ops.seg_loss(model(x), y, m)
     loss.backward()
     opt.step()
 torch.cuda.synchronize()
