@@ -50,6 +50,8 @@ SIGNATURES = {
     "dgcnn_tc_gemm_colstats_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "dgcnn_tc_gemm_bn_lrelu_segmax_f32": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P,
                                                   c_float, c_float, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "dgcnn_global_feature_bwd_sparse_f32": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, c_int, c_int, c_int, _P, c_int, _P, _P]),
+    "dgcnn_vecmat_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_float, _P, _P]),
     "dgcnn_rows_bn_supported": (c_int, [c_int]),
     "dgcnn_rows_bn_workspace_bytes": (c_size_t, [c_int]),
     "dgcnn_rows_bn_lrelu_fwd": (c_int, [_P, c_int, c_int, _P, c_int, _P, _P, c_float, c_float, c_int, _P, _P, _P, _P, _P, _P,

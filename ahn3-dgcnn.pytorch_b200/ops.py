@@ -302,16 +302,25 @@ class GlobalFeature(torch.autograd.Function):
         s1, s2 = gdz.sum(0), (gdz * yhat).sum(0)
         kappa = a * (s2 / M) * rstd
         bprime = a * (s1 / M) - kappa * mean
-        idx = nstar.reshape(-1).long()
-        # dfeat
-        gram_w = (w * kappa[:, None]).t() @ w                          # [K,K] = W^T diag(kappa) W (symmetric)
-        dfeat = tc_gemm(feat, gram_w, nsplit=GRAD_NSPLIT)
-        dfeat.neg_().sub_(bprime @ w)
-        dfeat.index_add_(0, idx, (a * gdz).reshape(-1, 1) * w.repeat(B, 1))
-        # dW
-        t1 = (gdz.unsqueeze(-1) * feat[idx].view(B, E, -1)).sum(0)     # [E,K] = dz^T feat
-        f2 = tc_gemm(feat.t(), feat.t(), nsplit=GRAD_NSPLIT)                     # [K,K] = feat^T feat (split-K over the points)
-        dw = a[:, None] * t1 - bprime[:, None] * rows_colsum(feat, M) - kappa[:, None] * (w @ f2)
+        K = feat.shape[1]
+        if K % 4 or feat.stride(1) != 1 or w.stride(1) != 1:
+            raise RuntimeError("GlobalFeature: feature width must be a multiple of 4 with unit inner stride")
+        dev = feat.device
+        # dense parts on the tensor cores: dfeat = -feat (W^T diag(kappa) W) - b' W  (the sign is folded into the small matrix)
+        gram_neg = tc_gemm((w * (-kappa)[:, None]).t(), w.t(), nsplit=GRAD_NSPLIT)      # [K,K] = -W^T diag(kappa) W (symmetric)
+        dfeat = tc_gemm(feat, gram_neg, nsplit=GRAD_NSPLIT)
+        cvec = torch.empty(K, dtype=torch.float32, device=dev)
+        _call("dgcnn_vecmat_f32", dev, _ptr(bprime), _ptr(w), w.stride(0), E, K, -1.0, _ptr(cvec))
+        dfeat.add_(cvec)
+        # sparse parts in one pass: scatter of a dz W into dfeat, and t1 = dz^T feat
+        t1 = torch.empty(E, K, dtype=torch.float32, device=dev)
+        gdz_c = gdz.contiguous()
+        _call("dgcnn_global_feature_bwd_sparse_f32", dev, _ptr(feat), feat.stride(0), _ptr(w), w.stride(0), _ptr(nstar), _ptr(gdz_c),
+              _ptr(a.contiguous()), B, E, K, _ptr(dfeat), dfeat.stride(0), _ptr(t1))
+        # dW = a dz^T feat - b' colsum(feat)^T - diag(kappa) W (feat^T feat)
+        f2 = tc_gemm(feat.t(), feat.t(), nsplit=GRAD_NSPLIT)                    # [K,K] = feat^T feat (split-K over the points)
+        wf2 = tc_gemm(w, f2, nsplit=GRAD_NSPLIT)                                # f2 is symmetric: W f2 = W f2^T
+        dw = a[:, None] * t1 - bprime[:, None] * rows_colsum(feat, M) - kappa[:, None] * wf2
         return dfeat, dw, s2, s1, None, None, None, None
 
 
@@ -379,12 +388,9 @@ def bn_lrelu_rows(y: torch.Tensor, bn_mod, training: bool, N: int, bias: Optiona
 
 
 def linear(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
-    """x @ w^T; tensor-core path for GEMMs big enough to fill the machine, library GEMM otherwise."""
-    M, K = x.shape
-    N = w.shape[0]
-    if x.is_cuda and x.dtype == torch.float32 and M >= 1024 and K >= 64:
-        return TcLinear.apply(x, w)                 # also the 5-class conv9: padded tiles beat the library's large-K path
-    return x @ w.t()
+    """x @ w^T on the tensor cores (tcgen05, FP32-accurate split); no library GEMM on the model path, whatever the shape."""
+    _need_cuda(x, "linear")
+    return TcLinear.apply(x, w)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -534,7 +540,7 @@ class EdgeConvTrain(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             wcat = torch.cat((wa1, wa2 - wa1), dim=0)                   # [128, C]
-            dx = tc_gemm(rs, wcat.t(), nsplit=GRAD_NSPLIT) if Cn >= 16 else rs @ wcat
+            dx = tc_gemm(rs, wcat.t(), nsplit=GRAD_NSPLIT)
             if dx.shape != ctx.x_shape:                                 # rows padded to a multiple of 4 channels
                 dx = torch.nn.functional.pad(dx, (0, ctx.x_shape[1] - dx.shape[1]))
         G = tc_gemm(rs.t(), X.t(), nsplit=GRAD_NSPLIT)                            # [128, C]

@@ -183,6 +183,16 @@ int dgcnn_tc_gemm_bn_lrelu_segmax_f32(const float* A, int64_t a_row_stride, int6
                                       float* g, float* ysel, int32_t* nstar,
                                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- backward of conv6 + bn6 + LeakyReLU + global max, sparse half (model.py:172-175; see dgcnn_tc_gemm_bn_lrelu_segmax_f32) ----
+ * gdz[B,E] = gradient at the B*E arg-max entries (row nstar[b,e] of block b), a[E] = gamma*rstd.
+ *   dfeat[nstar[b,e], :] += a[e] * gdz[b,e] * w[e, :]   (atomic scatter into the caller-initialised dfeat[M,K])
+ *   t1[e, :] = sum_b gdz[b,e] * feat[nstar[b,e], :]      ([E,K], overwritten; fixed order)
+ * K % 4 == 0, 16-byte aligned rows.  dgcnn_vecmat_f32: c[K] = scale * v[E] W[E,K] (the b' W row constant).                */
+int dgcnn_global_feature_bwd_sparse_f32(const float* feat, int ld_feat, const float* w, int ld_w, const int32_t* nstar,
+                                        const float* gdz, const float* a, int B, int E, int K, float* dfeat, int ld_dfeat,
+                                        float* t1, void* stream);
+int dgcnn_vecmat_f32(const float* v, const float* w, int ld_w, int E, int K, float scale, float* c, void* stream);
+
 /* ---- shared-MLP head: BatchNorm1d (+ per-block bias) + LeakyReLU(0.2) over point-major rows ---------------------------
  * Replaces `bn7(conv7(..))`, `bn8(conv8(..))` + LeakyReLU of reference model.py:131-139,179-184 on y[M,C] (row-major,
  * contiguous).  v = y + bias[row / N] (bias may be NULL: it carries the once-per-block global-feature half of conv7),
