@@ -63,6 +63,14 @@ SIGNATURES = {
     "dgcnn_seg_loss_f32": (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, c_int, _P, _P, c_float, c_float, _P,
                                    _P, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
     "dgcnn_seg_predict_f32": (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_float, c_int64, _P, _P, _P]),
+    "dgcnn_sample_points_workspace_bytes": (c_size_t, [c_int]),
+    "dgcnn_sample_points": (c_int, [_P, c_int, c_int, c_int, C.c_uint64, _P, _P, c_size_t, _P]),
+    "dgcnn_gather_points": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int, _P, c_int64, c_int64, _P, _P]),
+    "dgcnn_tc_planes_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "dgcnn_tc_split_planes_f32": (c_int, [_P, c_int64, c_int64, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "dgcnn_tc_gemm_planes_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "dgcnn_tc_gemm_planes_f32": (c_int, [c_int, _P, c_int, c_int, _P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int,
+                                         _P, c_size_t, _P]),
     "dgcnn_tc_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "dgcnn_tc_gemm_f32": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int, c_int, c_int, c_int, c_int,
                                   _P, c_size_t, _P]),

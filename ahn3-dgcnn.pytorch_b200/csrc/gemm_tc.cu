@@ -7,6 +7,7 @@
 // that the tensor-core kNN and EdgeConv kernels build on.
 #include "common.cuh"
 #include "tc.cuh"
+#include "debug_lab.h"
 
 namespace dg {
 
@@ -137,7 +138,7 @@ struct GemmSmem {
 template <int NS, int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(192, 1)
 tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __restrict__ Bp, float* __restrict__ D,
-               int ldd, int M, int N, int KA, int ka_per_split, size_t split_stride, GemmEpi epi) {
+               int ldd, int M, int N, int KA, int ka_per_split, size_t split_stride, GemmEpi epi, int ns_a = NS, int ns_b = NS) {
   using SM = GemmSmem<NS, BN, STAGES>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -177,14 +178,14 @@ tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __rest
         unsigned char* b_s = a_s + NS * SM::a_plane;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const unsigned char* src = Ap + (static_cast<size_t>(2 * mt + h) * KA + ka) * NS * tc::kUnitBytes;
+          const unsigned char* src = Ap + (static_cast<size_t>(2 * mt + h) * KA + ka) * ns_a * tc::kUnitBytes;
 #pragma unroll
           for (int p = 0; p < NS; ++p)
             tc::bulk_g2s(a_s + p * SM::a_plane + h * tc::kUnitBytes, src + p * tc::kUnitBytes, tc::kUnitBytes, full + s);
         }
 #pragma unroll
         for (int h = 0; h < BN / 64; ++h) {
-          const unsigned char* src = Bp + (static_cast<size_t>(nt * (BN / 64) + h) * KA + ka) * NS * tc::kUnitBytes;
+          const unsigned char* src = Bp + (static_cast<size_t>(nt * (BN / 64) + h) * KA + ka) * ns_b * tc::kUnitBytes;
 #pragma unroll
           for (int p = 0; p < NS; ++p)
             tc::bulk_g2s(b_s + p * SM::b_plane + h * tc::kUnitBytes, src + p * tc::kUnitBytes, tc::kUnitBytes, full + s);
@@ -294,6 +295,137 @@ tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __rest
   if (warp == 1) tc::tmem_dealloc(taddr, BN);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Row-contraction GEMM ("TN", weight gradients):  D[N1, N2] = sum_r A[r, n1] * B[r, n2]  from the SAME split planes that
+// the K-major GEMMs consume (units of 64 rows x 64 columns, 128 B per row).  The contraction index is the unit ROW, i.e.
+// both operands are read MN-major: the 64 columns of a unit are the contiguous M (resp. N) extent, 16 rows are one
+// k16 step (2048 B apart), wider M / N extents are further units `lbo` bytes apart (descriptor fields pinned on the GPU by
+// tools/labs/mn_lab.py and used by ec_tc_bwd_b_kernel).  A weight gradient dW = dY^T X therefore needs NO transposing
+// re-split of dY and X: it reuses the planes made for the data-gradient / forward GEMMs.
+// One 128 x BN output tile per CTA and split (blockIdx.z = contiguous range of 64-row tiles); partial tiles are reduced in
+// a fixed order by splitk_reduce_kernel.  Units beyond an operand's width are left zero in shared memory.
+// ---------------------------------------------------------------------------------------------
+template <int NS, int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+tc_gemm_tn_kernel(const unsigned char* __restrict__ Ap, int KA_a, int ns_a, const unsigned char* __restrict__ Bp, int KA_b, int ns_b,
+                  float* __restrict__ D, int ldd, int N1, int N2, int RT, int rt_per_split, size_t split_stride) {
+  using SM = GemmSmem<NS, BN, STAGES>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * SM::stage);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accfull = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = blockIdx.x, mt = blockIdx.y;
+  const int rt_lo = blockIdx.z * rt_per_split, rt_hi = min(RT, rt_lo + rt_per_split);
+  D += static_cast<size_t>(blockIdx.z) * split_stride;
+  // operand units of this tile that exist (the rest of the stage stays zero)
+  const int a_units = max(0, min(2, KA_a - 2 * mt)), b_units = max(0, min(BN / 64, KA_b - nt * (BN / 64)));
+
+  // zero the stages once: skipped (out-of-range) units must read as zeros
+  for (uint32_t i = threadIdx.x; i < STAGES * SM::stage / 16; i += blockDim.x) reinterpret_cast<uint4*>(tiles)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(full + s, 1);
+      tc::mbar_init(empty + s, 1);
+    }
+    tc::mbar_init(accfull, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, BN);
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t taddr = *tmem_slot;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      const uint32_t bytes = static_cast<uint32_t>(NS * (a_units + b_units)) * tc::kUnitBytes;
+      for (int rt = rt_lo; rt < rt_hi; ++rt) {
+        const int it = rt - rt_lo, s = it % STAGES;
+        tc::mbar_wait(empty + s, ((it / STAGES) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(full + s, bytes);
+        unsigned char* a_s = tiles + s * SM::stage;
+        unsigned char* b_s = a_s + NS * SM::a_plane;
+        for (int h = 0; h < a_units; ++h) {
+          const unsigned char* src = Ap + (static_cast<size_t>(rt) * KA_a + 2 * mt + h) * ns_a * tc::kUnitBytes;
+#pragma unroll
+          for (int p = 0; p < NS; ++p)
+            tc::bulk_g2s(a_s + p * SM::a_plane + h * tc::kUnitBytes, src + p * tc::kUnitBytes, tc::kUnitBytes, full + s);
+        }
+        for (int h = 0; h < b_units; ++h) {
+          const unsigned char* src = Bp + (static_cast<size_t>(rt) * KA_b + nt * (BN / 64) + h) * ns_b * tc::kUnitBytes;
+#pragma unroll
+          for (int p = 0; p < NS; ++p)
+            tc::bulk_g2s(b_s + p * SM::b_plane + h * tc::kUnitBytes, src + p * tc::kUnitBytes, tc::kUnitBytes, full + s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::idesc_bf16(128, BN) | (1u << 15) | (1u << 16);       // A and B MN-major
+      auto desc_mn = [](uint32_t saddr) {      // SWIZZLE_128B, 64-wide MN atoms 8192 B apart, 8-row K groups 1024 B apart
+        const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (((tc::kUnitBytes >> 4) & 0x3FFFu) << 16);
+        const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+        return (static_cast<uint64_t>(hi) << 32) | lo;
+      };
+      uint32_t acc = 0u;
+      for (int rt = rt_lo; rt < rt_hi; ++rt) {
+        const int it = rt - rt_lo, s = it % STAGES;
+        tc::mbar_wait(full + s, (it / STAGES) & 1);
+        tc::fence_after_sync();
+        const uint32_t a_s = tc::smem_u32(tiles + s * SM::stage), b_s = a_s + NS * SM::a_plane;
+        // plane pairs (i, j), i + j <= NS + 1, smallest magnitude first; 4 k16 steps of 16 rows each
+#pragma unroll
+        for (int sum = NS + 1; sum >= 2; --sum) {
+#pragma unroll
+          for (int i = 1; i <= NS; ++i) {
+            const int j = sum - i;
+            if (j < 1 || j > NS) continue;
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16) {
+              tc::mma_bf16(taddr, desc_mn(a_s + (i - 1) * SM::a_plane + k16 * 2048), desc_mn(b_s + (j - 1) * SM::b_plane + k16 * 2048),
+                           idesc, acc);
+              acc = 1u;
+            }
+          }
+        }
+        tc::mma_commit(empty + s);
+      }
+      tc::mma_commit(accfull);
+    }
+  } else {
+    const int quarter = warp & 3;
+    tc::mbar_wait(accfull, 0);
+    tc::fence_after_sync();
+    const int row = mt * 128 + quarter * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
+      const int n0 = nt * BN + c0;
+      if (row < N1 && n0 < N2) {
+        float* dst = D + static_cast<size_t>(row) * ldd + n0;
+        if (n0 + 32 <= N2 && (ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (n0 + i < N2) dst[i] = v[i];
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(taddr, BN);
+}
+
 // D[i] = sum_z P[z][i] in a fixed order (deterministic split-K reduction)
 __global__ void splitk_reduce_kernel(const float* __restrict__ P, size_t split_stride, int splits, float* __restrict__ D,
                                      int ldd, int M, int N) {
@@ -342,21 +474,21 @@ static int splitk_factor(int M, int N, int KA) {
 
 template <int NS, int BN, int STAGES>
 static int launch_gemm(const unsigned char* Ap, const unsigned char* Bp, float* D, int ldd, int M, int N, int KA,
-                       float* partials, cudaStream_t st) {
+                       float* partials, cudaStream_t st, int ns_a = NS, int ns_b = NS) {
   using SM = GemmSmem<NS, BN, STAGES>;
   auto kern = tc_gemm_kernel<NS, BN, STAGES, EPI_STORE>;
   DG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SM::bytes)));
   const int splits = splitk_factor(M, N, KA);
   dim3 grid((N + BN - 1) / BN, (M + 127) / 128, splits);
   if (splits == 1) {
-    kern<<<grid, 192, SM::bytes, st>>>(Ap, Bp, D, ldd, M, N, KA, KA, 0, GemmEpi{});
+    kern<<<grid, 192, SM::bytes, st>>>(Ap, Bp, D, ldd, M, N, KA, KA, 0, GemmEpi{}, ns_a, ns_b);
     DG_CUDA(cudaGetLastError());
     return DGCNN_OK;
   }
   const int per = (KA + splits - 1) / splits;
   const size_t stride = static_cast<size_t>(M) * N;
   grid.z = (KA + per - 1) / per;
-  kern<<<grid, 192, SM::bytes, st>>>(Ap, Bp, partials, N, M, N, KA, per, stride, GemmEpi{});
+  kern<<<grid, 192, SM::bytes, st>>>(Ap, Bp, partials, N, M, N, KA, per, stride, GemmEpi{}, ns_a, ns_b);
   DG_CUDA(cudaGetLastError());
   const size_t total = stride;
   splitk_reduce_kernel<<<static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 8)), 256, 0, st>>>(partials, stride, grid.z, D,
@@ -402,6 +534,93 @@ extern "C" int dgcnn_tc_gemm_f32(const float* A, int64_t a_sr, int64_t a_sc, con
   if (Np % 256 == 0 && splitk_factor(M, N, KA) == 1 && static_cast<long long>((M + 127) / 128) * (Np / 256) >= 2 * 148)
     return launch_gemm<2, 256, 2>(Ap, Bp, D, ldd, M, N, KA, partials, st);
   return launch_gemm<2, 128, 3>(Ap, Bp, D, ldd, M, N, KA, partials, st);
+}
+
+
+namespace dg {
+static int tn_splits(int N1, int N2, int BN, int RT) {
+  const int tiles = ((N1 + 127) / 128) * ((N2 + BN - 1) / BN);
+  return std::max(1, std::min(RT, (2 * 148 + tiles - 1) / tiles));
+}
+template <int NS, int BN, int STAGES>
+static int launch_gemm_tn(const unsigned char* Ap, int KA_a, int ns_a, const unsigned char* Bp, int KA_b, int ns_b, float* D, int ldd,
+                          int N1, int N2, int RT, float* partials, cudaStream_t st) {
+  using SM = GemmSmem<NS, BN, STAGES>;
+  auto kern = tc_gemm_tn_kernel<NS, BN, STAGES>;
+  DG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SM::bytes)));
+  const int splits = tn_splits(N1, N2, BN, RT);
+  const int per = (RT + splits - 1) / splits;
+  dim3 grid((N2 + BN - 1) / BN, (N1 + 127) / 128, (RT + per - 1) / per);
+  if (grid.z == 1) {
+    kern<<<grid, 192, SM::bytes, st>>>(Ap, KA_a, ns_a, Bp, KA_b, ns_b, D, ldd, N1, N2, RT, per, 0);
+    DG_CUDA(cudaGetLastError());
+    return DGCNN_OK;
+  }
+  const size_t stride = static_cast<size_t>(N1) * N2;
+  kern<<<grid, 192, SM::bytes, st>>>(Ap, KA_a, ns_a, Bp, KA_b, ns_b, partials, N2, N1, N2, RT, per, stride);
+  DG_CUDA(cudaGetLastError());
+  splitk_reduce_kernel<<<static_cast<int>(std::min<size_t>((stride + 255) / 256, 148 * 8)), 256, 0, st>>>(partials, stride, grid.z, D, ldd,
+                                                                                                      N1, N2);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}
+}  // namespace dg
+
+// ---- plane-level interface: split once, multiply many times ------------------------------------------------------
+extern "C" size_t dgcnn_tc_planes_bytes(int R, int K, int nsplit) {
+  if (R <= 0 || K <= 0 || nsplit < 2 || nsplit > 3) return 0;
+  return planes_bytes((R + 127) / 128 * 128, (K + 63) / 64, nsplit) + 1024;
+}
+
+extern "C" int dgcnn_tc_split_planes_f32(const float* X, int64_t row_stride, int64_t col_stride, int R, int K, int nsplit,
+                                         void* planes, size_t planes_bytes_avail, void* stream) {
+  DG_REQUIRE(X && planes, DGCNN_E_INVALID, "tc_split_planes: null pointer");
+  DG_REQUIRE(R > 0 && K > 0 && (nsplit == 2 || nsplit == 3), DGCNN_E_INVALID, "tc_split_planes: bad arguments");
+  DG_REQUIRE((reinterpret_cast<uintptr_t>(planes) & 127) == 0, DGCNN_E_INVALID, "tc_split_planes: planes must be 128-byte aligned");
+  DG_REQUIRE(planes_bytes_avail >= dgcnn_tc_planes_bytes(R, K, nsplit) - 1024, DGCNN_E_WORKSPACE, "tc_split_planes: planes buffer too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int KA = (K + 63) / 64, Rp = (R + 127) / 128 * 128;
+  unsigned char* out = static_cast<unsigned char*>(planes);
+  return nsplit == 3 ? launch_split<3>(X, row_stride, col_stride, R, K, Rp, KA, out, st)
+                     : launch_split<2>(X, row_stride, col_stride, R, K, Rp, KA, out, st);
+}
+
+extern "C" size_t dgcnn_tc_gemm_planes_workspace_bytes(int mode, int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (mode == 0) return static_cast<size_t>(splitk_factor(M, N, (K + 63) / 64)) * M * N * sizeof(float) + 1024;
+  const int RT = (K + 63) / 64;
+  return static_cast<size_t>(tn_splits(M, N, 128, RT)) * M * N * sizeof(float) + 1024;
+}
+
+extern "C" int dgcnn_tc_gemm_planes_f32(int mode, const void* a_planes, int a_cols, int a_nsplit, const void* b_planes, int b_cols,
+                                        int b_nsplit, int nsplit, float* D, int ldd, int M, int N, int K, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  DG_REQUIRE(a_planes && b_planes && D && workspace, DGCNN_E_INVALID, "tc_gemm_planes: null pointer");
+  DG_REQUIRE(M > 0 && N > 0 && K > 0 && ldd >= N, DGCNN_E_INVALID, "tc_gemm_planes: bad shape M=%d N=%d K=%d ldd=%d", M, N, K, ldd);
+  DG_REQUIRE((nsplit == 2 || nsplit == 3) && a_nsplit >= nsplit && b_nsplit >= nsplit && a_nsplit <= 3 && b_nsplit <= 3, DGCNN_E_INVALID,
+             "tc_gemm_planes: nsplit=%d must not exceed the stored planes (%d, %d)", nsplit, a_nsplit, b_nsplit);
+  DG_REQUIRE(((reinterpret_cast<uintptr_t>(a_planes) | reinterpret_cast<uintptr_t>(b_planes)) & 127) == 0, DGCNN_E_INVALID,
+             "tc_gemm_planes: planes must be 128-byte aligned");
+  DG_REQUIRE(workspace_bytes >= dgcnn_tc_gemm_planes_workspace_bytes(mode, M, N, K), DGCNN_E_WORKSPACE, "tc_gemm_planes: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned char* Ap = static_cast<const unsigned char*>(a_planes);
+  const unsigned char* Bp = static_cast<const unsigned char*>(b_planes);
+  float* partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  if (mode == 0) {
+    // D[M,N] = A[M,K] B[N,K]^T: planes of A over [M, K] (a_cols == K), of B over [N, K] (b_cols == K)
+    DG_REQUIRE(a_cols == K && b_cols == K, DGCNN_E_INVALID, "tc_gemm_planes: mode 0 needs a_cols == b_cols == K");
+    const int KA = (K + 63) / 64, Np = (N + 127) / 128 * 128;
+    if (nsplit == 3) return launch_gemm<3, 128, 2>(Ap, Bp, D, ldd, M, N, KA, partials, st, a_nsplit, b_nsplit);
+    if (Np % 256 == 0 && splitk_factor(M, N, KA) == 1 && static_cast<long long>((M + 127) / 128) * (Np / 256) >= 2 * 148)
+      return launch_gemm<2, 256, 2>(Ap, Bp, D, ldd, M, N, KA, partials, st, a_nsplit, b_nsplit);
+    return launch_gemm<2, 128, 3>(Ap, Bp, D, ldd, M, N, KA, partials, st, a_nsplit, b_nsplit);
+  }
+  DG_REQUIRE(mode == 1, DGCNN_E_INVALID, "tc_gemm_planes: mode must be 0 (A B^T) or 1 (A^T B)");
+  // D[M,N] = sum_r A[r, m] B[r, n]: planes of A over [K rows, a_cols = M], of B over [K rows, b_cols = N]
+  DG_REQUIRE(a_cols == M && b_cols == N, DGCNN_E_INVALID, "tc_gemm_planes: mode 1 needs a_cols == M and b_cols == N");
+  const int RT = (K + 63) / 64, KA_a = (M + 63) / 64, KA_b = (N + 63) / 64;
+  if (nsplit == 3) return launch_gemm_tn<3, 128, 2>(Ap, KA_a, a_nsplit, Bp, KA_b, b_nsplit, D, ldd, M, N, RT, partials, st);
+  return launch_gemm_tn<2, 128, 3>(Ap, KA_a, a_nsplit, Bp, KA_b, b_nsplit, D, ldd, M, N, RT, partials, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -541,7 +760,7 @@ extern "C" int dgcnn_tc_gemm_bn_lrelu_segmax_f32(const float* A, int64_t a_sr, i
   auto kern = tc_gemm_kernel<3, 128, 2, EPI_COLSTATS>;
   DG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SM::bytes)));
   GemmEpi epi{seg_len, stats, gext, gamma};
-  kern<<<dim3(Np / 128, num_mt, 1), 192, SM::bytes, st>>>(Ap, Bp, nullptr, 0, M, N, KA, KA, 0, epi);
+  kern<<<dim3(Np / 128, num_mt, 1), 192, SM::bytes, st>>>(Ap, Bp, nullptr, 0, M, N, KA, KA, 0, epi, 3, 3);
   DG_CUDA(cudaGetLastError());
   colstats_bn_kernel<<<(N + 31) / 32, 256, 0, st>>>(stats, num_mt, N, static_cast<double>(M), gamma, eps, momentum, use_batch_stats,
                                                       running_mean, running_var, mean, rstd);

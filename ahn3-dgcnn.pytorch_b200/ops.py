@@ -237,23 +237,63 @@ def tc_gemm(a: torch.Tensor, b: torch.Tensor, nsplit: int = 3) -> torch.Tensor:
     return d
 
 
+class Planes:
+    """An FP32 matrix [R, K] in the tensor-core operand format (nsplit bf16 planes, see include/dgcnn_b200.h)."""
+
+    __slots__ = ("buf", "R", "K", "nsplit")
+
+    def __init__(self, x: torch.Tensor, nsplit: int):
+        lib = _lib.load()
+        self.R, self.K = x.shape
+        self.nsplit = nsplit
+        nbytes = lib.dgcnn_tc_planes_bytes(self.R, self.K, nsplit)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _call("dgcnn_tc_split_planes_f32", x.device, _ptr(x), x.stride(0), x.stride(1), self.R, self.K, nsplit, _ptr(self.buf), nbytes)
+
+
+def gemm_planes(a: Planes, b: Planes, nsplit: int, transposed: bool = False) -> torch.Tensor:
+    """transposed=False: D[a.R, b.R] = A B^T (contraction over the K columns).
+    transposed=True:  D[a.K, b.K] = A^T B  (contraction over the rows: weight gradients, no re-split)."""
+    lib = _lib.load()
+    dev = a.buf.device
+    if transposed:
+        assert a.R == b.R
+        M, N, K, mode = a.K, b.K, a.R, 1
+    else:
+        assert a.K == b.K
+        M, N, K, mode = a.R, b.R, a.K, 0
+    ws = _workspace(dev, lib.dgcnn_tc_gemm_planes_workspace_bytes(mode, M, N, K))
+    d = torch.empty(M, N, dtype=torch.float32, device=dev)
+    _call("dgcnn_tc_gemm_planes_f32", dev, mode, _ptr(a.buf), a.K, a.nsplit, _ptr(b.buf), b.K, b.nsplit, nsplit, _ptr(d), N, M, N, K,
+          _ptr(ws), ws.numel())
+    return d
+
+
 class TcLinear(torch.autograd.Function):
-    """y = x @ w^T (x [M,K], w [N,K]) with all three GEMMs (y, dx, dw) on the tensor cores."""
+    """y = x @ w^T (x [M,K], w [N,K]) with all three GEMMs (y, dx, dw) on the tensor cores.
+
+    The operands are split into bf16 planes once: x for the forward (3 planes; the first GRAD_NSPLIT are reused by the
+    weight gradient, which contracts over the ROWS of the same planes), dy once for both gradient GEMMs."""
 
     @staticmethod
     def forward(ctx, x, w):
-        ctx.save_for_backward(x, w)
-        return tc_gemm(x, w)
+        xp = Planes(x, 3)
+        ctx.xp = xp
+        ctx.save_for_backward(w)
+        return gemm_planes(xp, Planes(w, 3), 3)
 
     @staticmethod
     def backward(ctx, dy):
-        x, w = ctx.saved_tensors
+        (w,) = ctx.saved_tensors
+        xp = ctx.xp
         dx = dw = None
         # gradient GEMMs: GRAD_NSPLIT planes (2: relative error 2^-17, two orders below the gradient noise floor; 3: FP32-accurate)
+        dyp = Planes(dy, GRAD_NSPLIT)
         if ctx.needs_input_grad[0]:
-            dx = tc_gemm(dy, w.t(), nsplit=GRAD_NSPLIT)       # [M,K] = dy[M,N] @ w[N,K]
+            dx = gemm_planes(dyp, Planes(w.t(), GRAD_NSPLIT), GRAD_NSPLIT)           # [M,K] = dy[M,N] @ w[N,K]
         if ctx.needs_input_grad[1]:
-            dw = tc_gemm(dy.t(), x.t(), nsplit=GRAD_NSPLIT)   # [N,K] = dy^T[N,M] @ x[M,K]   (split-K over the points)
+            dw = gemm_planes(dyp, xp, GRAD_NSPLIT, transposed=True)                    # [N,K] = dy^T[N,M] @ x[M,K]
+        ctx.xp = None
         return dx, dw
 
 
@@ -308,7 +348,8 @@ class GlobalFeature(torch.autograd.Function):
         dev = feat.device
         # dense parts on the tensor cores: dfeat = -feat (W^T diag(kappa) W) - b' W  (the sign is folded into the small matrix)
         gram_neg = tc_gemm((w * (-kappa)[:, None]).t(), w.t(), nsplit=GRAD_NSPLIT)      # [K,K] = -W^T diag(kappa) W (symmetric)
-        dfeat = tc_gemm(feat, gram_neg, nsplit=GRAD_NSPLIT)
+        featp = Planes(feat, GRAD_NSPLIT)                                                # split once for both feature GEMMs
+        dfeat = gemm_planes(featp, Planes(gram_neg, GRAD_NSPLIT), GRAD_NSPLIT)
         cvec = torch.empty(K, dtype=torch.float32, device=dev)
         _call("dgcnn_vecmat_f32", dev, _ptr(bprime), _ptr(w), w.stride(0), E, K, -1.0, _ptr(cvec))
         dfeat.add_(cvec)
@@ -318,7 +359,7 @@ class GlobalFeature(torch.autograd.Function):
         _call("dgcnn_global_feature_bwd_sparse_f32", dev, _ptr(feat), feat.stride(0), _ptr(w), w.stride(0), _ptr(nstar), _ptr(gdz_c),
               _ptr(a.contiguous()), B, E, K, _ptr(dfeat), dfeat.stride(0), _ptr(t1))
         # dW = a dz^T feat - b' colsum(feat)^T - diag(kappa) W (feat^T feat)
-        f2 = tc_gemm(feat.t(), feat.t(), nsplit=GRAD_NSPLIT)                    # [K,K] = feat^T feat (split-K over the points)
+        f2 = gemm_planes(featp, featp, GRAD_NSPLIT, transposed=True)            # [K,K] = feat^T feat (row contraction, split over the points)
         wf2 = tc_gemm(w, f2, nsplit=GRAD_NSPLIT)                                # f2 is symmetric: W f2 = W f2^T
         dw = a[:, None] * t1 - bprime[:, None] * rows_colsum(feat, M) - kappa[:, None] * wf2
         return dfeat, dw, s2, s1, None, None, None, None
@@ -538,12 +579,13 @@ class EdgeConvTrain(torch.autograd.Function):
         X = rows[:, :Cn]
         wa1, wa2 = wa[:, :Cn], wa[:, Cn:]
         dx = None
+        rsp = Planes(rs, GRAD_NSPLIT)                                   # split once: K-major for dX, row-contraction for dWa
         if ctx.needs_input_grad[0]:
             wcat = torch.cat((wa1, wa2 - wa1), dim=0)                   # [128, C]
-            dx = tc_gemm(rs, wcat.t(), nsplit=GRAD_NSPLIT)
+            dx = gemm_planes(rsp, Planes(wcat.t(), GRAD_NSPLIT), GRAD_NSPLIT)
             if dx.shape != ctx.x_shape:                                 # rows padded to a multiple of 4 channels
                 dx = torch.nn.functional.pad(dx, (0, ctx.x_shape[1] - dx.shape[1]))
-        G = tc_gemm(rs.t(), X.t(), nsplit=GRAD_NSPLIT)                            # [128, C]
+        G = gemm_planes(rsp, Planes(X, GRAD_NSPLIT), GRAD_NSPLIT, transposed=True)        # [128, C] = [r|s]^T X
         dwa = torch.cat((G[:COUT] - G[COUT:], G[COUT:]), dim=1)
         # returns: x, idx, meta, w_a, gamma_a, beta_a, w_b, gamma_b, beta_b, bn_a, bn_b
         if two:

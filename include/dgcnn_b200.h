@@ -168,6 +168,24 @@ int dgcnn_tc_gemm_f32(const float* A, int64_t a_row_stride, int64_t a_col_stride
                       float* D, int ldd, int M, int N, int K, int nsplit,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- plane-level form: split an operand ONCE, multiply it many times --------------------------------------------------
+ * The tensor-core operand format ("split planes", csrc/tc.cuh): an FP32 matrix X[R,K] as nsplit bf16 planes x = x1 + x2
+ * (+ x3) in units of 64 rows x 64 columns (128 B per row, SWIZZLE_128B).  dgcnn_tc_split_planes_f32 writes them (buffer of
+ * dgcnn_tc_planes_bytes(R,K,nsplit) bytes, 128-byte aligned).  dgcnn_tc_gemm_planes_f32 multiplies two such operands:
+ *   mode 0   D[M,N] = A[M,K] B[N,K]^T      planes of A over [M,K] (a_cols = K), of B over [N,K] (b_cols = K)
+ *   mode 1   D[M,N] = sum_r A[r,m] B[r,n]  planes of A over [K rows, a_cols = M], of B over [K rows, b_cols = N]: the
+ *            contraction runs over the unit ROWS (MN-major operand descriptors), so a weight gradient dW = dY^T X reuses
+ *            the planes of dY (made for the data gradient) and of X (made for the forward) — no transposing re-split.
+ * a_nsplit / b_nsplit = planes stored per operand (2 or 3), nsplit <= both = planes used.  The layer sequence of a Linear:
+ * forward split(X,3) -> mode 0; backward split(dY,2) -> mode 0 with split(W^T,2) for dX, mode 1 with X's planes for dW.  */
+size_t dgcnn_tc_planes_bytes(int R, int K, int nsplit);
+int dgcnn_tc_split_planes_f32(const float* X, int64_t row_stride, int64_t col_stride, int R, int K, int nsplit,
+                              void* planes, size_t planes_bytes, void* stream);
+size_t dgcnn_tc_gemm_planes_workspace_bytes(int mode, int M, int N, int K);
+int dgcnn_tc_gemm_planes_f32(int mode, const void* a_planes, int a_cols, int a_nsplit, const void* b_planes, int b_cols,
+                             int b_nsplit, int nsplit, float* D, int ldd, int M, int N, int K,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- conv6 + bn6 + LeakyReLU + global max over the points (model.py:172-175) without materialising [B,emb,N] -------
  * g[segments,N] = max over the `seg_len` rows of each segment of LeakyReLU(BN(A B^T)).  The GEMM epilogue only emits
  * per-row-tile column sums / sums of squares and per-segment column max / min (with the attaining row); BN-affine and
@@ -236,6 +254,21 @@ int dgcnn_seg_loss_f32(const float* logits, int64_t stride_b, int64_t stride_c, 
  * the reference's tensor; conf (may be NULL): float [B*N] max probability.                                          */
 int dgcnn_seg_predict_f32(const float* logits, int64_t stride_b, int64_t stride_c, int64_t stride_n, int B, int C, int N,
                           float min_conf, int64_t unclassified, int64_t* pred, float* conf, void* stream);
+
+/* ---- input pipeline on device (data.py:107-143 sample_points, data.py:169-182 collate_pcs, train.py:176) -------------
+ * dgcnn_sample_points: indices of n_samples points of one tile drawn WITHOUT replacement with the reference's class
+ * weights (w_c = (tot - count_c) / sum_c (tot - count_c); uniform when that is 0/0), as an exponential race
+ * (key = -log(u)/w, the n smallest keys; counter-based u from `seed` and the point index, so the draw is a pure function
+ * of labels and seed).  labels: int32 [Nt] class ids (0..num_classes-1; other values are never drawn).  out_idx: int32
+ * [n_samples]: the points whose key is below the n-th smallest in index order, then the one(s) at it.  Needs n_samples <= number of points with non-zero weight.
+ * dgcnn_gather_points: x[f*x_stride_f + j*x_stride_n] = (float) points[idx[j]*ld_points + f] for f < F — the collate and
+ * the permute(0,2,1).float() in one pass, straight into a [F, n] slot of the model's input batch — and y[j] =
+ * labels[idx[j]] (int64, may be NULL).  points: float64 (points_are_f64 != 0, what np.load delivers) or float32.      */
+size_t dgcnn_sample_points_workspace_bytes(int Nt);
+int dgcnn_sample_points(const int32_t* labels, int Nt, int num_classes, int n_samples, uint64_t seed, int32_t* out_idx,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int dgcnn_gather_points(const void* points, int points_are_f64, int ld_points, const int32_t* labels, const int32_t* idx,
+                        int n, int F, float* x, int64_t x_stride_f, int64_t x_stride_n, int64_t* y, void* stream);
 
 #ifdef __cplusplus
 }

@@ -98,3 +98,33 @@ def create_train_mask(labels: np.ndarray, classes, tot_samples: int, rs: np.rand
             training_idxs = rs.choice(this_label_idxs, n_samples, replace=False)
             train_mask[training_idxs] = 1
     return train_mask
+
+
+def sample_points(labels: np.ndarray, classes, tot_samples: int, rs: np.random.RandomState) -> np.ndarray:
+    """data.py:107-143 for one tile: class-weighted sampling of `tot_samples` point indices without replacement."""
+    label_counts = np.zeros(len(classes))
+    for i in range(len(classes)):
+        label_counts[i] = np.sum(labels == classes[i])
+    tot = sum(label_counts)
+    shuf_nums = np.array([tot - i for i in label_counts])
+    tot = sum(shuf_nums)
+    weights = shuf_nums / tot
+    weights /= weights.sum()
+    point_weights = weights[labels.astype(np.int64)]            # the reference fills this with a Python loop over the points
+    point_weights = point_weights / point_weights.sum()
+    if np.isnan(sum(point_weights)):
+        point_weights = np.full(len(labels), 1.0 / len(labels))
+    return rs.choice(np.arange(len(labels)), tot_samples, p=point_weights, replace=False)
+
+
+def collate_pcs(data, rs: np.random.RandomState):
+    """data.py:169-182: every sample is re-drawn to the smallest sample size of the batch; float64 tensors out."""
+    points, labels, idxs = zip(*data)
+    min_num_points = min(p.shape[0] for p in points)
+    batch_points = np.zeros((len(points), min_num_points, points[0].shape[1]))
+    batch_labels = np.zeros((len(points), min_num_points))
+    for i in range(len(points)):
+        sub = rs.choice(range(points[i].shape[0]), min_num_points, replace=False)
+        batch_points[i, :, :] = points[i][sub, :]
+        batch_labels[i, :] = labels[i][sub]
+    return torch.tensor(batch_points), torch.tensor(batch_labels), torch.tensor(idxs)

@@ -57,7 +57,7 @@ def run(rows, B, Cn, N, k, tag, exact=True):
 
 torch.manual_seed(0)
 B, N, k = 8, 7000, 30
-x, _ = bench.make_batch(0, B)
+x, _, _ = bench.make_batch(0, B)
 rows4 = ops.pack_rows(x.cuda())
 run(rows4, B, 4, N, k, "cfg2 layer 1 (real-like xyz+agl)")
 run(torch.randn(B * N, 64, device="cuda"), B, 64, N, k, "randn64")
