@@ -539,8 +539,9 @@ extern "C" int dgcnn_tc_gemm_f32(const float* A, int64_t a_sr, int64_t a_sc, con
 
 namespace dg {
 static int tn_splits(int N1, int N2, int BN, int RT) {
+  // one wave of CTAs, at least 4 row tiles each: every split costs a partial tile in HBM and a pass of the reduce kernel
   const int tiles = ((N1 + 127) / 128) * ((N2 + BN - 1) / BN);
-  return std::max(1, std::min(RT, (2 * 148 + tiles - 1) / tiles));
+  return std::max(1, std::min((RT + 3) / 4, (148 + tiles - 1) / tiles));
 }
 template <int NS, int BN, int STAGES>
 static int launch_gemm_tn(const unsigned char* Ap, int KA_a, int ns_a, const unsigned char* Bp, int KA_b, int ns_b, float* D, int ldd,

@@ -194,9 +194,21 @@ __global__ void __launch_bounds__(kRbThreads) rows_colsum_partial_kernel(const f
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
   const float* base = x + static_cast<size_t>(seg) * N * C;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = r0 + rl; r < r1 && rl < RL; r += RL) {
-    const float4 v = ld4(base + static_cast<size_t>(r) * C + 4 * cg);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  if (rl < RL) {
+    // four independent rows in flight per thread (a single dependent chain of loads made this pass latency-bound)
+    int r = r0 + rl;
+    for (; r + 3 * RL < r1; r += 4 * RL) {
+      const float4 v0 = ld4(base + static_cast<size_t>(r) * C + 4 * cg);
+      const float4 v1 = ld4(base + static_cast<size_t>(r + RL) * C + 4 * cg);
+      const float4 v2 = ld4(base + static_cast<size_t>(r + 2 * RL) * C + 4 * cg);
+      const float4 v3 = ld4(base + static_cast<size_t>(r + 3 * RL) * C + 4 * cg);
+      s.x += (v0.x + v1.x) + (v2.x + v3.x); s.y += (v0.y + v1.y) + (v2.y + v3.y);
+      s.z += (v0.z + v1.z) + (v2.z + v3.z); s.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; r < r1; r += RL) {
+      const float4 v = ld4(base + static_cast<size_t>(r) * C + 4 * cg);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
   }
   red[threadIdx.x] = s;
   __syncthreads();

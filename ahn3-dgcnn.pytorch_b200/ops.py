@@ -457,6 +457,16 @@ def _v_scratch(B: int, Cn: int, N: int, dev) -> Optional[torch.Tensor]:
     return torch.empty(B * N, COUT, dtype=torch.float32, device=dev) if Cn == COUT else None
 
 
+def _use_lin(Cn: int, w_b) -> bool:
+    """Single-conv block on 64-channel features with the default kernel family: no per-edge GEMM (csrc/edgeconv_lin.cu)."""
+    return w_b is None and Cn == COUT and EDGECONV_IMPL == 0
+
+
+def _lin_weight(wa: torch.Tensor, Cn: int) -> torch.Tensor:
+    """[Wa1 ; Wa2 - Wa1] ([128, C]): X @ this^T = [U | V] with y[(i,j)] = U_j + V_i."""
+    return torch.cat((wa[:, :Cn], wa[:, Cn:] - wa[:, :Cn]), dim=0)
+
+
 def eval_affine(gamma: torch.Tensor, beta: torch.Tensor, bn: BNState) -> torch.Tensor:
     """float[192] = running_mean | gamma/sqrt(running_var+eps) | beta."""
     return torch.cat((bn.running_mean, gamma * torch.rsqrt(bn.running_var + bn.eps), beta)).float().contiguous()
@@ -470,6 +480,19 @@ def edgeconv_eval(rows: torch.Tensor, idx: torch.Tensor, B: int, Cn: int, N: int
     rows, ld = _rows_view(rows)
     out = torch.empty(B * N, COUT, dtype=torch.float32, device=rows.device)
     wa = w_a.detach().reshape(COUT, -1).contiguous()
+    if _use_lin(Cn, w_b):
+        # single conv, 64 channels: y = U_j + V_i from ONE point-level GEMM, then a gather pass for the extrema over k
+        M, dev = B * N, rows.device
+        uv = tc_gemm(rows[:, :Cn], _lin_weight(wa, Cn))
+        ymax, ymin = torch.empty(M, COUT, dtype=torch.float32, device=dev), torch.empty(M, COUT, dtype=torch.float32, device=dev)
+        amax, amin = torch.empty(M, COUT, dtype=torch.uint8, device=dev), torch.empty(M, COUT, dtype=torch.uint8, device=dev)
+        a = _args(rows, ld, idx, B, Cn, N, k, wa, None, None, COUT)
+        _call("dgcnn_edgeconv_lin_extrema", dev, C.byref(a), _ptr(uv), uv.stride(0), _ptr(uv[:, COUT:]), uv.stride(0), _ptr(None),
+              _ptr(ymax), _ptr(ymin), _ptr(amax), _ptr(amin))
+        ysel, arg = torch.empty_like(ymax), torch.empty_like(amax)
+        _call("dgcnn_edgeconv_select", dev, M, _ptr(ymax), _ptr(ymin), _ptr(amax), _ptr(amin), _ptr(aff_a), _ptr(out), COUT,
+              _ptr(ysel), _ptr(arg))
+        return out
     wb = None if w_b is None else w_b.detach().reshape(COUT, COUT).contiguous()
     vs = _v_scratch(B, Cn, N, rows.device)
     a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, out, COUT, vs)
@@ -496,7 +519,8 @@ class EdgeConvTrain(torch.autograd.Function):
         partials, _ = _partials(dev)
 
         f32 = dict(dtype=torch.float32, device=dev)
-        y_a = torch.empty(E, COUT, **f32)
+        lin = _use_lin(Cn, w_b)
+        y_a = None if lin else torch.empty(E, COUT, **f32)
         ymax = torch.empty(M, COUT, **f32)
         ymin = torch.empty(M, COUT, **f32)
         amax = torch.empty(M, COUT, dtype=torch.uint8, device=dev)
@@ -505,11 +529,18 @@ class EdgeConvTrain(torch.autograd.Function):
         ysel = torch.empty(M, COUT, **f32)
         arg = torch.empty(M, COUT, dtype=torch.uint8, device=dev)
         stat_a = torch.empty(2 + 3, COUT, **f32)     # mean, rstd, affine(mean|scale|beta)
-        vs = _v_scratch(B, Cn, N, dev)
+        vs = None if lin else _v_scratch(B, Cn, N, dev)
         a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, None, COUT, vs)
 
-        _call("dgcnn_edgeconv_conv_a_train", dev, C.byref(a), _ptr(y_a), _ptr(partials), _ptr(ymax), _ptr(ymin),
-                                                   _ptr(amax), _ptr(amin))
+        uv = None
+        if lin:
+            # y = U_j + V_i: one point-level GEMM + a gather pass (extrema over k, batch sums); nothing per-edge in HBM
+            uv = tc_gemm(rows[:, :Cn], _lin_weight(wa, Cn))
+            _call("dgcnn_edgeconv_lin_extrema", dev, C.byref(a), _ptr(uv), uv.stride(0), _ptr(uv[:, COUT:]), uv.stride(0), _ptr(partials),
+                  _ptr(ymax), _ptr(ymin), _ptr(amax), _ptr(amin))
+        else:
+            _call("dgcnn_edgeconv_conv_a_train", dev, C.byref(a), _ptr(y_a), _ptr(partials), _ptr(ymax), _ptr(ymin),
+                                                       _ptr(amax), _ptr(amin))
         _call("dgcnn_bn_finalize", dev, _ptr(partials), COUT, float(E), _ptr(gamma_a.detach()), _ptr(beta_a.detach()),
                                          bn_a.eps, bn_a.momentum, _ptr(bn_a.running_mean), _ptr(bn_a.running_var),
                                          _ptr(stat_a[0]), _ptr(stat_a[1]), _ptr(stat_a[2:]))
@@ -526,8 +557,9 @@ class EdgeConvTrain(torch.autograd.Function):
                                              _ptr(out), COUT, _ptr(ysel), _ptr(arg))
         ctx.meta = meta
         ctx.two = two
+        ctx.lin = lin
         ctx.save_for_backward(rows, idx, wa, wb if two else wa, gamma_a.detach(), gamma_b.detach() if two else gamma_a.detach(),
-                              y_a, stat_a, stat_b if two else stat_a, ysel, arg)
+                              uv if lin else y_a, stat_a, stat_b if two else stat_a, ysel, arg)
         ctx.x_shape = tuple(x.shape)
         ctx.ld = ld
         return out
@@ -571,8 +603,13 @@ class EdgeConvTrain(torch.autograd.Function):
             dz_a, coef_a, dga = None, coef_l, dgl
         rs = torch.zeros(M, 2 * COUT, **f32)            # [ r | s ]: scatter target and per-point sums, one GEMM operand
         r, s = rs[:, :COUT], rs[:, COUT:]
-        _call("dgcnn_edgeconv_bwd_a", dev, C.byref(a), _ptr(y_a), _ptr(dz_a), _ptr(g), _ptr(arg), _ptr(coef_a),
-              _ptr(s), _ptr(r), 2 * COUT)
+        if ctx.lin:
+            uv = y_a                                    # (saved in its place) [U | V]
+            _call("dgcnn_edgeconv_bwd_a_lin", dev, C.byref(a), _ptr(uv), uv.stride(0), _ptr(uv[:, COUT:]), uv.stride(0), _ptr(g), _ptr(arg),
+                  _ptr(coef_a), _ptr(s), _ptr(r), 2 * COUT)
+        else:
+            _call("dgcnn_edgeconv_bwd_a", dev, C.byref(a), _ptr(y_a), _ptr(dz_a), _ptr(g), _ptr(arg), _ptr(coef_a),
+                  _ptr(s), _ptr(r), 2 * COUT)
         # point-level GEMMs on the tensor cores (bf16x2 split: gradient path):
         #   dX  = r Wa1 + s (Wa2 - Wa1)            = [r|s] @ [Wa1 ; Wa2-Wa1]
         #   dWa = [(r - s)^T X | s^T X]            from G = [r|s]^T X  (contraction over the points, split-K)

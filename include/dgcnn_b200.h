@@ -157,6 +157,21 @@ int dgcnn_edgeconv_bwd_a(const dgcnn_edgeconv_args* a, const float* y_a, const f
                          const float* g, const uint8_t* arg, const float* coef_a,
                          float* s, float* r, int ld_rs, void* stream);
 
+/* ---- single-convolution block without a per-edge GEMM (conv5 + bn5 + LeakyReLU + max over k, model.py:128-130,161-163) ----
+ * y[(i,j)] = W [x_j - x_i ; x_i] = U_j + V_i with U = X Wa1^T and V = X (Wa2 - Wa1)^T (ONE point-level GEMM by the caller,
+ * X [Wa1 ; Wa2 - Wa1]^T), and max_k LReLU(BN(y)) = LReLU(BN(V_i + max_j U_j)) (min for a negative BN scale).
+ * dgcnn_edgeconv_lin_extrema: one gather pass over U — per point and channel the extrema of fl(U_j + V_i) over the k
+ * neighbours (ymax, ymin float[B*N,64], slots amax, amin uint8) and the batch sums of y, y^2 (partials, as
+ * dgcnn_edgeconv_conv_a_train writes them; NULL in inference).  Follow with dgcnn_bn_finalize (training) and
+ * dgcnn_edgeconv_select.  dgcnn_edgeconv_bwd_a_lin is dgcnn_edgeconv_bwd_a for this block with y recomputed as
+ * U_j + V_i.  No per-edge tensor exists in HBM in either direction.  Only `idx`, B, N, k of the args are used.
+ * Intended for the 64-channel feature-space block (O(1) features); rows of U, V: >= 64 floats, 16-byte aligned.       */
+int dgcnn_edgeconv_lin_extrema(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
+                               double* partials, float* ymax, float* ymin, uint8_t* amax, uint8_t* amin, void* stream);
+int dgcnn_edgeconv_bwd_a_lin(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
+                             const float* g, const uint8_t* arg, const float* coef_a, float* s, float* r, int ld_rs,
+                             void* stream);
+
 /* ---- FP32-accurate tensor-core GEMM (tcgen05, bf16 split planes):  D[M,N] = A[M,K] * B[N,K]^T ---------------
  * A and B are FP32 with arbitrary element strides (row stride, column stride), so transposed operands need no
  * copy.  nsplit = 3: six bf16 MMAs per product, relative error ~2^-24 ("FP32-accurate", the dense GEMMs of the
