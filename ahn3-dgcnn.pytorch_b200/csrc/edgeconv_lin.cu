@@ -15,11 +15,15 @@
 
 namespace dg {
 
-// thread = (point, 4 channels): 16 points per CTA pass; persistent CTAs; per-CTA FP64 partials (sum, sum of squares)
+// thread = (point, 4 channels): 16 points per CTA pass; persistent CTAs; per-CTA FP64 partials (sum, sum of squares).
+// STORE_Y: the first convolution of a two-conv block — writes y_a = U_j + V_i [E,64] for the conv_b pass and the
+// backward (BatchNorm with batch statistics sits between the two convolutions, so y_a is needed per edge) instead of the
+// extrema; the per-edge tensor-core GEMM (gather, bf16x3 split, 24 MMAs per tile) it replaces took 4x as long.
+template <bool STORE_Y>
 __global__ void __launch_bounds__(kThreads)
 ec_lin_extrema_kernel(const float* __restrict__ U, int ld_u, const float* __restrict__ V, int ld_v, const int32_t* __restrict__ idx,
                       int M, int N, int k, float* __restrict__ ymax, float* __restrict__ ymin, uint8_t* __restrict__ amax,
-                      uint8_t* __restrict__ amin, double* __restrict__ partials) {
+                      uint8_t* __restrict__ amin, float* __restrict__ y_out, double* __restrict__ partials) {
   __shared__ float4 red[2][kThreads];
   const int c4 = threadIdx.x & 15, pl = threadIdx.x >> 4;
   const int c = 4 * c4;
@@ -36,24 +40,30 @@ ec_lin_extrema_kernel(const float* __restrict__ U, int ld_u, const float* __rest
       const float4 u = *reinterpret_cast<const float4*>(U + (base + nb[slot]) * ld_u + c);
       float4 y;
       y.x = __fadd_rn(u.x, v.x); y.y = __fadd_rn(u.y, v.y); y.z = __fadd_rn(u.z, v.z); y.w = __fadd_rn(u.w, v.w);
-      // first occurrence wins ties, like the per-edge kernels
-      if (y.x > mx.x) { mx.x = y.x; ax.x = slot; }
-      if (y.y > mx.y) { mx.y = y.y; ax.y = slot; }
-      if (y.z > mx.z) { mx.z = y.z; ax.z = slot; }
-      if (y.w > mx.w) { mx.w = y.w; ax.w = slot; }
-      if (y.x < mn.x) { mn.x = y.x; an.x = slot; }
-      if (y.y < mn.y) { mn.y = y.y; an.y = slot; }
-      if (y.z < mn.z) { mn.z = y.z; an.z = slot; }
-      if (y.w < mn.w) { mn.w = y.w; an.w = slot; }
+      if (STORE_Y) {
+        *reinterpret_cast<float4*>(y_out + (static_cast<size_t>(gp) * k + slot) * kCout + c) = y;
+      } else {
+        // first occurrence wins ties, like the per-edge kernels
+        if (y.x > mx.x) { mx.x = y.x; ax.x = slot; }
+        if (y.y > mx.y) { mx.y = y.y; ax.y = slot; }
+        if (y.z > mx.z) { mx.z = y.z; ax.z = slot; }
+        if (y.w > mx.w) { mx.w = y.w; ax.w = slot; }
+        if (y.x < mn.x) { mn.x = y.x; an.x = slot; }
+        if (y.y < mn.y) { mn.y = y.y; an.y = slot; }
+        if (y.z < mn.z) { mn.z = y.z; an.z = slot; }
+        if (y.w < mn.w) { mn.w = y.w; an.w = slot; }
+      }
       s1.x += y.x; s1.y += y.y; s1.z += y.z; s1.w += y.w;
       s2.x = __fmaf_rn(y.x, y.x, s2.x); s2.y = __fmaf_rn(y.y, y.y, s2.y);
       s2.z = __fmaf_rn(y.z, y.z, s2.z); s2.w = __fmaf_rn(y.w, y.w, s2.w);
     }
-    const size_t o = static_cast<size_t>(gp) * kCout + c;
-    *reinterpret_cast<float4*>(ymax + o) = mx;
-    *reinterpret_cast<float4*>(ymin + o) = mn;
-    *reinterpret_cast<uchar4*>(amax + o) = ax;
-    *reinterpret_cast<uchar4*>(amin + o) = an;
+    if (!STORE_Y) {
+      const size_t o = static_cast<size_t>(gp) * kCout + c;
+      *reinterpret_cast<float4*>(ymax + o) = mx;
+      *reinterpret_cast<float4*>(ymin + o) = mn;
+      *reinterpret_cast<uchar4*>(amax + o) = ax;
+      *reinterpret_cast<uchar4*>(amin + o) = an;
+    }
     t1.x += s1.x; t1.y += s1.y; t1.z += s1.z; t1.w += s1.w;
     t2.x += s2.x; t2.y += s2.y; t2.z += s2.z; t2.w += s2.w;
   }
@@ -128,8 +138,21 @@ extern "C" int dgcnn_edgeconv_lin_extrema(const dgcnn_edgeconv_args* a, const fl
   DG_REQUIRE(ymax && ymin && amax && amin, DGCNN_E_INVALID, "edgeconv_lin_extrema: null output");
   const int M = a->B * a->N;
   const int blocks = std::max(1, std::min((M + 15) / 16, std::min(kMaxPartialCtas, 8 * std::max(1, num_sms()))));
-  ec_lin_extrema_kernel<<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(U, ld_u, V, ld_v, a->idx, M, a->N, a->k, ymax, ymin,
-                                                                                  amax, amin, partials);
+  ec_lin_extrema_kernel<false><<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(U, ld_u, V, ld_v, a->idx, M, a->N, a->k, ymax,
+                                                                                         ymin, amax, amin, nullptr, partials);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}
+
+extern "C" int dgcnn_edgeconv_lin_conv_a(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
+                                         float* y_a, double* partials, void* stream) {
+  int rc = lin_check(a, U, ld_u, V, ld_v, "edgeconv_lin_conv_a");
+  if (rc) return rc;
+  DG_REQUIRE(y_a && partials && (reinterpret_cast<uintptr_t>(y_a) & 15) == 0, DGCNN_E_INVALID, "edgeconv_lin_conv_a: null / misaligned output");
+  const int M = a->B * a->N;
+  const int blocks = std::max(1, std::min((M + 15) / 16, std::min(kMaxPartialCtas, 8 * std::max(1, num_sms()))));
+  ec_lin_extrema_kernel<true><<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(U, ld_u, V, ld_v, a->idx, M, a->N, a->k, nullptr,
+                                                                                        nullptr, nullptr, nullptr, y_a, partials);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
 }

@@ -529,11 +529,18 @@ class EdgeConvTrain(torch.autograd.Function):
         ysel = torch.empty(M, COUT, **f32)
         arg = torch.empty(M, COUT, dtype=torch.uint8, device=dev)
         stat_a = torch.empty(2 + 3, COUT, **f32)     # mean, rstd, affine(mean|scale|beta)
-        vs = None if lin else _v_scratch(B, Cn, N, dev)
+        vs = None if (lin or EDGECONV_IMPL == 0) else _v_scratch(B, Cn, N, dev)
         a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, None, COUT, vs)
 
         uv = None
-        if lin:
+        if two and EDGECONV_IMPL == 0:
+            # first conv of a two-conv block: y_a = U_j + V_i written per edge (BN_a needs batch statistics before conv_b
+            # can start), no per-edge GEMM.  Also for the input block: y_a carries the centre term Wa2 x_i (~|W||x|) either
+            # way, so forming x_j - x_i first buys no accuracy at the level of y_a (both are within a few 1e-8 |W||x|).
+            uv2 = tc_gemm(rows[:, :Cn], _lin_weight(wa, Cn))
+            _call("dgcnn_edgeconv_lin_conv_a", dev, C.byref(a), _ptr(uv2), uv2.stride(0), _ptr(uv2[:, COUT:]), uv2.stride(0), _ptr(y_a),
+                  _ptr(partials))
+        elif lin:
             # y = U_j + V_i: one point-level GEMM + a gather pass (extrema over k, batch sums); nothing per-edge in HBM
             uv = tc_gemm(rows[:, :Cn], _lin_weight(wa, Cn))
             _call("dgcnn_edgeconv_lin_extrema", dev, C.byref(a), _ptr(uv), uv.stride(0), _ptr(uv[:, COUT:]), uv.stride(0), _ptr(partials),

@@ -168,6 +168,10 @@ int dgcnn_edgeconv_bwd_a(const dgcnn_edgeconv_args* a, const float* y_a, const f
  * Intended for the 64-channel feature-space block (O(1) features); rows of U, V: >= 64 floats, 16-byte aligned.       */
 int dgcnn_edgeconv_lin_extrema(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
                                double* partials, float* ymax, float* ymin, uint8_t* amax, uint8_t* amin, void* stream);
+/* first convolution of a TWO-conv block the same way: y_a[B*N*k,64] = U_j + V_i (kept per edge because batch-statistics BN
+ * sits between the convolutions) and its batch sums; replaces dgcnn_edgeconv_conv_a_train for 64-channel inputs.    */
+int dgcnn_edgeconv_lin_conv_a(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
+                              float* y_a, double* partials, void* stream);
 int dgcnn_edgeconv_bwd_a_lin(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
                              const float* g, const uint8_t* arg, const float* coef_a, float* s, float* r, int ld_rs,
                              void* stream);
