@@ -241,6 +241,11 @@ __device__ __forceinline__ float exact_score(const float* __restrict__ xi, const
   return __fsub_rn(__fmaf_rn(d, 2.0f, -norm_j), norm_i);
 }
 
+// candidate entry of the scan pass: approximate score (raw float bits) in the high word, key index in the low word.
+// (No order-preserving key transform here: the scan's hit path is issue-bound; the select pass compares the floats.)
+__device__ __forceinline__ float cand_score(unsigned long long e) { return __uint_as_float(static_cast<uint32_t>(e >> 32)); }
+__device__ __forceinline__ int cand_index(unsigned long long e) { return static_cast<int>(static_cast<uint32_t>(e)); }
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -391,15 +396,20 @@ knn_tc_scan_kernel(const unsigned char* __restrict__ tiles, int N, int T, int nk
     const uint32_t tbase = taddr + (static_cast<uint32_t>(quarter * 32) << 16) + cq * QC;
     const float2 two = make_float2(2.0f, 2.0f);
 
-    // load one tile's scores sc[ch][c] = 2 * gram + kn (the row constant |y_i|^2 is left out), then release the
-    // accumulator and the key slot: everything after that works from registers
-    auto load_scores = [&](int i, float (&sc)[CH][16]) {
-      const int s = i % kStages, a = i % kAccs;
+    // One tile's scores sc[ch][c] = 2 * gram + kn (the row constant |y_i|^2 is left out) in two halves, so that the TMEM
+    // loads of tile i + 1 are in flight while tile i is being scanned (software pipelining: with 4 warps per scheduler the
+    // barrier wake-up + tcgen05.ld latency was exposed once per tile):
+    //   issue_loads(i, r)   wait for the MMAs of tile i, issue the tcgen05.ld's (no wait)
+    //   finish_loads(i, r)  wait::ld, add the key norms, hand the accumulator and the key slot back
+    auto issue_loads = [&](int i, uint32_t (&r)[CH][16]) {
+      const int a = i % kAccs;
       tc::mbar_wait(accfull + a, (i / kAccs) & 1);
       tc::fence_after_sync();
-      uint32_t r[CH][16];
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch) tc::tmem_ld16_issue(tbase + a * KEYS + ch * 16, r[ch]);
+    };
+    auto finish_loads = [&](int i, uint32_t (&r)[CH][16], float (&sc)[CH][16]) {
+      const int s = i % kStages, a = i % kAccs;
       const float4* kn4 = reinterpret_cast<const float4*>(Bs + s * S::stage_bytes + Tile::norm_off) + cq * (QC / 4);
       float4 kk[CH][4];
 #pragma unroll
@@ -426,6 +436,11 @@ knn_tc_scan_kernel(const unsigned char* __restrict__ tiles, int N, int T, int nk
         tc::mbar_arrive(sfree + s);            // slot first: an observed `accfree` phase implies the slot's release
         tc::mbar_arrive(accfree + a);
       }
+    };
+    auto load_scores = [&](int i, float (&sc)[CH][16]) {
+      uint32_t r[CH][16];
+      issue_loads(i, r);
+      finish_loads(i, r, sc);
     };
 
     // ---- pass 1: threshold estimate from T1 sampled tiles ----------------------------------------------------------
@@ -461,39 +476,49 @@ knn_tc_scan_kernel(const unsigned char* __restrict__ tiles, int N, int T, int nk
     if (row_ok) tau_out[g] = tau;
 
     // ---- pass 2: collect every key above tau --------------------------------------------------------------------------
-    unsigned long long* mycand = cand + (g * 4 + cq) * kSubCands;
+    uint2* wp = reinterpret_cast<uint2*>(cand + (g * 4 + cq) * kSubCands);       // next free slot of this thread's sub-buffer
     float* park = scr + (warp * 32 + lane) * S::scr_stride;
     const float tau_eff = row_ok ? tau : INFINITY;       // rows past the end of the block collect nothing
     const float2 tau2 = make_float2(tau_eff, tau_eff), neg1 = make_float2(-1.0f, -1.0f);
     int n = 0;
+    float sc[CH][16];
+    load_scores(T1, sc);                                   // (TT > T1: a block has at least one key tile)
     for (int i = T1; i < TT; ++i) {
-      float sc[CH][16];
-      load_scores(i, sc);
+      uint32_t rn[CH][16];
+      if (i + 1 < TT) issue_loads(i + 1, rn);              // next tile's accumulator -> registers while this one is scanned
       const int j0 = (i - T1) * KEYS + cq * QC;
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch) {
-        // sign(tau - score) of column c ends up in bit 15 - c
-        uint32_t mask = 0u;
+        // sign(tau - score) of column c ends up in bit 15 - c.  Four independent 4-bit chains: one 16-deep chain of
+        // dependent funnel shifts left the warp waiting on the 4-cycle ALU latency with only 4 warps per scheduler.
+        uint32_t mq[4];
 #pragma unroll
-        for (int c = 0; c < 16; c += 2) {
-          const float2 d = __ffma2_rn(make_float2(sc[ch][c], sc[ch][c + 1]), neg1, tau2);
-          mask = shift_in_sign(mask, d.x);
-          mask = shift_in_sign(mask, d.y);
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const float2 d0 = __ffma2_rn(make_float2(sc[ch][4 * q4], sc[ch][4 * q4 + 1]), neg1, tau2);
+          const float2 d1 = __ffma2_rn(make_float2(sc[ch][4 * q4 + 2], sc[ch][4 * q4 + 3]), neg1, tau2);
+          uint32_t mm = shift_in_sign(0u, d0.x);
+          mm = shift_in_sign(mm, d0.y);
+          mm = shift_in_sign(mm, d1.x);
+          mq[q4] = shift_in_sign(mm, d1.y);
         }
+        const uint32_t mask = (((mq[0] << 4) | mq[1]) << 8) | ((mq[2] << 4) | mq[3]);
         if (mask != 0u) {
           // rare per thread (a few % of the chunks): park the 16 scores so that the hit columns can be indexed
           float4* p4 = reinterpret_cast<float4*>(park);
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) p4[q4] = make_float4(sc[ch][4 * q4], sc[ch][4 * q4 + 1], sc[ch][4 * q4 + 2], sc[ch][4 * q4 + 3]);
-          uint32_t m = mask & 0xFFFFu;
-          while (m) {
-            const int c = 15 - (31 - __clz(m));              // highest set bit first = lowest column first
-            m &= ~(0x8000u >> c);
-            if (n < kSubCands) mycand[n] = make_key(park[c], j0 + ch * 16 + c);
+          uint32_t m = mask;
+          const int jc = j0 + ch * 16 + 15;
+          do {
+            const int pos = 31 - __clz(m);                    // highest set bit first = lowest column first (c = 15 - pos)
+            m ^= 1u << pos;
+            if (n < kSubCands) *wp = make_uint2(static_cast<uint32_t>(jc - pos), __float_as_uint(park[15 - pos]));
+            ++wp;
             ++n;
-          }
+          } while (m);
         }
       }
+      if (i + 1 < TT) finish_loads(i + 1, rn, sc);
     }
     if (row_ok) cnt4[g * 4 + cq] = n;
   }
@@ -550,7 +575,7 @@ knn_tc_select_kernel(const float* __restrict__ rows, int ld, const float* __rest
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     key[r] = lane < cs[r] ? rc[r * kSubCands + lane] : 0ull;
-    ap[r] = key[r] != 0ull ? sel::key_score(key[r]) : -INFINITY;
+    ap[r] = lane < cs[r] ? cand_score(key[r]) : -INFINITY;
     key[4 + r] = 0ull;
     ap[4 + r] = -INFINITY;
   }
@@ -558,7 +583,7 @@ knn_tc_select_kernel(const float* __restrict__ rows, int ld, const float* __rest
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       key[4 + r] = 32 + lane < cs[r] ? rc[r * kSubCands + 32 + lane] : 0ull;
-      ap[4 + r] = key[4 + r] != 0ull ? sel::key_score(key[4 + r]) : -INFINITY;
+      ap[4 + r] = 32 + lane < cs[r] ? cand_score(key[4 + r]) : -INFINITY;
     }
   }
   auto count_above = [&](float t) {
@@ -581,7 +606,7 @@ knn_tc_select_kernel(const float* __restrict__ rows, int ld, const float* __rest
   if (tau_open) {                                  // start from the smallest candidate
     float mn = INFINITY;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) mn = fminf(mn, key[r] != 0ull ? ap[r] : INFINITY);
+    for (int r = 0; r < 8; ++r) mn = fminf(mn, ap[r] > -INFINITY ? ap[r] : INFINITY);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
     lo = mn - fabsf(mn) * 1e-6f - 1e-30f;
@@ -637,7 +662,7 @@ knn_tc_select_kernel(const float* __restrict__ rows, int ld, const float* __rest
       const bool is_sure = ap[r] > sure_cut;
       const bool is_band = !is_sure && ap[r] > cut;
       const unsigned ms = __ballot_sync(0xffffffffu, is_sure), mb = __ballot_sync(0xffffffffu, is_band);
-      if (is_sure) idx[g * k + s + __popc(ms & lt_mask)] = key_index(key[r]);      // s + ... < k: fewer than k keys exceed a_k
+      if (is_sure) idx[g * k + s + __popc(ms & lt_mask)] = cand_index(key[r]);      // s + ... < k: fewer than k keys exceed a_k
       const int pb = nb + __popc(mb & lt_mask);
       if (is_band && pb < kSurvivors) stg[pb] = key[r];
       s += __popc(ms);
@@ -654,7 +679,7 @@ knn_tc_select_kernel(const float* __restrict__ rows, int ld, const float* __rest
       ex[r] = 0ull;
       const int e = lane + 32 * r;
       if (e < ns) {
-        const int j = key_index(stg[e]);
+        const int j = cand_index(stg[e]);
         const size_t gj = static_cast<size_t>(b) * N + j;
         ex[r] = make_key(exact_score<8>(xi, rows + gj * ld, C4, norm_i, norms[gj]), j);
       }
@@ -709,7 +734,7 @@ knn_tc_select_kernel(const float* __restrict__ rows, int ld, const float* __rest
     ex[r] = 0ull;
     const int e = lane + 32 * r;
     if (e < ns) {
-      const int j = key_index(stg[e]);
+      const int j = cand_index(stg[e]);
       const size_t gj = static_cast<size_t>(b) * N + j;
       ex[r] = make_key(exact_score(xi, rows + gj * ld, C4, norm_i, norms[gj]), j);
     }
