@@ -77,30 +77,38 @@ __global__ void __launch_bounds__(kRbThreads) rows_bn_reduce_kernel(RowsBn p, co
   }
 }
 
-// one warp per channel: lane l sums partials l, l+32, ... then a fixed shuffle tree (deterministic), all in FP64
-__device__ __forceinline__ void rows_bn_sum_partials(const double* __restrict__ partials, int nparts, int C, int c, double& s, double& q) {
-  const int lane = threadIdx.x & 31;
+// CTA = 32 channels x 32 part groups (1024 threads): group g adds the per-CTA partials g, g+32, ... (coalesced 256-byte
+// reads), the 32 group sums are added in a fixed order, all in FP64 (deterministic).  One warp per channel with
+// 8-byte strided reads made these two-value reductions cost 19 us each (5 launches per step).
+__device__ __forceinline__ bool rows_bn_sum_partials(const double* __restrict__ partials, int nparts, int C, int& c, double& s, double& q) {
+  __shared__ double red[2][32][33];
+  const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+  c = blockIdx.x * 32 + cl;
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+#pragma unroll 4
+    for (int i = g; i < nparts; i += 32) {
+      a += partials[static_cast<size_t>(i) * 2 * C + c];
+      b += partials[static_cast<size_t>(i) * 2 * C + C + c];
+    }
+  }
+  red[0][g][cl] = a;
+  red[1][g][cl] = b;
+  __syncthreads();
+  if (g != 0 || c >= C) return false;
   s = 0.0; q = 0.0;
-  for (int i = lane; i < nparts; i += 32) {
-    s += partials[static_cast<size_t>(i) * 2 * C + c];
-    q += partials[static_cast<size_t>(i) * 2 * C + C + c];
-  }
 #pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    q += __shfl_xor_sync(0xffffffffu, q, o);
-  }
+  for (int j = 0; j < 32; ++j) { s += red[0][j][cl]; q += red[1][j][cl]; }
+  return true;
 }
 
-__global__ void __launch_bounds__(256) rows_bn_fwd_finalize_kernel(const double* __restrict__ partials, int nparts, int C, double count,
+__global__ void __launch_bounds__(1024) rows_bn_fwd_finalize_kernel(const double* __restrict__ partials, int nparts, int C, double count,
                                             const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                             float momentum, float* running_mean, float* running_var, float* __restrict__ mean,
                                             float* __restrict__ rstd, float* __restrict__ aff) {
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (c >= C) return;
+  int c;
   double s, q;
-  rows_bn_sum_partials(partials, nparts, C, c, s, q);
-  if (threadIdx.x & 31) return;
+  if (!rows_bn_sum_partials(partials, nparts, C, c, s, q)) return;
   const double m = s / count;
   double var = q / count - m * m;
   if (var < 0.0) var = 0.0;
@@ -129,14 +137,12 @@ __global__ void rows_bn_eval_affine_kernel(int C, const float* __restrict__ gamm
 }
 
 // coef = [kA | kB | kC] with dy = kA * dz - kB - kC * (v - mean):   kA = gamma rstd, kB = kA * s1 / M, kC = kA * rstd^2 * s2 / M
-__global__ void __launch_bounds__(256) rows_bn_bwd_finalize_kernel(const double* __restrict__ partials, int nparts, int C, double count,
+__global__ void __launch_bounds__(1024) rows_bn_bwd_finalize_kernel(const double* __restrict__ partials, int nparts, int C, double count,
                                             const float* __restrict__ gamma, const float* __restrict__ rstd,
                                             float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (c >= C) return;
+  int c;
   double s1, s2;
-  rows_bn_sum_partials(partials, nparts, C, c, s1, s2);
-  if (threadIdx.x & 31) return;
+  if (!rows_bn_sum_partials(partials, nparts, C, c, s1, s2)) return;
   const double rs = rstd[c], kA = static_cast<double>(gamma[c]) * rs;
   dbeta[c] = static_cast<float>(s1);
   dgamma[c] = static_cast<float>(s2 * rs);                  // sum dz * vhat
@@ -273,7 +279,7 @@ extern "C" int dgcnn_rows_bn_lrelu_fwd(const float* y, int M, int C, const float
     int rpc;
     const int grid = rows_bn_grid(M, &rpc);
     rows_bn_reduce_kernel<false><<<grid, kRbThreads, 0, st>>>(p, nullptr, rpc, partials);
-    rows_bn_fwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partials, grid, C, static_cast<double>(M), gamma, beta, eps,
+    rows_bn_fwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partials, grid, C, static_cast<double>(M), gamma, beta, eps,
                                                                  momentum, running_mean, running_var, mean, rstd, aff);
   } else {
     rows_bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, eps, running_mean, running_var, aff);
@@ -298,7 +304,7 @@ extern "C" int dgcnn_rows_bn_lrelu_bwd(const float* dh, const float* y, int M, i
   int rpc;
   const int grid = rows_bn_grid(M, &rpc);
   rows_bn_reduce_kernel<true><<<grid, kRbThreads, 0, st>>>(p, dh, rpc, partials);
-  rows_bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partials, grid, C, static_cast<double>(M), gamma, rstd, dgamma, dbeta, coef);
+  rows_bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partials, grid, C, static_cast<double>(M), gamma, rstd, dgamma, dbeta, coef);
   const int blocks = rows_bn_apply_grid(M, C);
   rows_bn_apply_kernel<true><<<blocks, kRbThreads, 0, st>>>(p, dh, coef, dy);
   DG_CUDA(cudaGetLastError());
