@@ -85,10 +85,13 @@ ec_lin_extrema_kernel(const float* __restrict__ U, int ld_u, const float* __rest
   if (blockIdx.x == 0 && threadIdx.x == 0) partials[0] = static_cast<double>(gridDim.x);
 }
 
-// backward edge pass through BN_a for the linearised block: dy = cA dz - cB - cC (U_j + V_i), dz non-zero at the arg rows
+// backward edge pass through BN_a with y recomputed as U_j + V_i (an L2 gather instead of a 430 MB HBM read of y_a):
+// dy = cA dz - cB - cC (U_j + V_i).  DENSE_DZ: dz is the per-edge dz_a of a two-conv block; otherwise (single conv) dz is
+// non-zero at the arg rows only and comes from g / arg.
+template <bool DENSE_DZ>
 __global__ void __launch_bounds__(kThreads)
 ec_lin_bwd_a_kernel(const float* __restrict__ U, int ld_u, const float* __restrict__ V, int ld_v, const int32_t* __restrict__ idx,
-                    int M, int N, int k, const float* __restrict__ g, const uint8_t* __restrict__ arg,
+                    int M, int N, int k, const float* __restrict__ dz_a, const float* __restrict__ g, const uint8_t* __restrict__ arg,
                     const float* __restrict__ coef_a, float* __restrict__ s_out, float* __restrict__ r_out, int ld_rs) {
   const int c4 = threadIdx.x & 15, pl = threadIdx.x >> 4;
   const int c = 4 * c4;
@@ -97,8 +100,12 @@ ec_lin_bwd_a_kernel(const float* __restrict__ U, int ld_u, const float* __restri
   const float4 cC = *reinterpret_cast<const float4*>(coef_a + 128 + c);
   for (int gp = blockIdx.x * 16 + pl; gp < M; gp += gridDim.x * 16) {
     const size_t base = static_cast<size_t>(gp / N) * N;
-    const float4 gv = *reinterpret_cast<const float4*>(g + static_cast<size_t>(gp) * kCout + c);
-    const uchar4 av = *reinterpret_cast<const uchar4*>(arg + static_cast<size_t>(gp) * kCout + c);
+    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+    uchar4 av = make_uchar4(255, 255, 255, 255);
+    if (!DENSE_DZ) {
+      gv = *reinterpret_cast<const float4*>(g + static_cast<size_t>(gp) * kCout + c);
+      av = *reinterpret_cast<const uchar4*>(arg + static_cast<size_t>(gp) * kCout + c);
+    }
     const float4 v = *reinterpret_cast<const float4*>(V + static_cast<size_t>(gp) * ld_v + c);
     const int32_t* nb = idx + static_cast<size_t>(gp) * k;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -106,11 +113,18 @@ ec_lin_bwd_a_kernel(const float* __restrict__ U, int ld_u, const float* __restri
     for (int slot = 0; slot < k; ++slot) {
       const size_t j = base + nb[slot];
       const float4 u = *reinterpret_cast<const float4*>(U + j * ld_u + c);
+      float4 dz;
+      if (DENSE_DZ) {
+        dz = *reinterpret_cast<const float4*>(dz_a + (static_cast<size_t>(gp) * k + slot) * kCout + c);
+      } else {
+        dz.x = av.x == slot ? gv.x : 0.f; dz.y = av.y == slot ? gv.y : 0.f;
+        dz.z = av.z == slot ? gv.z : 0.f; dz.w = av.w == slot ? gv.w : 0.f;
+      }
       float4 dy;
-      dy.x = cA.x * (av.x == slot ? gv.x : 0.f) - cB.x - cC.x * __fadd_rn(u.x, v.x);
-      dy.y = cA.y * (av.y == slot ? gv.y : 0.f) - cB.y - cC.y * __fadd_rn(u.y, v.y);
-      dy.z = cA.z * (av.z == slot ? gv.z : 0.f) - cB.z - cC.z * __fadd_rn(u.z, v.z);
-      dy.w = cA.w * (av.w == slot ? gv.w : 0.f) - cB.w - cC.w * __fadd_rn(u.w, v.w);
+      dy.x = cA.x * dz.x - cB.x - cC.x * __fadd_rn(u.x, v.x);
+      dy.y = cA.y * dz.y - cB.y - cC.y * __fadd_rn(u.y, v.y);
+      dy.z = cA.z * dz.z - cB.z - cC.z * __fadd_rn(u.z, v.z);
+      dy.w = cA.w * dz.w - cB.w - cC.w * __fadd_rn(u.w, v.w);
       s.x += dy.x; s.y += dy.y; s.z += dy.z; s.w += dy.w;
       atomicAdd(reinterpret_cast<float4*>(r_out + j * ld_rs + c), dy);
     }
@@ -158,17 +172,22 @@ extern "C" int dgcnn_edgeconv_lin_conv_a(const dgcnn_edgeconv_args* a, const flo
 }
 
 extern "C" int dgcnn_edgeconv_bwd_a_lin(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
-                                        const float* g, const uint8_t* arg, const float* coef_a, float* s, float* r, int ld_rs,
-                                        void* stream) {
+                                        const float* dz_a, const float* g, const uint8_t* arg, const float* coef_a, float* s,
+                                        float* r, int ld_rs, void* stream) {
   int rc = lin_check(a, U, ld_u, V, ld_v, "edgeconv_bwd_a_lin");
   if (rc) return rc;
-  DG_REQUIRE(g && arg && coef_a && s && r, DGCNN_E_INVALID, "edgeconv_bwd_a_lin: null pointer");
+  DG_REQUIRE(coef_a && s && r && (dz_a || (g && arg)), DGCNN_E_INVALID, "edgeconv_bwd_a_lin: null pointer");
+  DG_REQUIRE(!dz_a || (reinterpret_cast<uintptr_t>(dz_a) & 15) == 0, DGCNN_E_INVALID, "edgeconv_bwd_a_lin: dz_a must be 16-byte aligned");
   DG_REQUIRE(ld_rs >= kCout && ld_rs % 4 == 0 && ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(r)) & 15) == 0,
              DGCNN_E_INVALID, "edgeconv_bwd_a_lin: s/r need 16-byte alignment and ld_rs %% 4 == 0, ld_rs >= 64");
   const int M = a->B * a->N;
   const int blocks = std::max(1, std::min((M + 15) / 16, 8 * std::max(1, num_sms())));
-  ec_lin_bwd_a_kernel<<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(U, ld_u, V, ld_v, a->idx, M, a->N, a->k, g, arg, coef_a,
-                                                                                s, r, ld_rs);
+  if (dz_a)
+    ec_lin_bwd_a_kernel<true><<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(U, ld_u, V, ld_v, a->idx, M, a->N, a->k, dz_a,
+                                                                                        g, arg, coef_a, s, r, ld_rs);
+  else
+    ec_lin_bwd_a_kernel<false><<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(U, ld_u, V, ld_v, a->idx, M, a->N, a->k, dz_a,
+                                                                                         g, arg, coef_a, s, r, ld_rs);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
 }

@@ -532,7 +532,7 @@ class EdgeConvTrain(torch.autograd.Function):
         vs = None if (lin or EDGECONV_IMPL == 0) else _v_scratch(B, Cn, N, dev)
         a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, None, COUT, vs)
 
-        uv = None
+        uv = uv2 = None
         if two and EDGECONV_IMPL == 0:
             # first conv of a two-conv block: y_a = U_j + V_i written per edge (BN_a needs batch statistics before conv_b
             # can start), no per-edge GEMM.  Also for the input block: y_a carries the centre term Wa2 x_i (~|W||x|) either
@@ -565,6 +565,7 @@ class EdgeConvTrain(torch.autograd.Function):
         ctx.meta = meta
         ctx.two = two
         ctx.lin = lin
+        ctx.uv2 = uv2                                   # [U | V] of a two-conv block: the backward gathers it instead of re-reading y_a
         ctx.save_for_backward(rows, idx, wa, wb if two else wa, gamma_a.detach(), gamma_b.detach() if two else gamma_a.detach(),
                               uv if lin else y_a, stat_a, stat_b if two else stat_a, ysel, arg)
         ctx.x_shape = tuple(x.shape)
@@ -610,10 +611,11 @@ class EdgeConvTrain(torch.autograd.Function):
             dz_a, coef_a, dga = None, coef_l, dgl
         rs = torch.zeros(M, 2 * COUT, **f32)            # [ r | s ]: scatter target and per-point sums, one GEMM operand
         r, s = rs[:, :COUT], rs[:, COUT:]
-        if ctx.lin:
-            uv = y_a                                    # (saved in its place) [U | V]
-            _call("dgcnn_edgeconv_bwd_a_lin", dev, C.byref(a), _ptr(uv), uv.stride(0), _ptr(uv[:, COUT:]), uv.stride(0), _ptr(g), _ptr(arg),
-                  _ptr(coef_a), _ptr(s), _ptr(r), 2 * COUT)
+        if ctx.lin or ctx.uv2 is not None:
+            uv = y_a if ctx.lin else ctx.uv2            # [U | V] (saved in y_a's place for the single-conv block)
+            _call("dgcnn_edgeconv_bwd_a_lin", dev, C.byref(a), _ptr(uv), uv.stride(0), _ptr(uv[:, COUT:]), uv.stride(0), _ptr(dz_a),
+                  _ptr(g), _ptr(arg), _ptr(coef_a), _ptr(s), _ptr(r), 2 * COUT)
+            ctx.uv2 = None
         else:
             _call("dgcnn_edgeconv_bwd_a", dev, C.byref(a), _ptr(y_a), _ptr(dz_a), _ptr(g), _ptr(arg), _ptr(coef_a),
                   _ptr(s), _ptr(r), 2 * COUT)

@@ -163,8 +163,9 @@ int dgcnn_edgeconv_bwd_a(const dgcnn_edgeconv_args* a, const float* y_a, const f
  * dgcnn_edgeconv_lin_extrema: one gather pass over U — per point and channel the extrema of fl(U_j + V_i) over the k
  * neighbours (ymax, ymin float[B*N,64], slots amax, amin uint8) and the batch sums of y, y^2 (partials, as
  * dgcnn_edgeconv_conv_a_train writes them; NULL in inference).  Follow with dgcnn_bn_finalize (training) and
- * dgcnn_edgeconv_select.  dgcnn_edgeconv_bwd_a_lin is dgcnn_edgeconv_bwd_a for this block with y recomputed as
- * U_j + V_i.  No per-edge tensor exists in HBM in either direction.  Only `idx`, B, N, k of the args are used.
+ * dgcnn_edgeconv_select.  dgcnn_edgeconv_bwd_a_lin is dgcnn_edgeconv_bwd_a with y recomputed as U_j + V_i (dz_a ==
+ * NULL: single-conv block, dz from g / arg; dz_a != NULL: two-conv block, the y_a read becomes an L2 gather).
+ * For the single-conv block no per-edge tensor exists in HBM in either direction.  Only `idx`, B, N, k of the args are used.
  * Intended for the 64-channel feature-space block (O(1) features); rows of U, V: >= 64 floats, 16-byte aligned.       */
 int dgcnn_edgeconv_lin_extrema(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
                                double* partials, float* ymax, float* ymin, uint8_t* amax, uint8_t* amin, void* stream);
@@ -173,8 +174,8 @@ int dgcnn_edgeconv_lin_extrema(const dgcnn_edgeconv_args* a, const float* U, int
 int dgcnn_edgeconv_lin_conv_a(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
                               float* y_a, double* partials, void* stream);
 int dgcnn_edgeconv_bwd_a_lin(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
-                             const float* g, const uint8_t* arg, const float* coef_a, float* s, float* r, int ld_rs,
-                             void* stream);
+                             const float* dz_a, const float* g, const uint8_t* arg, const float* coef_a, float* s, float* r,
+                             int ld_rs, void* stream);
 
 /* ---- FP32-accurate tensor-core GEMM (tcgen05, bf16 split planes):  D[M,N] = A[M,K] * B[N,K]^T ---------------
  * A and B are FP32 with arbitrary element strides (row stride, column stride), so transposed operands need no
