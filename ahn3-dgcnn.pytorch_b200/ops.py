@@ -494,6 +494,25 @@ def edgeconv_eval(rows: torch.Tensor, idx: torch.Tensor, B: int, Cn: int, N: int
               _ptr(ysel), _ptr(arg))
         return out
     wb = None if w_b is None else w_b.detach().reshape(COUT, COUT).contiguous()
+    if wb is not None and EDGECONV_IMPL == 0:
+        # two convs: the training-forward passes with the running statistics as affines — conv_a as y_a = U_j + V_i
+        # (point-level GEMM + gather pass), conv_b on the warp-specialised tcgen05 pipeline, extrema over k, BN_b +
+        # LeakyReLU on the selected extremum.  Faster than the fully fused per-edge kernel (which runs BOTH convolutions
+        # as per-edge MMAs) even though y_a takes a round trip through HBM.
+        M, dev = B * N, rows.device
+        partials, _ = _partials(dev)
+        uv = tc_gemm(rows[:, :Cn], _lin_weight(wa, Cn))
+        y_a = torch.empty(M * k, COUT, dtype=torch.float32, device=dev)
+        ymax, ymin = torch.empty(M, COUT, dtype=torch.float32, device=dev), torch.empty(M, COUT, dtype=torch.float32, device=dev)
+        amax, amin = torch.empty(M, COUT, dtype=torch.uint8, device=dev), torch.empty(M, COUT, dtype=torch.uint8, device=dev)
+        a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, None, COUT)
+        _call("dgcnn_edgeconv_lin_conv_a", dev, C.byref(a), _ptr(uv), uv.stride(0), _ptr(uv[:, COUT:]), uv.stride(0), _ptr(y_a), _ptr(partials))
+        _call("dgcnn_edgeconv_conv_b_train", dev, C.byref(a), _ptr(y_a), _ptr(aff_a), _ptr(partials), _ptr(ymax), _ptr(ymin), _ptr(amax),
+              _ptr(amin))
+        ysel, arg = torch.empty_like(ymax), torch.empty_like(amax)
+        _call("dgcnn_edgeconv_select", dev, M, _ptr(ymax), _ptr(ymin), _ptr(amax), _ptr(amin), _ptr(aff_b), _ptr(out), COUT, _ptr(ysel),
+              _ptr(arg))
+        return out
     vs = _v_scratch(B, Cn, N, rows.device)
     a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, out, COUT, vs)
     _call("dgcnn_edgeconv_fwd_eval", rows.device, C.byref(a), _ptr(aff_a), _ptr(aff_b))
