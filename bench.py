@@ -360,7 +360,7 @@ def run_ours(args, rank: int, local: int, world: int):
     parallel.broadcast_parameters(model)
     model.train()
     bucket = parallel.GradBucket(model.parameters())
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True, capturable=not args.no_graph)
 
     nbuf = 4
     host = [make_batch(1000 * rank + i, B_PER_GPU) for i in range(nbuf)]
@@ -398,36 +398,99 @@ def run_ours(args, rank: int, local: int, world: int):
 
     for i in range(max(args.warmup, 3)):
         step(*resident[i % nbuf])
+    eager_step = step
+
+    # ---- eager passes first (a captured graph ties the gradient accumulators to its capture stream; eager steps after the
+    # capture pay cross-stream synchronisations) -------------------------------------------------------------------------
+    # (1) per-entry-point device time: CUDA event pairs around every C-ABI call
+    ops.LOG.reset(timing=True)
+    ms_instr = timed(lambda i: eager_step(*resident[i % nbuf]), args.steps)
+    per_kernel = ops.LOG.summary()
+    # (2) launches per step and the optimizer alone (SURVEY §8d metric i): the eager step with and without the Adam update
+    ops.LOG.reset(timing=False)
+    ms_eager = timed(lambda i: eager_step(*resident[i % nbuf]), args.steps)
+    launches = ops.LOG.launches
+    ms_noopt = timed(lambda i: eager_step(*resident[i % nbuf], update=False), args.steps)
+    # (3) the FP32-accurate gradient setting
+    ms3 = None
+    if world == 1 and not args.no_extras:
+        old = ops.GRAD_NSPLIT
+        try:
+            ops.GRAD_NSPLIT = 3
+            for i in range(3):
+                eager_step(*resident[i % nbuf])
+            ms3 = timed(lambda i: eager_step(*resident[i % nbuf]), args.steps)
+        finally:
+            ops.GRAD_NSPLIT = old
+
+    # ---- CUDA graph of the step (one launch per step instead of ~220 kernel launches); with a gradient exchange (N > 1)
+    # the graph covers forward + criterion + backward and the all-reduce + Adam stay eager --------------------------------
+    graphed = None
+    if not args.no_graph:
+        graphs = __import__(entry.PKG_NAME + ".graphs", fromlist=["x"])
+        try:
+            if world == 1:
+                graphed = graphs.GraphedTrainStep(lambda x, y, m: eager_step(x, y, m), resident[0])
+                step = lambda x, y, m: graphed.run(x, y, m)
+            else:
+                def fwd_bwd(x, y, m):
+                    bucket.zero()
+                    loss = ops.seg_loss(model(x), y, m)
+                    loss.backward()
+                    return loss
+                graphed = graphs.GraphedTrainStep(fwd_bwd, resident[0])
+
+                def step(x, y, m):
+                    loss = graphed.run(x, y, m)
+                    bucket.all_reduce_mean()
+                    opt.step()
+                    return loss
+        except Exception as e:               # capture problems must not cost the bench line: fall back to eager launches
+            print(f"warning: CUDA graph capture failed ({e!r}); eager launches", file=sys.stderr)
+            torch.cuda.synchronize()
+            step, graphed = eager_step, None
+        for i in range(3):
+            step(*resident[i % nbuf])
+
     # ---- device-resident throughput: no per-call instrumentation inside this region ---------------------------------
     sampler = ClockSampler(local)
     sampler.start()
-    ops.LOG.reset(timing=False)
     ms = timed(lambda i: step(*resident[i % nbuf]), args.steps)
-    launches = ops.LOG.launches
     clocks = sampler.stop()
     points = B_PER_GPU * NPTS * world * args.steps
     value = points / (ms * 1e-3)
 
     # ---- end-to-end through the public API with host buffers ------------------------------------------
+    # Every step copies ONE batch from pinned host memory and reads its loss back.  The copy of batch i+1 is issued on a
+    # copy stream before the loss of step i is read (double buffering, what a DataLoader with pin_memory does), so it
+    # overlaps the tail of step i instead of serialising with the read-back.
+    copy_stream = torch.cuda.Stream(device=dev)
+    staged = {}
+
+    def stage(i):
+        with torch.cuda.stream(copy_stream):
+            xh, yh, mh = host[i % nbuf]
+            t = (xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True), mh.to(dev, non_blocking=True))
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        staged[i] = (t, ev)
+
     def e2e_step(i):
-        xh, yh, mh = host[i % nbuf]
-        x = xh.to(dev, non_blocking=True)
-        y = yh.to(dev, non_blocking=True)
-        m = mh.to(dev, non_blocking=True)
-        loss = step(x, y, m)
+        if i not in staged:
+            stage(i)
+        (x, y, m), ev = staged.pop(i)
+        torch.cuda.current_stream(dev).wait_event(ev)
+        for t in (x, y, m):
+            t.record_stream(torch.cuda.current_stream(dev))
+        loss = step(x, y, m)                 # (graph replay: device-to-device copy into the static inputs, then one launch)
+        stage(i + 1)                         # H2D of the next batch, inside this step's timed region
         return float(loss.item())            # D2H read of the step's result
 
     e2e_step(0)
+    staged.clear()
     ms_e2e = timed(e2e_step, args.steps)
+    staged.clear()
     e2e_value = points / (ms_e2e * 1e-3)
-
-    # ---- separate instrumented pass: per-entry-point device time (CUDA event pairs around every C-ABI call) ------------
-    ops.LOG.reset(timing=True)
-    ms_instr = timed(lambda i: step(*resident[i % nbuf]), args.steps)
-    per_kernel = ops.LOG.summary()
-    ops.LOG.reset(timing=False)
-    # ---- optimizer alone (SURVEY §8d metric i): the same step without the Adam update --------------------------------
-    ms_noopt = timed(lambda i: step(*resident[i % nbuf], update=False), args.steps)
 
     if rank != 0:
         return
@@ -442,17 +505,10 @@ def run_ours(args, rank: int, local: int, world: int):
     extras = None
     if world == 1 and not args.no_extras:
         extras = {"layers_us": layer_times(pkg, dev)}
-        old = ops.GRAD_NSPLIT
-        try:
-            ops.GRAD_NSPLIT = 3
-            for i in range(3):
-                step(*resident[i % nbuf])
-            ms3 = timed(lambda i: step(*resident[i % nbuf]), args.steps)
-            extras["grad_nsplit3"] = {"ms_per_step": ms3 / args.steps, "value": points / (ms3 * 1e-3), "unit": UNIT,
-                                      "what": "same step with every gradient GEMM on 3 bf16 planes (FP32-accurate, 6 MMAs per product) "
-                                              "and the conv_b backward on the FP32-FMA kernel; the headline uses 2 planes (2^-17) there"}
-        finally:
-            ops.GRAD_NSPLIT = old
+        extras["grad_nsplit3"] = {"ms_per_step": ms3 / args.steps, "value": points / (ms3 * 1e-3), "unit": UNIT,
+                                  "what": "the eagerly launched step with every gradient GEMM on 3 bf16 planes (FP32-accurate, 6 MMAs per "
+                                          "product) and the conv_b backward on the FP32-FMA kernel; compare optimizer.ms_per_step_eager "
+                                          "(2 planes, 2^-17, eager launches)"}
         extras["torch_eager_gpu"] = eager_gpu_oracle(dev)
 
     # ---- CPU baseline (bounded sample) -------------------------------------------------------------------
@@ -473,11 +529,13 @@ def run_ours(args, rank: int, local: int, world: int):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
+        "cuda_graph": graphed is not None,
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,
-        "optimizer": {"ms_per_step": max(ms - ms_noopt, 0.0) / args.steps, "what": "fused Adam (train.py:118): step time minus the same step without opt.step()",
-                      "ms_per_step_without": ms_noopt / args.steps},
+        "optimizer": {"ms_per_step": max(ms_eager - ms_noopt, 0.0) / args.steps,
+                      "what": "fused Adam (train.py:118): eagerly launched step time minus the same step without opt.step()",
+                      "ms_per_step_eager": ms_eager / args.steps, "ms_per_step_eager_without": ms_noopt / args.steps},
         "kernels": breakdown,
         "kernels_pass_ms_per_step": ms_instr / args.steps,
         "extras": extras,
@@ -577,6 +635,7 @@ def main():
     ap.add_argument("--workload", default="train", choices=["train", "infer"],
                     help="train = BASELINE configs[1]/[2] (the headline metric); infer = configs[3], sharded tile inference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-layer timings, the nsplit=3 step and the eager-GPU oracle run")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
