@@ -49,6 +49,10 @@ SIGNATURES = {
     "dgcnn_edgeconv_bwd_a": (c_int, [_ARGS, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "dgcnn_edgeconv_lin_extrema": (c_int, [_ARGS, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P]),
     "dgcnn_edgeconv_lin_conv_a": (c_int, [_ARGS, _P, c_int, _P, c_int, _P, _P, _P]),
+    "dgcnn_edgeconv_lin_conv_a_train": (c_int, [_ARGS, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P]),
+    "dgcnn_edgeconv_bwd_b_fused": (c_int, [_ARGS, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
+    "dgcnn_edgeconv_bwd_a_point_stats": (c_int, [c_int, _P, c_int, _P, c_int, _P, _P, c_int, _P, _P]),
+    "dgcnn_edgeconv_bwd_a_point_apply": (c_int, [c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P]),
     "dgcnn_edgeconv_bwd_a_lin": (c_int, [_ARGS, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "dgcnn_tc_gemm_colstats_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "dgcnn_tc_gemm_bn_lrelu_segmax_f32": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P,

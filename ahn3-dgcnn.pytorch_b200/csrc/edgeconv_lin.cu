@@ -23,7 +23,8 @@ template <bool STORE_Y>
 __global__ void __launch_bounds__(kThreads)
 ec_lin_extrema_kernel(const float* __restrict__ U, int ld_u, const float* __restrict__ V, int ld_v, const int32_t* __restrict__ idx,
                       int M, int N, int k, float* __restrict__ ymax, float* __restrict__ ymin, uint8_t* __restrict__ amax,
-                      uint8_t* __restrict__ amin, float* __restrict__ y_out, double* __restrict__ partials) {
+                      uint8_t* __restrict__ amin, float* __restrict__ y_out, double* __restrict__ partials,
+                      float* __restrict__ ysum, float* __restrict__ yin, float* __restrict__ cnt) {
   __shared__ float4 red[2][kThreads];
   const int c4 = threadIdx.x & 15, pl = threadIdx.x >> 4;
   const int c = 4 * c4;
@@ -42,6 +43,10 @@ ec_lin_extrema_kernel(const float* __restrict__ U, int ld_u, const float* __rest
       y.x = __fadd_rn(u.x, v.x); y.y = __fadd_rn(u.y, v.y); y.z = __fadd_rn(u.z, v.z); y.w = __fadd_rn(u.w, v.w);
       if (STORE_Y) {
         *reinterpret_cast<float4*>(y_out + (static_cast<size_t>(gp) * k + slot) * kCout + c) = y;
+        if (yin) {      // graph-structure sums of the backward (see dgcnn_edgeconv_bwd_a_point): sum of y over the in-edges of j
+          atomicAdd(reinterpret_cast<float4*>(yin + (base + nb[slot]) * kCout + c), y);
+          if (c4 == 0) atomicAdd(cnt + base + nb[slot], 1.f);
+        }
       } else {
         // first occurrence wins ties, like the per-edge kernels
         if (y.x > mx.x) { mx.x = y.x; ax.x = slot; }
@@ -57,6 +62,7 @@ ec_lin_extrema_kernel(const float* __restrict__ U, int ld_u, const float* __rest
       s2.x = __fmaf_rn(y.x, y.x, s2.x); s2.y = __fmaf_rn(y.y, y.y, s2.y);
       s2.z = __fmaf_rn(y.z, y.z, s2.z); s2.w = __fmaf_rn(y.w, y.w, s2.w);
     }
+    if (STORE_Y && ysum) *reinterpret_cast<float4*>(ysum + static_cast<size_t>(gp) * kCout + c) = s1;   // sum over the out-edges of gp
     if (!STORE_Y) {
       const size_t o = static_cast<size_t>(gp) * kCout + c;
       *reinterpret_cast<float4*>(ymax + o) = mx;
@@ -153,22 +159,34 @@ extern "C" int dgcnn_edgeconv_lin_extrema(const dgcnn_edgeconv_args* a, const fl
   const int M = a->B * a->N;
   const int blocks = std::max(1, std::min((M + 15) / 16, std::min(kMaxPartialCtas, 8 * std::max(1, num_sms()))));
   ec_lin_extrema_kernel<false><<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(U, ld_u, V, ld_v, a->idx, M, a->N, a->k, ymax,
-                                                                                         ymin, amax, amin, nullptr, partials);
+                                                                                         ymin, amax, amin, nullptr, partials, nullptr, nullptr, nullptr);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}
+
+static int lin_conv_a(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v, float* y_a, double* partials,
+                      float* ysum, float* yin, float* cnt, void* stream, const char* who) {
+  int rc = lin_check(a, U, ld_u, V, ld_v, who);
+  if (rc) return rc;
+  DG_REQUIRE(y_a && partials && (reinterpret_cast<uintptr_t>(y_a) & 15) == 0, DGCNN_E_INVALID, "%s: null / misaligned output", who);
+  const int M = a->B * a->N;
+  const int blocks = std::max(1, std::min((M + 15) / 16, std::min(kMaxPartialCtas, 8 * std::max(1, num_sms()))));
+  ec_lin_extrema_kernel<true><<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(U, ld_u, V, ld_v, a->idx, M, a->N, a->k, nullptr,
+                                                                                        nullptr, nullptr, nullptr, y_a, partials, ysum, yin, cnt);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
 }
 
 extern "C" int dgcnn_edgeconv_lin_conv_a(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
                                          float* y_a, double* partials, void* stream) {
-  int rc = lin_check(a, U, ld_u, V, ld_v, "edgeconv_lin_conv_a");
-  if (rc) return rc;
-  DG_REQUIRE(y_a && partials && (reinterpret_cast<uintptr_t>(y_a) & 15) == 0, DGCNN_E_INVALID, "edgeconv_lin_conv_a: null / misaligned output");
-  const int M = a->B * a->N;
-  const int blocks = std::max(1, std::min((M + 15) / 16, std::min(kMaxPartialCtas, 8 * std::max(1, num_sms()))));
-  ec_lin_extrema_kernel<true><<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(U, ld_u, V, ld_v, a->idx, M, a->N, a->k, nullptr,
-                                                                                        nullptr, nullptr, nullptr, y_a, partials);
-  DG_CUDA(cudaGetLastError());
-  return DGCNN_OK;
+  return lin_conv_a(a, U, ld_u, V, ld_v, y_a, partials, nullptr, nullptr, nullptr, stream, "edgeconv_lin_conv_a");
+}
+
+extern "C" int dgcnn_edgeconv_lin_conv_a_train(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
+                                               float* y_a, double* partials, float* ysum, float* yin, float* cnt, void* stream) {
+  DG_REQUIRE(ysum && yin && cnt && ((reinterpret_cast<uintptr_t>(ysum) | reinterpret_cast<uintptr_t>(yin)) & 15) == 0, DGCNN_E_INVALID,
+             "edgeconv_lin_conv_a_train: ysum / yin / cnt must be non-null, ysum and yin 16-byte aligned");
+  return lin_conv_a(a, U, ld_u, V, ld_v, y_a, partials, ysum, yin, cnt, stream, "edgeconv_lin_conv_a_train");
 }
 
 extern "C" int dgcnn_edgeconv_bwd_a_lin(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,

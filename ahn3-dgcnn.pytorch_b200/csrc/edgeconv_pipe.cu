@@ -150,14 +150,15 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ec_pipe_conv_b_kernel(const E
   } else if (warp == kPipeMmaWarp) {
     // =========================================== MMA issuer ===========================================================
     constexpr uint32_t idesc = tc::idesc_bf16(128, 64);
+    const bool leader = tc::elect_one();     // uniform control flow + elect.sync: the issue code stays on the uniform datapath
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += grid, ++it) {
       const int b = it & 1;
       const uint32_t u = static_cast<uint32_t>(it) >> 1;
-      if (lane == 0) {
-        mbar_wait_wd(&a_full[b], u & 1u);
-        mbar_wait_wd(&acc_free[b], (u & 1u) ^ 1u);
-        tc::fence_after_sync();
+      mbar_wait_wd(&a_full[b], u & 1u);
+      mbar_wait_wd(&acc_free[b], (u & 1u) ^ 1u);
+      tc::fence_after_sync();
+      if (leader) {
         tc::mma_split_katom<3>(taddr + b * 64, tc::smem_u32(Ap + b * kBufA), kPlA, tc::smem_u32(Wp), kPlW, idesc, true);
         tc::mma_commit(&a_free[b]);
         tc::mma_commit(&acc_full[b]);

@@ -633,17 +633,22 @@ __global__ void __launch_bounds__(256) ec_tc_dw_finish_kernel(const float* __res
   dw[o] = static_cast<float>(static_cast<double>(T[o]) - static_cast<double>(coef_b[128 + c]) * a);
 }
 
+int launch_ec_dw_finish(const float* dw_partials, int nparts, const float* w_b, const float* coef_b, float* dw_b, cudaStream_t st) {
+  float* T = const_cast<float*>(dw_partials) + static_cast<size_t>(kMaxPartialCtas) * 2 * kCout * kCout;
+  ec_tc_dw_sum_kernel<<<2 * kCout * kCout / 32, 256, 0, st>>>(dw_partials, nparts, T);
+  ec_tc_dw_finish_kernel<<<(kCout * kCout + 255) / 256, 256, 0, st>>>(T, w_b, coef_b, dw_b);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}
+
 int launch_ec_tc_bwd_b(const EcK& p, const float* g, const uint8_t* arg, const float* coef_b, float* dz_a,
                        float* dw_partials, float* dw_b, int grid, cudaStream_t st) {
   DG_REQUIRE((reinterpret_cast<uintptr_t>(p.y_a_in) & 31) == 0 && (reinterpret_cast<uintptr_t>(dz_a) & 31) == 0, DGCNN_E_INVALID,
              "edgeconv_bwd_b (tensor-core path): y_a and dz_a must be 32-byte aligned");
   DG_CUDA(cudaFuncSetAttribute(ec_tc_bwd_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcTcBwdSmem::bytes)));
   ec_tc_bwd_b_kernel<<<grid, kThreads, EcTcBwdSmem::bytes, st>>>(p, g, arg, coef_b, dz_a, dw_partials);
-  float* T = dw_partials + static_cast<size_t>(kMaxPartialCtas) * 2 * kCout * kCout;
-  ec_tc_dw_sum_kernel<<<2 * kCout * kCout / 32, 256, 0, st>>>(dw_partials, grid, T);
-  ec_tc_dw_finish_kernel<<<(kCout * kCout + 255) / 256, 256, 0, st>>>(T, p.w_b, coef_b, dw_b);
   DG_CUDA(cudaGetLastError());
-  return DGCNN_OK;
+  return launch_ec_dw_finish(dw_partials, grid, p.w_b, coef_b, dw_b, st);
 }
 
 int launch_ec_tc_fwd(const EcK& p, int mode, int grid, cudaStream_t st) {

@@ -21,6 +21,7 @@ from . import _lib
 COUT = 64
 TC_KNN_MIN_N = 256       # below this every key is a candidate anyway and the exact tile kernel is as fast
 EDGECONV_IMPL = 0        # dgcnn_edgeconv_args.impl: 0 = default (pipelined tcgen05), 1 = FP32 FMA, 2 = serial tcgen05 (A/B checks)
+FUSED_BWD = True         # two-conv blocks: conv_b backward with the scatter fused in (no dz_a[E,64]); False = the two-pass kernels
 # bf16 planes per operand in the GRADIENT GEMMs (forward GEMMs always use 3 = FP32-accurate).  2 = 3 MMAs per product,
 # relative error ~2^-17; 3 = 6 MMAs, ~2^-24 like the forward.  DGCNN_GRAD_NSPLIT overrides; bench.py reports both.
 GRAD_NSPLIT = int(os.environ.get("DGCNN_GRAD_NSPLIT", "2"))
@@ -551,14 +552,22 @@ class EdgeConvTrain(torch.autograd.Function):
         vs = None if (lin or EDGECONV_IMPL == 0) else _v_scratch(B, Cn, N, dev)
         a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, None, COUT, vs)
 
-        uv = uv2 = None
+        uv = uv2 = fused = None
         if two and EDGECONV_IMPL == 0:
             # first conv of a two-conv block: y_a = U_j + V_i written per edge (BN_a needs batch statistics before conv_b
             # can start), no per-edge GEMM.  Also for the input block: y_a carries the centre term Wa2 x_i (~|W||x|) either
             # way, so forming x_j - x_i first buys no accuracy at the level of y_a (both are within a few 1e-8 |W||x|).
             uv2 = tc_gemm(rows[:, :Cn], _lin_weight(wa, Cn))
-            _call("dgcnn_edgeconv_lin_conv_a", dev, C.byref(a), _ptr(uv2), uv2.stride(0), _ptr(uv2[:, COUT:]), uv2.stride(0), _ptr(y_a),
-                  _ptr(partials))
+            if FUSED_BWD and GRAD_NSPLIT == 2 and k >= 8:
+                # + the graph sums of y_a (out-edge sums, in-edge sums, in-degrees): with them the backward never forms dz_a[E,64]
+                ysum = torch.empty(M, COUT, **f32)
+                zin = torch.zeros(M * COUT + M, **f32)
+                fused = (ysum, zin[:M * COUT].view(M, COUT), zin[M * COUT:])
+                _call("dgcnn_edgeconv_lin_conv_a_train", dev, C.byref(a), _ptr(uv2), uv2.stride(0), _ptr(uv2[:, COUT:]), uv2.stride(0),
+                      _ptr(y_a), _ptr(partials), _ptr(fused[0]), _ptr(fused[1]), _ptr(fused[2]))
+            else:
+                _call("dgcnn_edgeconv_lin_conv_a", dev, C.byref(a), _ptr(uv2), uv2.stride(0), _ptr(uv2[:, COUT:]), uv2.stride(0), _ptr(y_a),
+                      _ptr(partials))
         elif lin:
             # y = U_j + V_i: one point-level GEMM + a gather pass (extrema over k, batch sums); nothing per-edge in HBM
             uv = tc_gemm(rows[:, :Cn], _lin_weight(wa, Cn))
@@ -584,6 +593,7 @@ class EdgeConvTrain(torch.autograd.Function):
         ctx.meta = meta
         ctx.two = two
         ctx.lin = lin
+        ctx.fused = fused
         ctx.uv2 = uv2                                   # [U | V] of a two-conv block: the backward gathers it instead of re-reading y_a
         ctx.save_for_backward(rows, idx, wa, wb if two else wa, gamma_a.detach(), gamma_b.detach() if two else gamma_a.detach(),
                               uv if lin else y_a, stat_a, stat_b if two else stat_a, ysel, arg)
@@ -615,29 +625,48 @@ class EdgeConvTrain(torch.autograd.Function):
         _call("dgcnn_bn_bwd_reduce", dev, _ptr(partials), COUT, float(E), _ptr(gamma_last), _ptr(last[0]), _ptr(last[1]),
                                            _ptr(dgl[0]), _ptr(dgl[1]), _ptr(coef_l))
         dw_b = dga = None
-        if two:
-            dz_a = torch.empty(E, COUT, **f32)
+        rs = torch.zeros(M, 2 * COUT, **f32)            # [ r | s ]: scatter target and per-point sums, one GEMM operand
+        r, s = rs[:, :COUT], rs[:, COUT:]
+        fused = ctx.fused if (two and GRAD_NSPLIT == 2) else None
+        ctx.fused = None
+        if fused is not None:
+            # conv_b backward with the scatter fused in (raw in-edge sums -> r, out-edge sums -> s), then BN_a's backward
+            # per POINT: its batch sums from U, V, r, s and the affine map with the forward's graph sums of y_a
+            uv = ctx.uv2
             dw_b = torch.empty(COUT, COUT, **f32)
-            # the tensor-core conv_b backward is a 2-plane (2^-17) kernel: the FP32-accurate setting takes the FP32-FMA one
-            ab = a if GRAD_NSPLIT == 2 else _args(rows, ctx.ld, idx, B, Cn, N, k, wa, wb, None, COUT, impl=1)
-            _call("dgcnn_edgeconv_bwd_b", dev, C.byref(ab), _ptr(y_a), _ptr(stat_a[2:]), _ptr(g), _ptr(arg), _ptr(coef_l),
-                                                _ptr(dz_a), _ptr(dw_b), _ptr(partials), _ptr(dw_partials))
+            _call("dgcnn_edgeconv_bwd_b_fused", dev, C.byref(a), _ptr(y_a), _ptr(stat_a[2:]), _ptr(g), _ptr(arg), _ptr(coef_l),
+                  _ptr(r), _ptr(s), 2 * COUT, _ptr(dw_b), _ptr(dw_partials))
+            _call("dgcnn_edgeconv_bwd_a_point_stats", dev, M, _ptr(uv), uv.stride(0), _ptr(uv[:, COUT:]), uv.stride(0), _ptr(r), _ptr(s),
+                  2 * COUT, _ptr(partials))
             dga = torch.empty(2, COUT, **f32)
             coef_a = torch.empty(3, COUT, **f32)
             _call("dgcnn_bn_bwd_reduce", dev, _ptr(partials), COUT, float(E), _ptr(gamma_a), _ptr(stat_a[0]), _ptr(stat_a[1]),
                                                _ptr(dga[0]), _ptr(dga[1]), _ptr(coef_a))
-        else:
-            dz_a, coef_a, dga = None, coef_l, dgl
-        rs = torch.zeros(M, 2 * COUT, **f32)            # [ r | s ]: scatter target and per-point sums, one GEMM operand
-        r, s = rs[:, :COUT], rs[:, COUT:]
-        if ctx.lin or ctx.uv2 is not None:
-            uv = y_a if ctx.lin else ctx.uv2            # [U | V] (saved in y_a's place for the single-conv block)
-            _call("dgcnn_edgeconv_bwd_a_lin", dev, C.byref(a), _ptr(uv), uv.stride(0), _ptr(uv[:, COUT:]), uv.stride(0), _ptr(dz_a),
-                  _ptr(g), _ptr(arg), _ptr(coef_a), _ptr(s), _ptr(r), 2 * COUT)
+            _call("dgcnn_edgeconv_bwd_a_point_apply", dev, M, k, _ptr(r), _ptr(s), 2 * COUT, _ptr(fused[1]), _ptr(fused[0]),
+                  _ptr(fused[2]), _ptr(coef_a))
             ctx.uv2 = None
         else:
-            _call("dgcnn_edgeconv_bwd_a", dev, C.byref(a), _ptr(y_a), _ptr(dz_a), _ptr(g), _ptr(arg), _ptr(coef_a),
-                  _ptr(s), _ptr(r), 2 * COUT)
+            if two:
+                dz_a = torch.empty(E, COUT, **f32)
+                dw_b = torch.empty(COUT, COUT, **f32)
+                # the tensor-core conv_b backward is a 2-plane (2^-17) kernel: the FP32-accurate setting takes the FP32-FMA one
+                ab = a if GRAD_NSPLIT == 2 else _args(rows, ctx.ld, idx, B, Cn, N, k, wa, wb, None, COUT, impl=1)
+                _call("dgcnn_edgeconv_bwd_b", dev, C.byref(ab), _ptr(y_a), _ptr(stat_a[2:]), _ptr(g), _ptr(arg), _ptr(coef_l),
+                                                    _ptr(dz_a), _ptr(dw_b), _ptr(partials), _ptr(dw_partials))
+                dga = torch.empty(2, COUT, **f32)
+                coef_a = torch.empty(3, COUT, **f32)
+                _call("dgcnn_bn_bwd_reduce", dev, _ptr(partials), COUT, float(E), _ptr(gamma_a), _ptr(stat_a[0]), _ptr(stat_a[1]),
+                                                   _ptr(dga[0]), _ptr(dga[1]), _ptr(coef_a))
+            else:
+                dz_a, coef_a, dga = None, coef_l, dgl
+            if ctx.lin or ctx.uv2 is not None:
+                uv = y_a if ctx.lin else ctx.uv2            # [U | V] (saved in y_a's place for the single-conv block)
+                _call("dgcnn_edgeconv_bwd_a_lin", dev, C.byref(a), _ptr(uv), uv.stride(0), _ptr(uv[:, COUT:]), uv.stride(0), _ptr(dz_a),
+                      _ptr(g), _ptr(arg), _ptr(coef_a), _ptr(s), _ptr(r), 2 * COUT)
+                ctx.uv2 = None
+            else:
+                _call("dgcnn_edgeconv_bwd_a", dev, C.byref(a), _ptr(y_a), _ptr(dz_a), _ptr(g), _ptr(arg), _ptr(coef_a),
+                      _ptr(s), _ptr(r), 2 * COUT)
         # point-level GEMMs on the tensor cores (bf16x2 split: gradient path):
         #   dX  = r Wa1 + s (Wa2 - Wa1)            = [r|s] @ [Wa1 ; Wa2-Wa1]
         #   dWa = [(r - s)^T X | s^T X]            from G = [r|s]^T X  (contraction over the points, split-K)

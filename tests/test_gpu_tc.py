@@ -137,9 +137,10 @@ def test_edgeconv_tc_matches_ffma_path(pkg, N, k):
     x = common.points(51, B, Fd, N, "real").to(DEV)
     w = common.weights(52, 5, Fd, 1024)
     outs = {}
-    for tcflag, impl in ((0, 1), (1, 2), (2, 0)):   # FP32 FMA, serial tcgen05 kernels, default (pipelined) — dgcnn_edgeconv_args.impl
-        old = pkg.ops.EDGECONV_IMPL
-        pkg.ops.EDGECONV_IMPL = impl
+    # FP32 FMA, serial tcgen05 kernels, default (pipelined, backward with the fused scatter), default with the two-pass backward
+    for tcflag, impl, fused in ((0, 1, True), (1, 2, True), (2, 0, True), (3, 0, False)):
+        old, oldf = pkg.ops.EDGECONV_IMPL, pkg.ops.FUSED_BWD
+        pkg.ops.EDGECONV_IMPL, pkg.ops.FUSED_BWD = impl, fused
         try:
             net = pkg.DGCNN(5, Fd, k, dropout=0.0, cuda=True)
             net.load_state_dict(w, strict=False)
@@ -151,15 +152,20 @@ def test_edgeconv_tc_matches_ffma_path(pkg, N, k):
             outs[tcflag] = (y.detach(), [p.grad.clone() for p in net.parameters()],
                             [getattr(net, f"bn{i}").running_var.clone() for i in range(1, 6)])
         finally:
-            pkg.ops.EDGECONV_IMPL = old
+            pkg.ops.EDGECONV_IMPL, pkg.ops.FUSED_BWD = old, oldf
     y0, g0, rv0 = outs[0]
-    for flag in (1, 2):
+    for flag in (1, 2, 3):
         y1, g1, rv1 = outs[flag]
         assert ((y0 - y1).abs().max() / y0.abs().max()).item() < 2e-5
         for a, b in zip(rv0, rv1):
             torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
         for a, b in zip(g0, g1):
             assert ((a - b).norm() / (a.norm() + 1e-30)).item() < 5e-3      # gradient noise floor, see test_gpu_parity
+    # fused scatter vs the two-pass backward: same forward, same 2-plane MMAs — only summation order and the point-level
+    # form of BN_a's backward differ
+    assert torch.equal(outs[2][0], outs[3][0])
+    for a, b in zip(outs[2][1], outs[3][1]):
+        assert ((a - b).norm() / (a.norm() + 1e-30)).item() < 3e-4, ((a - b).norm() / (a.norm() + 1e-30)).item()
 
 
 # ---------------------------------------------------------------------------------------------- plane-level GEMMs
