@@ -49,8 +49,8 @@ SIGNATURES = {
     "dgcnn_edgeconv_bwd_a": (c_int, [_ARGS, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "dgcnn_edgeconv_lin_extrema": (c_int, [_ARGS, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P]),
     "dgcnn_edgeconv_lin_conv_a": (c_int, [_ARGS, _P, c_int, _P, c_int, _P, _P, _P]),
-    "dgcnn_edgeconv_lin_conv_a_train": (c_int, [_ARGS, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P]),
-    "dgcnn_edgeconv_bwd_b_fused": (c_int, [_ARGS, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
+    "dgcnn_edgeconv_lin_conv_a_train": (c_int, [_ARGS, _P, c_int, _P, c_int, _P, _P, _P, _P]),
+    "dgcnn_edgeconv_bwd_b_fused": (c_int, [_ARGS, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P]),
     "dgcnn_edgeconv_bwd_a_point_stats": (c_int, [c_int, _P, c_int, _P, c_int, _P, _P, c_int, _P, _P]),
     "dgcnn_edgeconv_bwd_a_point_apply": (c_int, [c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P]),
     "dgcnn_edgeconv_bwd_a_lin": (c_int, [_ARGS, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, c_int, _P]),

@@ -748,19 +748,20 @@ extern "C" int dgcnn_edgeconv_bwd_b(const dgcnn_edgeconv_args* a, const float* y
 }
 
 extern "C" int dgcnn_edgeconv_bwd_b_fused(const dgcnn_edgeconv_args* a, const float* y_a, const float* aff_a, const float* g,
-                                          const uint8_t* arg, const float* coef_b, float* r_raw, float* s_raw, int ld_rs, float* dw_b,
-                                          float* dw_partials, void* stream) {
+                                          const uint8_t* arg, const float* coef_b, float* r_raw, float* s_raw, int ld_rs, float* yin,
+                                          float* cnt, float* dw_b, float* dw_partials, void* stream) {
   EcK p;
   int rc = fill_common(a, p, "edgeconv_bwd_b_fused");
   if (rc) return rc;
-  DG_REQUIRE(a->idx && a->w_b && y_a && aff_a && g && arg && coef_b && r_raw && s_raw && dw_b && dw_partials, DGCNN_E_INVALID,
-             "edgeconv_bwd_b_fused: null pointer");
+  DG_REQUIRE(a->idx && a->w_b && y_a && aff_a && g && arg && coef_b && r_raw && s_raw && yin && cnt && dw_b && dw_partials,
+             DGCNN_E_INVALID, "edgeconv_bwd_b_fused: null pointer");
+  DG_REQUIRE(a->N >= kMaxP, DGCNN_E_UNSUPPORTED, "edgeconv_bwd_b_fused: N >= 16 (a tile spans at most two clouds)");
   DG_REQUIRE(((reinterpret_cast<uintptr_t>(y_a) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(arg) |
-               reinterpret_cast<uintptr_t>(r_raw)) & 15) == 0 && ld_rs >= kCout && ld_rs % 4 == 0,
-             DGCNN_E_INVALID, "edgeconv_bwd_b_fused: y_a, g, arg, r_raw need 16-byte alignment; ld_rs %% 4 == 0, ld_rs >= 64");
+               reinterpret_cast<uintptr_t>(r_raw) | reinterpret_cast<uintptr_t>(yin)) & 15) == 0 && ld_rs >= kCout && ld_rs % 4 == 0,
+             DGCNN_E_INVALID, "edgeconv_bwd_b_fused: y_a, g, arg, r_raw, yin need 16-byte alignment; ld_rs %% 4 == 0, ld_rs >= 64");
   DG_REQUIRE(a->k >= 8, DGCNN_E_UNSUPPORTED, "edgeconv_bwd_b_fused: k >= 8 (a thread's 8 consecutive edge rows span at most two points)");
   p.y_a_in = y_a; p.aff_a = aff_a;
-  return launch_ec_pipe_bwd_b(p, g, arg, coef_b, r_raw, s_raw, ld_rs, dw_partials, dw_b, num_sms(), static_cast<cudaStream_t>(stream));
+  return launch_ec_pipe_bwd_b(p, g, arg, coef_b, r_raw, s_raw, ld_rs, yin, cnt, dw_partials, dw_b, num_sms(), static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dgcnn_edgeconv_bwd_a_point_stats(int M, const float* U, int ld_u, const float* V, int ld_v, const float* r_raw,

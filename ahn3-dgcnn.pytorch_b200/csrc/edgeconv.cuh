@@ -35,7 +35,7 @@ int launch_ec_tc_bwd_b(const EcK& p, const float* g, const uint8_t* arg, const f
 int launch_ec_dw_finish(const float* dw_partials, int nparts, const float* w_b, const float* coef_b, float* dw_b, cudaStream_t st);
 // pipelined conv_b backward with the fused scatter + the point-level finish of the BN_a backward (edgeconv_bwd_pipe.cu)
 int launch_ec_pipe_bwd_b(const EcK& p, const float* g, const uint8_t* arg, const float* coef_b, float* r_raw, float* s_raw, int ld_rs,
-                         float* dw_partials, float* dw_b, int sms, cudaStream_t st);
+                         float* yin, float* cnt, float* dw_partials, float* dw_b, int sms, cudaStream_t st);
 int launch_ec_bwd_point_stats(const float* U, int ld_u, const float* V, int ld_v, const float* R, const float* S, int ld_rs, int M,
                               double* partials, cudaStream_t st);
 int launch_ec_bwd_point_apply(float* R, float* S, int ld_rs, const float* yin, const float* ysum, const float* cnt, const float* coef_a,

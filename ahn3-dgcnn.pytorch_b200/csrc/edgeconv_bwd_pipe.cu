@@ -13,7 +13,8 @@
 //     r_j = cA' R_j - cnt_j cB' - cC' Yin_j,     R_j  = sum_in  dz_a,   Yin_j  = sum_in  y_a,   cnt_j = in-degree
 //     s_i = cA' S_i - k     cB' - cC' Ysum_i,    S_i  = sum_out dz_a,   Ysum_i = sum_out y_a
 //     sum dz_a     = sum_i S_i,          sum dz_a*y_a = sum_j U_j.R_j + sum_i V_i.S_i        (per channel)
-// Yin / Ysum / cnt depend on the graph only and come out of the forward conv_a pass (dgcnn_edgeconv_lin_conv_a_train).
+// Ysum comes out of the forward conv_a pass (dgcnn_edgeconv_lin_conv_a_train); Yin and cnt are accumulated here, by the
+// converter warps, from the y_a values that pass through their registers anyway.
 // So this kernel scatters the RAW dz_a rows (float reductions into the L2-resident [M,64] targets R and S) and three
 // point-level kernels (14 MB each) finish the job; dz_a[E,64] (430 MB at the training shape, written here and read back
 // by ec_lin_bwd_a_kernel<true> in the two-pass form) no longer exists.
@@ -65,7 +66,8 @@ __device__ __forceinline__ void red_add_v4(float* dst, const float4& v) {
 
 __global__ void __launch_bounds__(kBpThreads, 1)
 ec_pipe_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __restrict__ arg, const float* __restrict__ coef_b,
-                     float* __restrict__ r_raw, float* __restrict__ s_raw, int ld_rs, float* __restrict__ dw_partials) {
+                     float* __restrict__ r_raw, float* __restrict__ s_raw, int ld_rs, float* __restrict__ dw_partials,
+                     float* __restrict__ yin, float* __restrict__ cnt) {
   extern __shared__ __align__(1024) unsigned char sm[];
   unsigned char* Dp = sm + EcBpSmem::d_off;
   unsigned char* Hp = sm + EcBpSmem::h_off;
@@ -171,12 +173,35 @@ ec_pipe_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __
     uint32_t prev[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};   // byte offsets of the previous tile's patches
     // 16-byte pieces of the chunk in an order that keeps the 8 lanes of a row on 8 different bank groups
     const int first = (ch >= 4) ? 4 : 0, second = 4 - first;
+    // Yin_j += y_a rows, cnt_j += 1 (the in-edge sums of y_a and the in-degrees that BN_a's backward needs per point): done
+    // here, from the registers the raw tile passes through.  The forward conv_a pass, where y_a is produced, is bound by L2
+    // throughput; this kernel leaves it unused.  Neighbour indices are fetched one tile ahead.
+    int ppj[4], jn[4];
+    {
+      const int nv0 = min(P, M - static_cast<int>(blockIdx.x) * P) * k;
+      const size_t en = static_cast<size_t>(blockIdx.x) * P * k;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ppj[j] = (rb + 32 * j) / k;
+        jn[j] = (rb + 32 * j < nv0) ? p.idx[en + rb + 32 * j] : 0;
+      }
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += grid, ++it) {
       const int b = it & 1;
       const uint32_t u = static_cast<uint32_t>(it) >> 1;
       const int pv = min(P, M - tile * P);
       const int nvalid = pv * k;
+      int jc[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) jc[j] = jn[j];
+      if (tile + grid < p.num_tiles) {
+        const int nvn = min(P, M - (tile + grid) * P) * k;
+        const size_t en = static_cast<size_t>(tile + grid) * P * k;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) jn[j] = (rb + 32 * j < nvn) ? p.idx[en + rb + 32 * j] : 0;
+      }
+      const int bat0 = (tile * P) / p.N * p.N, bat1 = bat0 + p.N;        // a tile spans at most two clouds (P <= 16 <= N)
       unsigned char* H = Hp + b * kBufH;
       uint8_t* signs = Signs + (it & 3) * (128 * 8);     // read by the epilogue of this tile before it frees the accumulator
       mbar_wait_wd(&a_free[b], (u & 1u) ^ 1u);           // the MMAs that read this H buffer two tiles ago have completed
@@ -193,6 +218,13 @@ ec_pipe_bwd_b_kernel(const EcK p, const float* __restrict__ g, const uint8_t* __
           if (r < nvalid) {
             const float4 q0 = *reinterpret_cast<const float4*>(raw + rl * 64 + ch * 8 + first);
             const float4 q1 = *reinterpret_cast<const float4*>(raw + rl * 64 + ch * 8 + second);
+            {
+              const int gp = tile * P + ppj[2 * hh + j];
+              const size_t jrow = static_cast<size_t>((gp >= bat1 ? bat1 : bat0) + jc[2 * hh + j]);
+              red_add_v4(yin + jrow * kCout + ch * 8 + first, q0);
+              red_add_v4(yin + jrow * kCout + ch * 8 + second, q1);
+              if (ch == 0) atomicAdd(cnt + jrow, 1.f);
+            }
             const float4 lo = first ? q1 : q0, hi = first ? q0 : q1;
             v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
 #pragma unroll
@@ -472,10 +504,10 @@ ec_bwd_point_apply_kernel(float* __restrict__ R, float* __restrict__ S, int ld_r
 }
 
 int launch_ec_pipe_bwd_b(const EcK& p, const float* g, const uint8_t* arg, const float* coef_b, float* r_raw, float* s_raw, int ld_rs,
-                         float* dw_partials, float* dw_b, int sms, cudaStream_t st) {
+                         float* yin, float* cnt, float* dw_partials, float* dw_b, int sms, cudaStream_t st) {
   const int grid = std::max(1, std::min(p.num_tiles, std::min(std::max(1, sms), kMaxPartialCtas)));
   DG_CUDA(cudaFuncSetAttribute(ec_pipe_bwd_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(EcBpSmem::bytes)));
-  ec_pipe_bwd_b_kernel<<<grid, kBpThreads, EcBpSmem::bytes, st>>>(p, g, arg, coef_b, r_raw, s_raw, ld_rs, dw_partials);
+  ec_pipe_bwd_b_kernel<<<grid, kBpThreads, EcBpSmem::bytes, st>>>(p, g, arg, coef_b, r_raw, s_raw, ld_rs, dw_partials, yin, cnt);
   DG_CUDA(cudaGetLastError());
   return launch_ec_dw_finish(dw_partials, grid, p.w_b, coef_b, dw_b, st);
 }

@@ -42,7 +42,7 @@ ec_lin_extrema_kernel(const float* __restrict__ U, int ld_u, const float* __rest
       float4 y;
       y.x = __fadd_rn(u.x, v.x); y.y = __fadd_rn(u.y, v.y); y.z = __fadd_rn(u.z, v.z); y.w = __fadd_rn(u.w, v.w);
       if (STORE_Y) {
-        *reinterpret_cast<float4*>(y_out + (static_cast<size_t>(gp) * k + slot) * kCout + c) = y;
+        __stcs(reinterpret_cast<float4*>(y_out + (static_cast<size_t>(gp) * k + slot) * kCout + c), y);   // streaming: keep U / yin in L2
         if (yin) {      // graph-structure sums of the backward (see dgcnn_edgeconv_bwd_a_point): sum of y over the in-edges of j
           atomicAdd(reinterpret_cast<float4*>(yin + (base + nb[slot]) * kCout + c), y);
           if (c4 == 0) atomicAdd(cnt + base + nb[slot], 1.f);
@@ -183,10 +183,10 @@ extern "C" int dgcnn_edgeconv_lin_conv_a(const dgcnn_edgeconv_args* a, const flo
 }
 
 extern "C" int dgcnn_edgeconv_lin_conv_a_train(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
-                                               float* y_a, double* partials, float* ysum, float* yin, float* cnt, void* stream) {
-  DG_REQUIRE(ysum && yin && cnt && ((reinterpret_cast<uintptr_t>(ysum) | reinterpret_cast<uintptr_t>(yin)) & 15) == 0, DGCNN_E_INVALID,
-             "edgeconv_lin_conv_a_train: ysum / yin / cnt must be non-null, ysum and yin 16-byte aligned");
-  return lin_conv_a(a, U, ld_u, V, ld_v, y_a, partials, ysum, yin, cnt, stream, "edgeconv_lin_conv_a_train");
+                                               float* y_a, double* partials, float* ysum, void* stream) {
+  DG_REQUIRE(ysum && (reinterpret_cast<uintptr_t>(ysum) & 15) == 0, DGCNN_E_INVALID,
+             "edgeconv_lin_conv_a_train: ysum must be non-null and 16-byte aligned");
+  return lin_conv_a(a, U, ld_u, V, ld_v, y_a, partials, ysum, nullptr, nullptr, stream, "edgeconv_lin_conv_a_train");
 }
 
 extern "C" int dgcnn_edgeconv_bwd_a_lin(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,

@@ -558,13 +558,11 @@ class EdgeConvTrain(torch.autograd.Function):
             # can start), no per-edge GEMM.  Also for the input block: y_a carries the centre term Wa2 x_i (~|W||x|) either
             # way, so forming x_j - x_i first buys no accuracy at the level of y_a (both are within a few 1e-8 |W||x|).
             uv2 = tc_gemm(rows[:, :Cn], _lin_weight(wa, Cn))
-            if FUSED_BWD and GRAD_NSPLIT == 2 and k >= 8:
-                # + the graph sums of y_a (out-edge sums, in-edge sums, in-degrees): with them the backward never forms dz_a[E,64]
-                ysum = torch.empty(M, COUT, **f32)
-                zin = torch.zeros(M * COUT + M, **f32)
-                fused = (ysum, zin[:M * COUT].view(M, COUT), zin[M * COUT:])
+            if FUSED_BWD and GRAD_NSPLIT == 2 and k >= 8 and N >= 16:
+                # + the out-edge sums of y_a: with them (and the in-edge sums the backward accumulates) dz_a[E,64] is never formed
+                fused = torch.empty(M, COUT, **f32)
                 _call("dgcnn_edgeconv_lin_conv_a_train", dev, C.byref(a), _ptr(uv2), uv2.stride(0), _ptr(uv2[:, COUT:]), uv2.stride(0),
-                      _ptr(y_a), _ptr(partials), _ptr(fused[0]), _ptr(fused[1]), _ptr(fused[2]))
+                      _ptr(y_a), _ptr(partials), _ptr(fused))
             else:
                 _call("dgcnn_edgeconv_lin_conv_a", dev, C.byref(a), _ptr(uv2), uv2.stride(0), _ptr(uv2[:, COUT:]), uv2.stride(0), _ptr(y_a),
                       _ptr(partials))
@@ -634,16 +632,18 @@ class EdgeConvTrain(torch.autograd.Function):
             # per POINT: its batch sums from U, V, r, s and the affine map with the forward's graph sums of y_a
             uv = ctx.uv2
             dw_b = torch.empty(COUT, COUT, **f32)
+            zin = torch.zeros(M * COUT + M, **f32)          # in-edge sums of y_a [M,64] | in-degrees [M]
+            yin, cnt = zin[:M * COUT].view(M, COUT), zin[M * COUT:]
             _call("dgcnn_edgeconv_bwd_b_fused", dev, C.byref(a), _ptr(y_a), _ptr(stat_a[2:]), _ptr(g), _ptr(arg), _ptr(coef_l),
-                  _ptr(r), _ptr(s), 2 * COUT, _ptr(dw_b), _ptr(dw_partials))
+                  _ptr(r), _ptr(s), 2 * COUT, _ptr(yin), _ptr(cnt), _ptr(dw_b), _ptr(dw_partials))
             _call("dgcnn_edgeconv_bwd_a_point_stats", dev, M, _ptr(uv), uv.stride(0), _ptr(uv[:, COUT:]), uv.stride(0), _ptr(r), _ptr(s),
                   2 * COUT, _ptr(partials))
             dga = torch.empty(2, COUT, **f32)
             coef_a = torch.empty(3, COUT, **f32)
             _call("dgcnn_bn_bwd_reduce", dev, _ptr(partials), COUT, float(E), _ptr(gamma_a), _ptr(stat_a[0]), _ptr(stat_a[1]),
                                                _ptr(dga[0]), _ptr(dga[1]), _ptr(coef_a))
-            _call("dgcnn_edgeconv_bwd_a_point_apply", dev, M, k, _ptr(r), _ptr(s), 2 * COUT, _ptr(fused[1]), _ptr(fused[0]),
-                  _ptr(fused[2]), _ptr(coef_a))
+            _call("dgcnn_edgeconv_bwd_a_point_apply", dev, M, k, _ptr(r), _ptr(s), 2 * COUT, _ptr(yin), _ptr(fused), _ptr(cnt),
+                  _ptr(coef_a))
             ctx.uv2 = None
         else:
             if two:

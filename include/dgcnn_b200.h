@@ -181,19 +181,19 @@ int dgcnn_edgeconv_bwd_a_lin(const dgcnn_edgeconv_args* a, const float* U, int l
  * BN_a's backward is affine in (dz_a, y_a) and conv_a's backward only needs in-edge / out-edge sums, so the sums are taken
  * of the raw quantities and the affine map is applied per POINT afterwards:
  *   r_j = cA R_j - cnt_j cB - cC Yin_j,   s_i = cA S_i - k cB - cC Ysum_i
- * dgcnn_edgeconv_lin_conv_a_train: dgcnn_edgeconv_lin_conv_a + the graph sums of y_a the backward needs — ysum[B*N,64]
- *   (over the out-edges of i, written), yin[B*N,64] and cnt[B*N] (over the in-edges of j / the in-degree, ACCUMULATED with
- *   float reductions: zero them first).
+ * dgcnn_edgeconv_lin_conv_a_train: dgcnn_edgeconv_lin_conv_a + ysum[B*N,64], the sum of y_a over the out-edges of i.
  * dgcnn_edgeconv_bwd_b_fused: dgcnn_edgeconv_bwd_b (tcgen05, 2 bf16 planes) that, instead of writing dz_a[E,64], adds its
- *   rows into r_raw[j] and their per-point sums into s_raw[i] (float4 reductions, row stride ld_rs: zero both first).  k >= 8.
+ *   rows into r_raw[j] and their per-point sums into s_raw[i] (row stride ld_rs), and the y_a rows it streams into
+ *   yin[j] ([B*N,64], the sum of y_a over the in-edges of j) and cnt[j] ([B*N], the in-degree) — all float reductions:
+ *   zero the four targets first.  k >= 8, N >= 16.
  * dgcnn_edgeconv_bwd_a_point_stats: the batch sums BN_a's backward needs, from point-level data:
  *   sum dz_a = sum_i S_i,  sum dz_a*y_a = sum_j U_j.R_j + sum_i V_i.S_i  -> partials (then dgcnn_bn_bwd_reduce -> coef_a).
  * dgcnn_edgeconv_bwd_a_point_apply: the affine map above, in place on r_raw / s_raw.                                  */
 int dgcnn_edgeconv_lin_conv_a_train(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
-                                    float* y_a, double* partials, float* ysum, float* yin, float* cnt, void* stream);
+                                    float* y_a, double* partials, float* ysum, void* stream);
 int dgcnn_edgeconv_bwd_b_fused(const dgcnn_edgeconv_args* a, const float* y_a, const float* aff_a, const float* g,
-                               const uint8_t* arg, const float* coef_b, float* r_raw, float* s_raw, int ld_rs, float* dw_b,
-                               float* dw_partials, void* stream);
+                               const uint8_t* arg, const float* coef_b, float* r_raw, float* s_raw, int ld_rs, float* yin,
+                               float* cnt, float* dw_b, float* dw_partials, void* stream);
 int dgcnn_edgeconv_bwd_a_point_stats(int M, const float* U, int ld_u, const float* V, int ld_v, const float* r_raw,
                                      const float* s_raw, int ld_rs, double* partials, void* stream);
 int dgcnn_edgeconv_bwd_a_point_apply(int M, int k, float* r, float* s, int ld_rs, const float* yin, const float* ysum,
