@@ -264,39 +264,39 @@ __global__ void __launch_bounds__(kThreads, 2) ec_fwd_kernel(const EcK p) {
 // ---------------------------------------------------------------------------------------------
 // small per-channel kernels
 // ---------------------------------------------------------------------------------------------
-// Sum partials[part][2][C] over the parts with 16 thread groups (fixed order -> deterministic): thread (grp, c)
-// accumulates parts grp, grp+16, ... with all its loads in flight together (the kernel is pure latency: a few hundred
-// parts, one CTA); the group sums are added in order.  Result valid for threadIdx.x < C.  blockDim.x = 1024.
-constexpr int kRedGroups = 16;
+// Sum partials[part][2][C] over the parts (fixed order -> deterministic).  The kernel is pure latency (up to 1024 parts of
+// 1 KB), so it is spread over kFinCtas CTAs of 4 channels: thread = (channel, statistic, part lane), 32 part lanes with
+// all their loads in flight; a part contributes two fully used 32-byte sectors per CTA.  Result valid for threadIdx.x < 4
+// (channel blockIdx.x * 4 + threadIdx.x).  blockDim.x = 256, C = 64.
+constexpr int kFinCtas = 16, kFinThreads = 256;
 __device__ __forceinline__ void reduce_partials(const double* __restrict__ partials, int C, double& s, double& q) {
-  __shared__ double red[2][kRedGroups][64];
-  const int c = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  __shared__ double red[2][4][33];
+  const int cl = threadIdx.x & 3, stat = (threadIdx.x >> 2) & 1, pl = threadIdx.x >> 3;
   const int nparts = static_cast<int>(partials[0]);
-  double a = 0.0, b = 0.0;
+  const double* src = partials + 128 + stat * C + blockIdx.x * 4 + cl;
+  double a = 0.0;
 #pragma unroll 8
-  for (int i = grp; i < nparts; i += kRedGroups) {
-    a += partials[128 + static_cast<size_t>(i) * 2 * C + c];
-    b += partials[128 + static_cast<size_t>(i) * 2 * C + C + c];
-  }
-  red[0][grp][c] = a;
-  red[1][grp][c] = b;
+  for (int i = pl; i < nparts; i += 32) a += src[static_cast<size_t>(i) * 2 * C];
+  red[stat][cl][pl] = a;
   __syncthreads();
   s = 0.0; q = 0.0;
+  if (threadIdx.x < 4) {
 #pragma unroll
-  for (int g2 = 0; g2 < kRedGroups; ++g2) {
-    s += red[0][g2][c];
-    q += red[1][g2][c];
+    for (int g2 = 0; g2 < 32; ++g2) {
+      s += red[0][threadIdx.x][g2];
+      q += red[1][threadIdx.x][g2];
+    }
   }
 }
 
-__global__ void __launch_bounds__(1024) bn_finalize_kernel(const double* __restrict__ partials, int C, double count,
+__global__ void __launch_bounds__(kFinThreads) bn_finalize_kernel(const double* __restrict__ partials, int C, double count,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float eps, float momentum, float* running_mean,
                                                           float* running_var, float* mean, float* rstd, float* aff) {
   double s, q;
   reduce_partials(partials, C, s, q);
-  const int c = threadIdx.x;
-  if (c >= C) return;
+  if (threadIdx.x >= 4) return;
+  const int c = blockIdx.x * 4 + threadIdx.x;
   const double m = s / count;
   double var = q / count - m * m;
   if (var < 0.0) var = 0.0;
@@ -361,14 +361,14 @@ __global__ void __launch_bounds__(kThreads) bwd_prep_kernel(int M, const float* 
 
 // From S1 = sum dz, S2 = sum dz*y:  dgamma = rstd (S2 - mean S1), dbeta = S1 and the coefficients of
 // dy = cA dz - cB - cC y  (BatchNorm backward with batch statistics).
-__global__ void __launch_bounds__(1024) bn_bwd_reduce_kernel(const double* __restrict__ partials, int C, double count,
+__global__ void __launch_bounds__(kFinThreads) bn_bwd_reduce_kernel(const double* __restrict__ partials, int C, double count,
                                                             const float* __restrict__ gamma, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, float* dgamma, float* dbeta,
                                                             float* coef) {
   double s1, s2;
   reduce_partials(partials, C, s1, s2);
-  const int c = threadIdx.x;
-  if (c >= C) return;
+  if (threadIdx.x >= 4) return;
+  const int c = blockIdx.x * 4 + threadIdx.x;
   const double m = mean[c], rs = rstd[c], ga = gamma[c];
   const double dg = rs * (s2 - m * s1);
   dgamma[c] = static_cast<float>(dg);
@@ -685,7 +685,7 @@ extern "C" int dgcnn_bn_finalize(const double* partials, int C, double count, co
   DG_REQUIRE(partials && gamma && beta && mean && rstd && aff, DGCNN_E_INVALID, "bn_finalize: null pointer");
   DG_REQUIRE(C == kCout, DGCNN_E_UNSUPPORTED, "bn_finalize: C must be 64");
   DG_REQUIRE(count >= 1.0 && (!running_mean == !running_var), DGCNN_E_INVALID, "bn_finalize: bad count / running stats");
-  bn_finalize_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(partials, C, count, gamma, beta, eps, momentum,
+  bn_finalize_kernel<<<kFinCtas, kFinThreads, 0, static_cast<cudaStream_t>(stream)>>>(partials, C, count, gamma, beta, eps, momentum,
                                                                     running_mean, running_var, mean, rstd, aff);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
@@ -718,7 +718,7 @@ extern "C" int dgcnn_bn_bwd_reduce(const double* partials, int C, double count, 
                                    const float* rstd, float* dgamma, float* dbeta, float* coef, void* stream) {
   DG_REQUIRE(partials && gamma && mean && rstd && dgamma && dbeta && coef, DGCNN_E_INVALID, "bn_bwd_reduce: null pointer");
   DG_REQUIRE(C == kCout && count >= 1.0, DGCNN_E_UNSUPPORTED, "bn_bwd_reduce: C must be 64");
-  bn_bwd_reduce_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(partials, C, count, gamma, mean, rstd, dgamma, dbeta, coef);
+  bn_bwd_reduce_kernel<<<kFinCtas, kFinThreads, 0, static_cast<cudaStream_t>(stream)>>>(partials, C, count, gamma, mean, rstd, dgamma, dbeta, coef);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
 }

@@ -201,15 +201,16 @@ __global__ void __launch_bounds__(kRbThreads) rows_colsum_partial_kernel(const f
   const float* base = x + static_cast<size_t>(seg) * N * C;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (rl < RL) {
-    // four independent rows in flight per thread (a single dependent chain of loads made this pass latency-bound)
+    // eight independent rows in flight per thread (a single dependent chain of loads made this pass latency-bound)
     int r = r0 + rl;
-    for (; r + 3 * RL < r1; r += 4 * RL) {
-      const float4 v0 = ld4(base + static_cast<size_t>(r) * C + 4 * cg);
-      const float4 v1 = ld4(base + static_cast<size_t>(r + RL) * C + 4 * cg);
-      const float4 v2 = ld4(base + static_cast<size_t>(r + 2 * RL) * C + 4 * cg);
-      const float4 v3 = ld4(base + static_cast<size_t>(r + 3 * RL) * C + 4 * cg);
-      s.x += (v0.x + v1.x) + (v2.x + v3.x); s.y += (v0.y + v1.y) + (v2.y + v3.y);
-      s.z += (v0.z + v1.z) + (v2.z + v3.z); s.w += (v0.w + v1.w) + (v2.w + v3.w);
+    for (; r + 7 * RL < r1; r += 8 * RL) {
+      float4 v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = ld4(base + static_cast<size_t>(r + e * RL) * C + 4 * cg);
+      s.x += ((v[0].x + v[1].x) + (v[2].x + v[3].x)) + ((v[4].x + v[5].x) + (v[6].x + v[7].x));
+      s.y += ((v[0].y + v[1].y) + (v[2].y + v[3].y)) + ((v[4].y + v[5].y) + (v[6].y + v[7].y));
+      s.z += ((v[0].z + v[1].z) + (v[2].z + v[3].z)) + ((v[4].z + v[5].z) + (v[6].z + v[7].z));
+      s.w += ((v[0].w + v[1].w) + (v[2].w + v[3].w)) + ((v[4].w + v[5].w) + (v[6].w + v[7].w));
     }
     for (; r < r1; r += RL) {
       const float4 v = ld4(base + static_cast<size_t>(r) * C + 4 * cg);
@@ -229,13 +230,28 @@ __global__ void __launch_bounds__(kRbThreads) rows_colsum_partial_kernel(const f
     for (int e = 0; e < 4; ++e) dst[e] = acc[e];
   }
 }
-__global__ void rows_colsum_finish_kernel(const double* __restrict__ partials, int nparts, int C, int nseg, float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nseg * C) return;
-  const int seg = i / C, c = i - seg * C;
+// 32 consecutive outputs x 8 part groups per CTA: group g adds parts g, g + 8, ... (coalesced 256-byte rows, loads
+// independent), then the 8 group sums are added in order.
+__global__ void __launch_bounds__(256) rows_colsum_finish_kernel(const double* __restrict__ partials, int nparts, int C, int nseg,
+                                                                 float* __restrict__ out) {
+  __shared__ double red[8][32];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   double s = 0.0;
-  for (int q = 0; q < nparts; ++q) s += partials[(static_cast<size_t>(seg) * nparts + q) * C + c];
-  out[i] = static_cast<float>(s);
+  if (i < nseg * C) {
+    const int seg = i / C, c = i - seg * C;
+    const double* src = partials + static_cast<size_t>(seg) * nparts * C + c;
+#pragma unroll 4
+    for (int q = g; q < nparts; q += 8) s += src[static_cast<size_t>(q) * C];
+  }
+  red[g][lane] = s;
+  __syncthreads();
+  if (g == 0 && i < nseg * C) {
+    double a = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a += red[q][lane];
+    out[i] = static_cast<float>(a);
+  }
 }
 
 static bool rows_bn_shape_ok(int C) { return C == 64 || C == 128 || C == 256 || C == 512 || C == 1024; }
@@ -311,9 +327,10 @@ extern "C" int dgcnn_rows_bn_lrelu_bwd(const float* dh, const float* y, int M, i
   return DGCNN_OK;
 }
 
+constexpr int kColsumMaxParts = 1024;      // CTAs per segment: a single segment (colsum of the whole batch) must still fill the GPU
 extern "C" size_t dgcnn_rows_colsum_workspace_bytes(int M, int C, int N) {
   if (M <= 0 || C <= 0 || N <= 0) return 0;
-  return static_cast<size_t>(M / N) * 64 * C * sizeof(double);
+  return static_cast<size_t>(M / N) * kColsumMaxParts * C * sizeof(double);
 }
 
 extern "C" int dgcnn_rows_colsum_f32(const float* x, int M, int C, int N, float* out, void* workspace, size_t workspace_bytes,
@@ -326,11 +343,11 @@ extern "C" int dgcnn_rows_colsum_f32(const float* x, int M, int C, int N, float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nseg = M / N;
   const int sms = std::max(1, num_sms());
-  const int parts = std::max(1, std::min(64, std::min(N, (sms * 4 + nseg - 1) / nseg)));
+  const int parts = std::max(1, std::min(kColsumMaxParts, std::min(N, (sms * 8 + nseg - 1) / nseg)));
   const int rpc = (N + parts - 1) / parts;
   const int nparts = (N + rpc - 1) / rpc;
   rows_colsum_partial_kernel<<<dim3(nparts, nseg), kRbThreads, 0, st>>>(x, C, N, rpc, static_cast<double*>(workspace));
-  rows_colsum_finish_kernel<<<(nseg * C + 255) / 256, 256, 0, st>>>(static_cast<const double*>(workspace), nparts, C, nseg, out);
+  rows_colsum_finish_kernel<<<(nseg * C + 31) / 32, 256, 0, st>>>(static_cast<const double*>(workspace), nparts, C, nseg, out);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
 }
