@@ -132,37 +132,43 @@ struct GemmSmem {
   static constexpr uint32_t a_plane = 128 * 128;          // 128 rows x 128 B
   static constexpr uint32_t b_plane = BN * 128;
   static constexpr uint32_t stage = NS * (a_plane + b_plane);
-  static constexpr uint32_t bytes = STAGES * stage + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t stat_bytes = 4 * 2 * BN * 4;  // EPI_COLSTATS: [4 quarters][2][BN] floats
+  static constexpr uint32_t bytes = STAGES * stage + stat_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
+// Persistent: CTA b works on the 128 x BN output tiles b, b + gridDim.x, ... (column tile fastest, so that concurrently
+// running CTAs share their A rows in L2) with TWO accumulators in TMEM — the epilogue of a tile (tcgen05.ld, global stores or
+// column statistics) overlaps the loads and MMAs of the next one.  The stage ring runs on across tiles.
 template <int NS, int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(192, 1)
 tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __restrict__ Bp, float* __restrict__ D,
-               int ldd, int M, int N, int KA, int ka_per_split, size_t split_stride, GemmEpi epi, int ns_a = NS, int ns_b = NS) {
+               int ldd, int M, int N, int KA, int ka_per_split, size_t split_stride, GemmEpi epi, int ns_a, int ns_b, int NT, int MT,
+               int Z) {
   using SM = GemmSmem<NS, BN, STAGES>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * SM::stage);
+  float* statS = reinterpret_cast<float*>(tiles + STAGES * SM::stage);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * SM::stage + SM::stat_bytes);
   uint64_t* empty = full + STAGES;
-  uint64_t* accfull = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
-  float* statS = reinterpret_cast<float*>(tiles);     // EPI_COLSTATS: [4 quarters][2][BN], reuses stage 0 after the last MMA
+  uint64_t* accfull = empty + STAGES;     // [2] MMA commit -> epilogue
+  uint64_t* accfree = accfull + 2;        // [2] epilogue (4 warps) -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfree + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nt = blockIdx.x, mt = blockIdx.y;
-  // split-K: this CTA contracts k-atoms [ka_lo, ka_hi) and writes its partial tile to D + z * split_stride
-  const int ka_lo = blockIdx.z * ka_per_split, ka_hi = min(KA, ka_lo + ka_per_split);
-  D += static_cast<size_t>(blockIdx.z) * split_stride;
+  const int total = NT * MT * Z;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       tc::mbar_init(full + s, 1);
       tc::mbar_init(empty + s, 1);
     }
-    tc::mbar_init(accfull, 1);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(accfull + s, 1);
+      tc::mbar_init(accfree + s, 4);
+    }
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 2 * BN);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -170,55 +176,75 @@ tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __rest
 
   if (warp == 0) {
     if (tc::elect_one()) {             // one lane, chosen with elect.sync: the issue code stays on the uniform datapath
-      for (int ka = ka_lo; ka < ka_hi; ++ka) {
-        const int it = ka - ka_lo, s = it % STAGES;
-        tc::mbar_wait(empty + s, ((it / STAGES) & 1) ^ 1);
-        tc::mbar_arrive_expect_tx(full + s, SM::stage);
-        unsigned char* a_s = tiles + s * SM::stage;
-        unsigned char* b_s = a_s + NS * SM::a_plane;
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int nt = t % NT, mt = (t / NT) % MT, z = t / (NT * MT);
+        // split-K: this tile contracts k-atoms [ka_lo, ka_hi) and goes to D + z * split_stride
+        const int ka_lo = z * ka_per_split, ka_hi = min(KA, ka_lo + ka_per_split);
+        for (int ka = ka_lo; ka < ka_hi; ++ka, ++it) {
+          const int s = it % STAGES;
+          tc::mbar_wait(empty + s, ((it / STAGES) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(full + s, SM::stage);
+          unsigned char* a_s = tiles + s * SM::stage;
+          unsigned char* b_s = a_s + NS * SM::a_plane;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const unsigned char* src = Ap + (static_cast<size_t>(2 * mt + h) * KA + ka) * ns_a * tc::kUnitBytes;
+          for (int h = 0; h < 2; ++h) {
+            const unsigned char* src = Ap + (static_cast<size_t>(2 * mt + h) * KA + ka) * ns_a * tc::kUnitBytes;
 #pragma unroll
-          for (int p = 0; p < NS; ++p)
-            tc::bulk_g2s(a_s + p * SM::a_plane + h * tc::kUnitBytes, src + p * tc::kUnitBytes, tc::kUnitBytes, full + s);
-        }
+            for (int p = 0; p < NS; ++p)
+              tc::bulk_g2s(a_s + p * SM::a_plane + h * tc::kUnitBytes, src + p * tc::kUnitBytes, tc::kUnitBytes, full + s);
+          }
 #pragma unroll
-        for (int h = 0; h < BN / 64; ++h) {
-          const unsigned char* src = Bp + (static_cast<size_t>(nt * (BN / 64) + h) * KA + ka) * ns_b * tc::kUnitBytes;
+          for (int h = 0; h < BN / 64; ++h) {
+            const unsigned char* src = Bp + (static_cast<size_t>(nt * (BN / 64) + h) * KA + ka) * ns_b * tc::kUnitBytes;
 #pragma unroll
-          for (int p = 0; p < NS; ++p)
-            tc::bulk_g2s(b_s + p * SM::b_plane + h * tc::kUnitBytes, src + p * tc::kUnitBytes, tc::kUnitBytes, full + s);
+            for (int p = 0; p < NS; ++p)
+              tc::bulk_g2s(b_s + p * SM::b_plane + h * tc::kUnitBytes, src + p * tc::kUnitBytes, tc::kUnitBytes, full + s);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::idesc_bf16(128, BN);
-      for (int ka = ka_lo; ka < ka_hi; ++ka) {
-        const int it = ka - ka_lo, s = it % STAGES;
-        tc::mbar_wait(full + s, (it / STAGES) & 1);
+      int it = 0, tl = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
+        const int z = t / (NT * MT);
+        const int ka_lo = z * ka_per_split, ka_hi = min(KA, ka_lo + ka_per_split);
+        const int ab = tl & 1;
+        tc::mbar_wait(accfree + ab, ((tl >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator (two tiles ago)
         tc::fence_after_sync();
-        const uint32_t a_s = tc::smem_u32(tiles + s * SM::stage);
-        tc::mma_split_katom<NS>(taddr, a_s, SM::a_plane, a_s + NS * SM::a_plane, SM::b_plane, idesc, ka == ka_lo);
-        tc::mma_commit(empty + s);       // frees the stage once these MMAs have read it
+        for (int ka = ka_lo; ka < ka_hi; ++ka, ++it) {
+          const int s = it % STAGES;
+          tc::mbar_wait(full + s, (it / STAGES) & 1);
+          tc::fence_after_sync();
+          const uint32_t a_s = tc::smem_u32(tiles + s * SM::stage);
+          tc::mma_split_katom<NS>(taddr + ab * BN, a_s, SM::a_plane, a_s + NS * SM::a_plane, SM::b_plane, idesc, ka == ka_lo);
+          tc::mma_commit(empty + s);       // frees the stage once these MMAs have read it
+        }
+        tc::mma_commit(accfull + ab);
       }
-      tc::mma_commit(accfull);
     }
   } else {
     const int quarter = warp & 3;        // TMEM lanes this warp may read: 32*quarter .. +31
-    tc::mbar_wait(accfull, 0);
+    int tl = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
+    const int nt = t % NT, mt = (t / NT) % MT, z = t / (NT * MT);
+    const int ab = tl & 1;
+    const uint32_t tacc = taddr + ab * BN;
+    float* Dz = D + static_cast<size_t>(z) * split_stride;
+    tc::mbar_wait(accfull + ab, (tl >> 1) & 1);
     tc::fence_after_sync();
     const int row = mt * 128 + quarter * 32 + lane;
     if (EPI == EPI_STORE) {
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
-        tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
+        tc::tmem_ld32(tacc + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
         const int n0 = nt * BN + c0;
         if (row < M) {
-          float* dst = D + static_cast<size_t>(row) * ldd + n0;
-          if (n0 + 32 <= N && (ldd & 7) == 0 && (reinterpret_cast<uintptr_t>(D) & 31) == 0) {
+          float* dst = Dz + static_cast<size_t>(row) * ldd + n0;
+          if (n0 + 32 <= N && (ldd & 7) == 0 && (reinterpret_cast<uintptr_t>(Dz) & 31) == 0) {
             // thread = output row: 32-byte stores write whole sectors (16-byte stores would touch every sector twice)
 #pragma unroll
             for (int i = 0; i < 32; i += 8)
@@ -235,6 +261,9 @@ tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __rest
           }
         }
       }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(accfree + ab);         // accumulator drained (the stores are in flight on their own)
     } else {
       const bool rvalid = row < M;
       const int seg = rvalid ? row / epi.seg_len : -1;
@@ -244,7 +273,7 @@ tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __rest
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
-        tc::tmem_ld32(taddr + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
+        tc::tmem_ld32(tacc + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
         const int col = nt * BN + c0 + lane;
         {
           float a[32], q[32];
@@ -277,22 +306,27 @@ tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __rest
           }
         }
       }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(accfree + ab);
       // combine the four lane quarters in a fixed order: one partial per (row tile, column)
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int t = threadIdx.x - 64;                      // 0..127 over the four epilogue warps
-      if (t < BN && nt * BN + t < N) {
+      const int te = threadIdx.x - 64;                     // 0..127 over the four epilogue warps
+      if (te < BN && nt * BN + te < N) {
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
-          const float sum = ((statS[(0 * 2 + w) * BN + t] + statS[(1 * 2 + w) * BN + t]) + statS[(2 * 2 + w) * BN + t]) +
-                            statS[(3 * 2 + w) * BN + t];
-          epi.stat_partials[(static_cast<size_t>(mt) * 2 + w) * N + nt * BN + t] = sum;
+          const float sum = ((statS[(0 * 2 + w) * BN + te] + statS[(1 * 2 + w) * BN + te]) + statS[(2 * 2 + w) * BN + te]) +
+                            statS[(3 * 2 + w) * BN + te];
+          epi.stat_partials[(static_cast<size_t>(mt) * 2 + w) * N + nt * BN + te] = sum;
         }
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // statS is rewritten by the next tile
     }
+    }  // tiles
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(taddr, BN);
+  if (warp == 1) tc::tmem_dealloc(taddr, 2 * BN);
 }
 
 
@@ -479,19 +513,19 @@ static int launch_gemm(const unsigned char* Ap, const unsigned char* Bp, float* 
   auto kern = tc_gemm_kernel<NS, BN, STAGES, EPI_STORE>;
   DG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SM::bytes)));
   const int splits = splitk_factor(M, N, KA);
-  dim3 grid((N + BN - 1) / BN, (M + 127) / 128, splits);
+  const int NT = (N + BN - 1) / BN, MT = (M + 127) / 128, sms = std::max(1, num_sms());
   if (splits == 1) {
-    kern<<<grid, 192, SM::bytes, st>>>(Ap, Bp, D, ldd, M, N, KA, KA, 0, GemmEpi{}, ns_a, ns_b);
+    kern<<<std::min(NT * MT, sms), 192, SM::bytes, st>>>(Ap, Bp, D, ldd, M, N, KA, KA, 0, GemmEpi{}, ns_a, ns_b, NT, MT, 1);
     DG_CUDA(cudaGetLastError());
     return DGCNN_OK;
   }
   const int per = (KA + splits - 1) / splits;
   const size_t stride = static_cast<size_t>(M) * N;
-  grid.z = (KA + per - 1) / per;
-  kern<<<grid, 192, SM::bytes, st>>>(Ap, Bp, partials, N, M, N, KA, per, stride, GemmEpi{}, ns_a, ns_b);
+  const int Z = (KA + per - 1) / per;
+  kern<<<std::min(NT * MT * Z, sms), 192, SM::bytes, st>>>(Ap, Bp, partials, N, M, N, KA, per, stride, GemmEpi{}, ns_a, ns_b, NT, MT, Z);
   DG_CUDA(cudaGetLastError());
   const size_t total = stride;
-  splitk_reduce_kernel<<<static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 8)), 256, 0, st>>>(partials, stride, grid.z, D,
+  splitk_reduce_kernel<<<static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 8)), 256, 0, st>>>(partials, stride, Z, D,
                                                                                                      ldd, M, N);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
@@ -761,7 +795,8 @@ extern "C" int dgcnn_tc_gemm_bn_lrelu_segmax_f32(const float* A, int64_t a_sr, i
   auto kern = tc_gemm_kernel<3, 128, 2, EPI_COLSTATS>;
   DG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SM::bytes)));
   GemmEpi epi{seg_len, stats, gext, gamma};
-  kern<<<dim3(Np / 128, num_mt, 1), 192, SM::bytes, st>>>(Ap, Bp, nullptr, 0, M, N, KA, KA, 0, epi, 3, 3);
+  kern<<<std::min((Np / 128) * num_mt, std::max(1, num_sms())), 192, SM::bytes, st>>>(Ap, Bp, nullptr, 0, M, N, KA, KA, 0, epi, 3, 3,
+                                                                                   Np / 128, num_mt, 1);
   DG_CUDA(cudaGetLastError());
   colstats_bn_kernel<<<(N + 31) / 32, 256, 0, st>>>(stats, num_mt, N, static_cast<double>(M), gamma, eps, momentum, use_batch_stats,
                                                       running_mean, running_var, mean, rstd);
