@@ -9,12 +9,15 @@
 //             pass 2: dy = gamma * rstd * (dz - mean(dz) - vhat * mean(dz * vhat))
 // All reductions are per-CTA partials in a fixed order (deterministic), finished in FP64.
 // HBM-bound streaming kernels: 16-byte accesses, a warp covers 512 contiguous bytes of a row.
+#include <cuda_bf16.h>
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace dg {
 
 constexpr int kRbThreads = 256;
 constexpr int kRbMaxCtas = 1184;          // 148 SMs x 8
+constexpr int kColsumMaxParts = 1024;     // CTAs per segment: a single segment (colsum of the whole batch) must still fill the GPU
 
 struct RowsBn {
   const float* y; int M, C, N;            // rows, channels, points per block (bias row = row / N)
@@ -152,9 +155,15 @@ __global__ void __launch_bounds__(1024) rows_bn_bwd_finalize_kernel(const double
 }
 
 // BWD = false: out = LReLU((v - mean) scale + beta);   BWD = true: out = kA dz - kB - kC (v - mean)
-template <bool BWD>
+// NSP = 0: FP32 rows.  NSP = 2 / 3: the result goes straight into the tensor-core operand format (NSP bf16 planes in 64 x 64
+// SWIZZLE_128B units, see gemm_tc.cu) for the GEMM that consumes it — the FP32 tensor and the separate split pass (4 B
+// written + 4 B read + 4-6 B written per element) never exist.  Rows M .. Mpad-1 of the planes are written as zeros.
+template <bool BWD, int NSP>
 __global__ void __launch_bounds__(kRbThreads) rows_bn_apply_kernel(RowsBn p, const float* __restrict__ dh,
-                                                                  const float* __restrict__ coef, float* __restrict__ out) {
+                                                                  const float* __restrict__ coef, float* __restrict__ out,
+                                                                  unsigned char* __restrict__ planes, int Mpad, int seg_len,
+                                                                  int rows_per_cta, double* __restrict__ colsum_partials) {
+  __shared__ float4 red[kRbThreads];
   const int c4n = p.C >> 2, RL = kRbThreads / c4n;
   const int cg = threadIdx.x % c4n, rl = threadIdx.x / c4n;
   const float4 mean = ld4(p.a + 4 * cg), scale = ld4(p.a + p.C + 4 * cg), beta = ld4(p.a + 2 * p.C + 4 * cg);
@@ -164,27 +173,84 @@ __global__ void __launch_bounds__(kRbThreads) rows_bn_apply_kernel(RowsBn p, con
     kB = ld4(coef + p.C + 4 * cg);
     kC = ld4(coef + 2 * p.C + 4 * cg);
   }
-  for (int r = blockIdx.x * RL + rl; r < p.M; r += gridDim.x * RL) {
-    const size_t off = static_cast<size_t>(r) * p.C + 4 * cg;
-    float4 v = ld4(p.y + off);
-    if (p.bias) {
-      const float4 b = ld4(p.bias + static_cast<size_t>(r / p.N) * p.C + 4 * cg);
-      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  // NSP == 0: rows interleaved over the grid.  Planes: grid (parts, segments), CTA (q, seg) owns a contiguous slice of the
+  // rows of segment seg (so that its column sums are per-segment partials); the zero rows M .. Mpad-1 go to CTA (0, 0).
+  int r_begin, r_end, r_step;
+  if (NSP == 0) {
+    r_begin = blockIdx.x * RL + rl; r_end = p.M; r_step = gridDim.x * RL;
+  } else {
+    const int s0 = blockIdx.y * seg_len;
+    r_begin = s0 + blockIdx.x * rows_per_cta + rl;
+    r_end = min(s0 + seg_len, s0 + (static_cast<int>(blockIdx.x) + 1) * rows_per_cta);
+    r_step = RL;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && rl < RL) {
+      for (int r = p.M + rl; r < Mpad; r += RL) {
+        const int c = 4 * cg;
+        unsigned char* unit = planes + (static_cast<size_t>(r >> 6) * (p.C >> 6) + (c >> 6)) * NSP * tc::kUnitBytes +
+                              tc::unit_elem_offset(r & 63, c & 63);
+#pragma unroll
+        for (int q = 0; q < NSP; ++q) *reinterpret_cast<uint2*>(unit + static_cast<size_t>(q) * tc::kUnitBytes) = make_uint2(0u, 0u);
+      }
     }
-    const float dx = v.x - mean.x, dy = v.y - mean.y, dz = v.z - mean.z, dw = v.w - mean.w;
-    const float zx = __fmaf_rn(dx, scale.x, beta.x), zy = __fmaf_rn(dy, scale.y, beta.y);
-    const float zz = __fmaf_rn(dz, scale.z, beta.z), zw = __fmaf_rn(dw, scale.w, beta.w);
-    float4 o;
-    if (!BWD) {
-      o = make_float4(lrelu(zx), lrelu(zy), lrelu(zz), lrelu(zw));
-    } else {
-      const float4 g = ld4(dh + off);
-      o.x = kA.x * (g.x * lrelu_grad(zx)) - kB.x - kC.x * dx;
-      o.y = kA.y * (g.y * lrelu_grad(zy)) - kB.y - kC.y * dy;
-      o.z = kA.z * (g.z * lrelu_grad(zz)) - kB.z - kC.z * dz;
-      o.w = kA.w * (g.w * lrelu_grad(zw)) - kB.w - kC.w * dw;
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rl < RL) {
+    for (int r = r_begin; r < r_end; r += r_step) {
+      const size_t off = static_cast<size_t>(r) * p.C + 4 * cg;
+      float4 v = ld4(p.y + off);
+      if (p.bias) {
+        const float4 b = ld4(p.bias + static_cast<size_t>(r / p.N) * p.C + 4 * cg);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      }
+      const float dx = v.x - mean.x, dy = v.y - mean.y, dz = v.z - mean.z, dw = v.w - mean.w;
+      const float zx = __fmaf_rn(dx, scale.x, beta.x), zy = __fmaf_rn(dy, scale.y, beta.y);
+      const float zz = __fmaf_rn(dz, scale.z, beta.z), zw = __fmaf_rn(dw, scale.w, beta.w);
+      float4 o;
+      if (!BWD) {
+        o = make_float4(lrelu(zx), lrelu(zy), lrelu(zz), lrelu(zw));
+      } else {
+        const float4 g = ld4(dh + off);
+        o.x = kA.x * (g.x * lrelu_grad(zx)) - kB.x - kC.x * dx;
+        o.y = kA.y * (g.y * lrelu_grad(zy)) - kB.y - kC.y * dy;
+        o.z = kA.z * (g.z * lrelu_grad(zz)) - kB.z - kC.z * dz;
+        o.w = kA.w * (g.w * lrelu_grad(zw)) - kB.w - kC.w * dw;
+      }
+      if (NSP == 0) {
+        *reinterpret_cast<float4*>(out + off) = o;
+      } else {
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        const int c = 4 * cg;
+        unsigned char* unit = planes + (static_cast<size_t>(r >> 6) * (p.C >> 6) + (c >> 6)) * NSP * tc::kUnitBytes +
+                              tc::unit_elem_offset(r & 63, c & 63);
+        float v4[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int q = 0; q < NSP; ++q) {
+          const __nv_bfloat162 h0 = __floats2bfloat162_rn(v4[0], v4[1]), h1 = __floats2bfloat162_rn(v4[2], v4[3]);
+          if (q + 1 < NSP) {
+            const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+            v4[0] -= f0.x; v4[1] -= f0.y; v4[2] -= f1.x; v4[3] -= f1.y;       // exact in FP32
+          }
+          uint2 w;
+          w.x = *reinterpret_cast<const uint32_t*>(&h0);
+          w.y = *reinterpret_cast<const uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(unit + static_cast<size_t>(q) * tc::kUnitBytes) = w;
+        }
+      }
     }
-    *reinterpret_cast<float4*>(out + off) = o;
+  }
+  if (NSP != 0 && colsum_partials) {        // per-segment column sums of the result (the per-block bias gradient), fixed order
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < c4n) {
+      double a4[4] = {0, 0, 0, 0};
+      for (int l = 0; l < RL; ++l) {
+        const float4 a = red[l * c4n + cg];
+        a4[0] += a.x; a4[1] += a.y; a4[2] += a.z; a4[3] += a.w;
+      }
+      double* dst = colsum_partials + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * p.C + 4 * cg;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dst[e] = a4[e];
+    }
   }
 }
 
@@ -301,7 +367,7 @@ extern "C" int dgcnn_rows_bn_lrelu_fwd(const float* y, int M, int C, const float
     rows_bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, eps, running_mean, running_var, aff);
   }
   const int blocks = rows_bn_apply_grid(M, C);
-  rows_bn_apply_kernel<false><<<blocks, kRbThreads, 0, st>>>(p, nullptr, nullptr, h);
+  rows_bn_apply_kernel<false, 0><<<blocks, kRbThreads, 0, st>>>(p, nullptr, nullptr, h, nullptr, 0, 0, 0, nullptr);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
 }
@@ -322,12 +388,97 @@ extern "C" int dgcnn_rows_bn_lrelu_bwd(const float* dh, const float* y, int M, i
   rows_bn_reduce_kernel<true><<<grid, kRbThreads, 0, st>>>(p, dh, rpc, partials);
   rows_bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partials, grid, C, static_cast<double>(M), gamma, rstd, dgamma, dbeta, coef);
   const int blocks = rows_bn_apply_grid(M, C);
-  rows_bn_apply_kernel<true><<<blocks, kRbThreads, 0, st>>>(p, dh, coef, dy);
+  rows_bn_apply_kernel<true, 0><<<blocks, kRbThreads, 0, st>>>(p, dh, coef, dy, nullptr, 0, 0, 0, nullptr);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
 }
 
-constexpr int kColsumMaxParts = 1024;      // CTAs per segment: a single segment (colsum of the whole batch) must still fill the GPU
+extern "C" size_t dgcnn_rows_colsum_workspace_bytes(int M, int C, int N);
+
+// ---- the same two passes with the result written as GEMM operand planes (nsplit = 2 or 3; rows padded to a multiple of 128) ----
+static int planes_args_ok(int M, int C, int nsplit, const void* planes, size_t planes_bytes, const char* who) {
+  DG_REQUIRE(planes && (nsplit == 2 || nsplit == 3) && C % 64 == 0 && (reinterpret_cast<uintptr_t>(planes) & 15) == 0, DGCNN_E_INVALID,
+             "%s: planes must be non-null and 16-byte aligned, nsplit 2 or 3, C a multiple of 64", who);
+  const size_t need = static_cast<size_t>((M + 127) / 128 * 2) * (C / 64) * nsplit * tc::kUnitBytes;
+  DG_REQUIRE(planes_bytes >= need, DGCNN_E_WORKSPACE, "%s: planes buffer too small (%zu < %zu)", who, planes_bytes, need);
+  return DGCNN_OK;
+}
+
+// grid (parts, segments) of the planes-writing apply pass: as many CTAs as the interleaved form uses
+static dim3 planes_apply_grid(int M, int seg_len, int* rows_per_cta) {
+  const int nseg = M / seg_len, sms = std::max(1, num_sms());
+  const int parts = std::max(1, std::min(kColsumMaxParts, std::min(seg_len, (sms * 8 + nseg - 1) / nseg)));
+  *rows_per_cta = (seg_len + parts - 1) / parts;
+  return dim3((seg_len + *rows_per_cta - 1) / *rows_per_cta, nseg, 1);
+}
+
+extern "C" int dgcnn_rows_bn_lrelu_fwd_planes(const float* y, int M, int C, const float* bias, int N, const float* gamma,
+                                              const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                                              float* mean, float* rstd, float* aff, void* planes, size_t planes_bytes, int nsplit,
+                                              void* workspace, size_t workspace_bytes, void* stream) {
+  DG_REQUIRE(y && gamma && beta && aff && mean && rstd && workspace, DGCNN_E_INVALID, "rows_bn_lrelu_fwd_planes: null pointer");
+  DG_REQUIRE(rows_bn_shape_ok(C), DGCNN_E_UNSUPPORTED, "rows_bn_lrelu_fwd_planes: C must be 64, 128, 256, 512 or 1024");
+  DG_REQUIRE(M > 0 && N > 0 && (!bias || M % N == 0) && (!running_mean == !running_var), DGCNN_E_INVALID, "rows_bn_lrelu_fwd_planes: bad shape");
+  DG_REQUIRE(workspace_bytes >= dgcnn_rows_bn_workspace_bytes(C), DGCNN_E_INVALID, "rows_bn_lrelu_fwd_planes: workspace too small");
+  int rc = planes_args_ok(M, C, nsplit, planes, planes_bytes, "rows_bn_lrelu_fwd_planes");
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RowsBn p{y, M, C, N, bias, aff};
+  double* partials = static_cast<double*>(workspace);
+  int rpc;
+  const int grid = rows_bn_grid(M, &rpc);
+  rows_bn_reduce_kernel<false><<<grid, kRbThreads, 0, st>>>(p, nullptr, rpc, partials);
+  rows_bn_fwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partials, grid, C, static_cast<double>(M), gamma, beta, eps, momentum,
+                                                               running_mean, running_var, mean, rstd, aff);
+  const int Mpad = (M + 127) / 128 * 128;
+  int rpc2;
+  const dim3 blocks = planes_apply_grid(M, M, &rpc2);
+  unsigned char* pl = static_cast<unsigned char*>(planes);
+  if (nsplit == 3)
+    rows_bn_apply_kernel<false, 3><<<blocks, kRbThreads, 0, st>>>(p, nullptr, nullptr, nullptr, pl, Mpad, M, rpc2, nullptr);
+  else
+    rows_bn_apply_kernel<false, 2><<<blocks, kRbThreads, 0, st>>>(p, nullptr, nullptr, nullptr, pl, Mpad, M, rpc2, nullptr);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}
+
+extern "C" int dgcnn_rows_bn_lrelu_bwd_planes(const float* dh, const float* y, int M, int C, const float* bias, int N,
+                                              const float* gamma, const float* rstd, const float* aff, void* planes,
+                                              size_t planes_bytes, int nsplit, float* dgamma, float* dbeta, float* dbias,
+                                              void* colsum_workspace, size_t colsum_workspace_bytes, void* workspace,
+                                              size_t workspace_bytes, void* stream) {
+  DG_REQUIRE(dh && y && gamma && rstd && aff && dgamma && dbeta && workspace, DGCNN_E_INVALID, "rows_bn_lrelu_bwd_planes: null pointer");
+  DG_REQUIRE(rows_bn_shape_ok(C), DGCNN_E_UNSUPPORTED, "rows_bn_lrelu_bwd_planes: C must be 64, 128, 256, 512 or 1024");
+  DG_REQUIRE(M > 0 && N > 0 && (!bias || M % N == 0), DGCNN_E_INVALID, "rows_bn_lrelu_bwd_planes: bad shape");
+  DG_REQUIRE(workspace_bytes >= dgcnn_rows_bn_workspace_bytes(C), DGCNN_E_INVALID, "rows_bn_lrelu_bwd_planes: workspace too small");
+  int rc = planes_args_ok(M, C, nsplit, planes, planes_bytes, "rows_bn_lrelu_bwd_planes");
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RowsBn p{y, M, C, N, bias, aff};
+  double* partials = static_cast<double*>(workspace);
+  float* coef = reinterpret_cast<float*>(partials + static_cast<size_t>(kRbMaxCtas) * 2 * C);
+  int rpc;
+  const int grid = rows_bn_grid(M, &rpc);
+  rows_bn_reduce_kernel<true><<<grid, kRbThreads, 0, st>>>(p, dh, rpc, partials);
+  rows_bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partials, grid, C, static_cast<double>(M), gamma, rstd, dgamma, dbeta, coef);
+  const int Mpad = (M + 127) / 128 * 128;
+  // dbias (the gradient of the per-block bias = per-block column sums of dy) comes out of the same pass
+  DG_REQUIRE(!dbias || (bias && colsum_workspace && colsum_workspace_bytes >= dgcnn_rows_colsum_workspace_bytes(M, C, N)), DGCNN_E_INVALID,
+             "rows_bn_lrelu_bwd_planes: dbias needs a bias and dgcnn_rows_colsum_workspace_bytes(M, C, N) of workspace");
+  const int seg = dbias ? N : M;
+  int rpc2;
+  const dim3 blocks = planes_apply_grid(M, seg, &rpc2);
+  double* cs = dbias ? static_cast<double*>(colsum_workspace) : nullptr;
+  unsigned char* pl = static_cast<unsigned char*>(planes);
+  if (nsplit == 3)
+    rows_bn_apply_kernel<true, 3><<<blocks, kRbThreads, 0, st>>>(p, dh, coef, nullptr, pl, Mpad, seg, rpc2, cs);
+  else
+    rows_bn_apply_kernel<true, 2><<<blocks, kRbThreads, 0, st>>>(p, dh, coef, nullptr, pl, Mpad, seg, rpc2, cs);
+  if (dbias) rows_colsum_finish_kernel<<<(M / N * C + 31) / 32, 256, 0, st>>>(cs, static_cast<int>(blocks.x), C, M / N, dbias);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}
+
 extern "C" size_t dgcnn_rows_colsum_workspace_bytes(int M, int C, int N) {
   if (M <= 0 || C <= 0 || N <= 0) return 0;
   return static_cast<size_t>(M / N) * kColsumMaxParts * C * sizeof(double);

@@ -211,10 +211,13 @@ class DGCNN(nn.Module):
             raise RuntimeError(f"conv7 expects {w7.size(1)} input channels but emb_dims+192 = {E + feat.size(1)}")
         # conv7([g ; x1,x2,x3]) = W7[:, :E] g (once per block) + W7[:, E:] feat  — no repeat/cat of the global feature
         # the per-block term is added inside the fused BatchNorm + LeakyReLU passes
-        h7 = ops.bn_lrelu_rows(ops.linear(feat, w7[:, E:]), self.bn7, self.training, N, bias=ops.linear(g, w7[:, :E]))
-        if depth == 8:
-            return self._bcn(h7, B, N)
-        h8 = ops.bn_lrelu_rows(ops.linear(h7, self.conv8[0].weight.squeeze(-1)), self.bn8, self.training, N)
+        if self.training and depth > 8 and ops.FUSED_HEAD and self.bn7.track_running_stats and self.bn8.track_running_stats:
+            h8 = ops.head_mlp(feat, ops.linear(g, w7[:, :E]), w7[:, E:], self.bn7, self.conv8[0].weight.squeeze(-1), self.bn8, N)
+        else:
+            h7 = ops.bn_lrelu_rows(ops.linear(feat, w7[:, E:]), self.bn7, self.training, N, bias=ops.linear(g, w7[:, :E]))
+            if depth == 8:
+                return self._bcn(h7, B, N)
+            h8 = ops.bn_lrelu_rows(ops.linear(h7, self.conv8[0].weight.squeeze(-1)), self.bn8, self.training, N)
         if depth == 9:
             return self._bcn(h8, B, N)
         logits = ops.linear(self.dp1(h8), self.conv9.weight.squeeze(-1))   # [M,classes]

@@ -21,6 +21,7 @@ from . import _lib
 COUT = 64
 TC_KNN_MIN_N = 256       # below this every key is a candidate anyway and the exact tile kernel is as fast
 EDGECONV_IMPL = 0        # dgcnn_edgeconv_args.impl: 0 = default (pipelined tcgen05), 1 = FP32 FMA, 2 = serial tcgen05 (A/B checks)
+FUSED_HEAD = True        # training: conv7 -> bn7 -> conv8 -> bn8 as one autograd node, activations between BN and GEMM only as planes
 FUSED_BWD = True         # two-conv blocks: conv_b backward with the scatter fused in (no dz_a[E,64]); False = the two-pass kernels
 # bf16 planes per operand in the GRADIENT GEMMs (forward GEMMs always use 3 = FP32-accurate).  2 = 3 MMAs per product,
 # relative error ~2^-17; 3 = 6 MMAs, ~2^-24 like the forward.  DGCNN_GRAD_NSPLIT overrides; bench.py reports both.
@@ -69,10 +70,12 @@ class KernelLog:
 LOG = KernelLog()
 
 # kernels launched by each entry point
-_LAUNCHES = {"dgcnn_knn_f32": 2, "dgcnn_knn_tc_f32": 6, "dgcnn_knn_small_f32": 3, "dgcnn_edgeconv_bwd_b": 2, "dgcnn_tc_gemm_f32": 3, "dgcnn_tc_gemm_bn_lrelu_segmax_f32": 5}
+_LAUNCHES = {"dgcnn_knn_f32": 2, "dgcnn_knn_tc_f32": 6, "dgcnn_knn_small_f32": 3, "dgcnn_edgeconv_bwd_b": 3, "dgcnn_edgeconv_bwd_b_fused": 3,
+             "dgcnn_tc_gemm_f32": 3, "dgcnn_tc_gemm_bn_lrelu_segmax_f32": 5, "dgcnn_rows_bn_lrelu_fwd": 3, "dgcnn_rows_bn_lrelu_bwd": 3,
+             "dgcnn_rows_colsum_f32": 2, "dgcnn_seg_loss_f32": 2}
 
 
-def _call(name: str, dev: torch.device, *args) -> None:
+def _call(name: str, dev: torch.device, *args, tag: str = "") -> None:
     """Enqueue one C-ABI entry point on `dev`'s current stream (appended as the last argument).
 
     The library launches on the CURRENT device, so a tensor living on another device than the caller's current one
@@ -89,7 +92,7 @@ def _call(name: str, dev: torch.device, *args) -> None:
             a.record()
             rc = fn(*args, st)
             b.record()
-            LOG.events.append((name, a, b))
+            LOG.events.append((name + tag, a, b))
         else:
             rc = fn(*args, st)
     _lib.check(rc)
@@ -188,7 +191,8 @@ def knn_rows(rows: torch.Tensor, B: int, Cn: int, N: int, k: int, method: str = 
         nbytes = getattr(lib, f"dgcnn_knn_{method}_workspace_bytes")(B, N)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=rows.device)
         if method == "tc":
-            _call("dgcnn_knn_tc_f32", rows.device, _ptr(rows), ld, B, Cn, N, k, 1 if ordered else 0, _ptr(idx), _ptr(ws), nbytes)
+            _call("dgcnn_knn_tc_f32", rows.device, _ptr(rows), ld, B, Cn, N, k, 1 if ordered else 0, _ptr(idx), _ptr(ws), nbytes,
+                  tag=f"[C={Cn}]")
         else:
             _call("dgcnn_knn_small_f32", rows.device, _ptr(rows), ld, B, Cn, N, k, _ptr(idx), _ptr(ws), nbytes)
         if stats is not None and method == "tc":
@@ -243,13 +247,15 @@ class Planes:
 
     __slots__ = ("buf", "R", "K", "nsplit")
 
-    def __init__(self, x: torch.Tensor, nsplit: int):
+    def __init__(self, x: Optional[torch.Tensor], nsplit: int, shape: Optional[Tuple[int, int]] = None, device=None):
+        """Planes(x, nsplit) splits x; Planes(None, nsplit, shape=(R, K), device=dev) only allocates (a kernel fills them)."""
         lib = _lib.load()
-        self.R, self.K = x.shape
+        self.R, self.K = x.shape if x is not None else shape
         self.nsplit = nsplit
         nbytes = lib.dgcnn_tc_planes_bytes(self.R, self.K, nsplit)
-        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-        _call("dgcnn_tc_split_planes_f32", x.device, _ptr(x), x.stride(0), x.stride(1), self.R, self.K, nsplit, _ptr(self.buf), nbytes)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=x.device if x is not None else device)
+        if x is not None:
+            _call("dgcnn_tc_split_planes_f32", x.device, _ptr(x), x.stride(0), x.stride(1), self.R, self.K, nsplit, _ptr(self.buf), nbytes)
 
 
 def gemm_planes(a: Planes, b: Planes, nsplit: int, transposed: bool = False) -> torch.Tensor:
@@ -427,6 +433,87 @@ def bn_lrelu_rows(y: torch.Tensor, bn_mod, training: bool, N: int, bias: Optiona
     if training:
         bn_mod.num_batches_tracked.add_(1)
     return h
+
+
+class HeadMlp(torch.autograd.Function):
+    """h8 = LReLU(bn8(conv8(LReLU(bn7(conv7_points(feat) + bias7[block]))))) (model.py:176-184, training form) as ONE node, so
+    that every tensor between a BatchNorm pass and the GEMM next to it lives only as operand planes:
+      forward   bn7's apply pass writes h7 as 3 planes (conv8's A operand; its first planes are conv8's weight-gradient operand)
+      backward  bn8's / bn7's apply passes write dy8 / dy7 as GRAD_NSPLIT planes (operands of the data- and weight-gradient
+                GEMMs); the per-block bias gradient comes out of bn7's apply pass.
+    Saves three split passes, a column-sum pass and the FP32 copies of h7, dy7, dy8 (~0.9 GB of HBM traffic per step)."""
+
+    @staticmethod
+    def forward(ctx, feat, bias7, w7, g7, b7, w8, g8, b8, bn7: BNState, bn8: BNState, N: int):
+        lib = _lib.load()
+        dev = feat.device
+        M = feat.shape[0]
+        f32 = dict(dtype=torch.float32, device=dev)
+        fp = Planes(feat.detach(), 3)
+        y7 = gemm_planes(fp, Planes(w7.detach(), 3), 3)
+        C7 = y7.shape[1]
+        bias_c = None if bias7 is None else bias7.detach().contiguous()
+        ws7 = torch.empty(lib.dgcnn_rows_bn_workspace_bytes(C7), dtype=torch.uint8, device=dev)
+        stat7, aff7 = torch.empty(2, C7, **f32), torch.empty(3 * C7, **f32)
+        h7p = Planes(None, 3, shape=(M, C7), device=dev)
+        _call("dgcnn_rows_bn_lrelu_fwd_planes", dev, _ptr(y7), M, C7, _ptr(bias_c), N, _ptr(g7.detach()), _ptr(b7.detach()), bn7.eps,
+              bn7.momentum, _ptr(bn7.running_mean), _ptr(bn7.running_var), _ptr(stat7[0]), _ptr(stat7[1]), _ptr(aff7), _ptr(h7p.buf),
+              h7p.buf.numel(), 3, _ptr(ws7), ws7.numel())
+        y8 = gemm_planes(h7p, Planes(w8.detach(), 3), 3)
+        C8 = y8.shape[1]
+        ws8 = torch.empty(lib.dgcnn_rows_bn_workspace_bytes(C8), dtype=torch.uint8, device=dev)
+        stat8, aff8 = torch.empty(2, C8, **f32), torch.empty(3 * C8, **f32)
+        h8 = torch.empty_like(y8)
+        _call("dgcnn_rows_bn_lrelu_fwd", dev, _ptr(y8), M, C8, _ptr(None), N, _ptr(g8.detach()), _ptr(b8.detach()), bn8.eps, bn8.momentum, 1,
+              _ptr(bn8.running_mean), _ptr(bn8.running_var), _ptr(stat8[0]), _ptr(stat8[1]), _ptr(aff8), _ptr(h8), _ptr(ws8), ws8.numel())
+        ctx.save_for_backward(y7, bias_c, w7.detach(), g7.detach(), stat7, aff7, y8, w8.detach(), g8.detach(), stat8, aff8)
+        ctx.fp, ctx.h7p, ctx.ws7, ctx.ws8, ctx.N = fp, h7p, ws7, ws8, N
+        return h8
+
+    @staticmethod
+    def backward(ctx, dh8):
+        y7, bias7, w7, g7, stat7, aff7, y8, w8, g8, stat8, aff8 = ctx.saved_tensors
+        fp, h7p, N = ctx.fp, ctx.h7p, ctx.N
+        dev = y7.device
+        M, C7 = y7.shape
+        C8 = y8.shape[1]
+        G = GRAD_NSPLIT
+        f32 = dict(dtype=torch.float32, device=dev)
+        dh8 = dh8.contiguous()
+        dg8, db8 = torch.empty(C8, **f32), torch.empty(C8, **f32)
+        dy8p = Planes(None, G, shape=(M, C8), device=dev)
+        _call("dgcnn_rows_bn_lrelu_bwd_planes", dev, _ptr(dh8), _ptr(y8), M, C8, _ptr(None), N, _ptr(g8), _ptr(stat8[1]), _ptr(aff8),
+              _ptr(dy8p.buf), dy8p.buf.numel(), G, _ptr(dg8), _ptr(db8), _ptr(None), _ptr(None), 0, _ptr(ctx.ws8), ctx.ws8.numel())
+        dh7 = gemm_planes(dy8p, Planes(w8.t(), G), G)                      # [M,C7] = dy8 @ w8
+        dw8 = gemm_planes(dy8p, h7p, G, transposed=True)                   # [C8,C7] = dy8^T h7
+        dg7, db7 = torch.empty(C7, **f32), torch.empty(C7, **f32)
+        dy7p = Planes(None, G, shape=(M, C7), device=dev)
+        dbias7 = csw = None
+        if bias7 is not None and ctx.needs_input_grad[1]:
+            dbias7 = torch.empty(M // N, C7, **f32)
+            csw = torch.empty(_lib.load().dgcnn_rows_colsum_workspace_bytes(M, C7, N), dtype=torch.uint8, device=dev)
+        _call("dgcnn_rows_bn_lrelu_bwd_planes", dev, _ptr(dh7), _ptr(y7), M, C7, _ptr(bias7), N, _ptr(g7), _ptr(stat7[1]), _ptr(aff7),
+              _ptr(dy7p.buf), dy7p.buf.numel(), G, _ptr(dg7), _ptr(db7), _ptr(dbias7), _ptr(csw), 0 if csw is None else csw.numel(),
+              _ptr(ctx.ws7), ctx.ws7.numel())
+        dfeat = gemm_planes(dy7p, Planes(w7.t(), G), G) if ctx.needs_input_grad[0] else None
+        dw7 = gemm_planes(dy7p, fp, G, transposed=True)
+        ctx.fp = ctx.h7p = None
+        return dfeat, dbias7, dw7, dg7, db7, dw8, dg8, db8, None, None, None
+
+
+def _bn_state_of(bn_mod) -> BNState:
+    mom = bn_mod.momentum
+    if mom is None:                      # cumulative moving average (nn.BatchNorm with momentum=None)
+        mom = 1.0 / float(int(bn_mod.num_batches_tracked) + 1)
+    return BNState(bn_mod.running_mean, bn_mod.running_var, bn_mod.eps, mom)
+
+
+def head_mlp(feat: torch.Tensor, bias7: Optional[torch.Tensor], w7: torch.Tensor, bn7, w8: torch.Tensor, bn8, N: int) -> torch.Tensor:
+    """Training-mode conv7(points part) + bn7 + LReLU + conv8 + bn8 + LReLU on point-major rows (see HeadMlp)."""
+    h8 = HeadMlp.apply(feat, bias7, w7, bn7.weight, bn7.bias, w8, bn8.weight, bn8.bias, _bn_state_of(bn7), _bn_state_of(bn8), N)
+    bn7.num_batches_tracked.add_(1)
+    bn8.num_batches_tracked.add_(1)
+    return h8
 
 
 def linear(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:

@@ -208,8 +208,10 @@ def kernel_flops(name: str, B: int, N: int = NPTS):
     """Algorithmic FLOPs of ALL launches of one entry point in one step."""
     M = B * N
     E = M * KNN
-    if name == "dgcnn_knn_tc_f32":                    # all three graphs: C = 4 (input), 64, 64 (feature space): 2*B*N^2*C
-        return 2.0 * B * N * N * (FEAT + 64 + 64)
+    if name == "dgcnn_knn_tc_f32[C=64]":              # the two feature-space graphs (layers 2 and 3): 2*B*N^2*C each
+        return 2.0 * B * N * N * (64 + 64)
+    if name == f"dgcnn_knn_tc_f32[C={FEAT}]":         # the input-space graph (same kernel, C padded to one 64-wide K atom)
+        return 2.0 * B * N * N * FEAT
     if name == "dgcnn_edgeconv_conv_a_train":         # conv1 (2F->64), conv3, conv5 (128->64) when run as per-edge GEMMs
         return 2.0 * E * 64 * (2 * FEAT + 128 + 128)
     if name == "dgcnn_edgeconv_lin_conv_a":           # conv1 + conv3 as y = U_j + V_i (algorithmic work of the per-edge convolution)
@@ -218,7 +220,7 @@ def kernel_flops(name: str, B: int, N: int = NPTS):
         return 2.0 * E * 64 * 128
     if name == "dgcnn_edgeconv_conv_b_train":         # conv2, conv4 (64->64)
         return 2.0 * E * 64 * 64 * 2
-    if name == "dgcnn_edgeconv_bwd_b":                # per block: dW_b and dh GEMMs
+    if name in ("dgcnn_edgeconv_bwd_b", "dgcnn_edgeconv_bwd_b_fused"):   # per block: dW_b and dh GEMMs
         return 2.0 * E * 64 * 64 * 2 * 2
     if name == "dgcnn_tc_gemm_planes_f32":            # conv7/8/9 forward + dgrad + wgrad, conv6 backward, EdgeConv point-level GEMMs
         head = 2.0 * M * (192 * 512 + 512 * 256 + 256 * CLASSES) * 3 + 2.0 * M * 192 * 192 * 2

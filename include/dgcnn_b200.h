@@ -269,6 +269,20 @@ int dgcnn_rows_bn_lrelu_fwd(const float* y, int M, int C, const float* bias, int
 int dgcnn_rows_bn_lrelu_bwd(const float* dh, const float* y, int M, int C, const float* bias, int N, const float* gamma,
                             const float* rstd, const float* aff, float* dy, float* dgamma, float* dbeta,
                             void* workspace, size_t workspace_bytes, void* stream);
+/* The same two passes with the result written directly as GEMM operand planes (dgcnn_tc_split_planes_f32's format, nsplit =
+ * 2 or 3, rows padded with zeros to a multiple of 128; `planes` 128-byte aligned, dgcnn_tc_planes_bytes(M, C, nsplit) bytes):
+ * the FP32 activation / gradient between a BatchNorm pass and the GEMM that consumes it never exists.  Training form only
+ * (batch statistics).  C must be a multiple of 64.  dbias (optional, [M/N, C]): the per-block bias gradient, from the same
+ * pass (colsum_workspace: dgcnn_rows_colsum_workspace_bytes(M, C, N) bytes).                                                                  */
+int dgcnn_rows_bn_lrelu_fwd_planes(const float* y, int M, int C, const float* bias, int N, const float* gamma,
+                                   const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                                   float* mean, float* rstd, float* aff, void* planes, size_t planes_bytes, int nsplit,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+int dgcnn_rows_bn_lrelu_bwd_planes(const float* dh, const float* y, int M, int C, const float* bias, int N,
+                                   const float* gamma, const float* rstd, const float* aff, void* planes,
+                                   size_t planes_bytes, int nsplit, float* dgamma, float* dbeta, float* dbias,
+                                   void* colsum_workspace, size_t colsum_workspace_bytes, void* workspace,
+                                   size_t workspace_bytes, void* stream);
 
 /* out[s][c] = sum_{n < N} x[s*N + n][c] for the M/N segments of x[M,C] (the per-block bias gradient `dy.view(B,N,C).sum(1)`
  * of the conv7 split, column sums of the features); deterministic two-pass FP64 reduction.  C % 4 == 0, C <= 1024.    */

@@ -93,3 +93,51 @@ def test_rows_colsum_matches_fp64(pkg, B, N, C):
     assert out.shape == (B, C)
     assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 1e-6
     assert torch.equal(out, pkg.ops.rows_colsum(x, N))          # deterministic
+
+
+@pytest.mark.parametrize("B,N", [(3, 700), (2, 1001), (8, 7000)])
+def test_head_mlp_node_matches_fp64_and_the_unfused_chain(pkg, B, N):
+    """ops.head_mlp (conv7 + bn7 + LReLU + conv8 + bn8 + LReLU as one node, activations between BN and GEMM only as operand
+    planes) against an FP64 composition of the reference's layers (model.py:176-184) and against the op-by-op chain."""
+    ops = pkg.ops
+    g = torch.Generator().manual_seed(B * 31 + N)
+    M = B * N
+    feat0 = torch.randn(M, 192, generator=g).to(DEV)
+    bias0 = torch.randn(B, 512, generator=g).to(DEV)
+    w7_0 = (torch.randn(512, 192, generator=g) * 0.08).to(DEV)
+    w8_0 = (torch.randn(256, 512, generator=g) * 0.05).to(DEV)
+    up = torch.randn(M, 256, generator=g).to(DEV)
+
+    def run(mode):
+        dt = torch.float64 if mode == "fp64" else torch.float32
+        feat, bias, w7, w8 = (t.clone().to(dt).requires_grad_(True) for t in (feat0, bias0, w7_0, w8_0))
+        bn7, bn8 = torch.nn.BatchNorm1d(512).to(DEV).to(dt), torch.nn.BatchNorm1d(256).to(DEV).to(dt)
+        with torch.no_grad():
+            bn7.weight.copy_(torch.linspace(-1.0, 1.5, 512)); bn7.bias.copy_(torch.linspace(-0.3, 0.3, 512))
+            bn8.weight.copy_(torch.linspace(1.2, -0.8, 256)); bn8.bias.copy_(torch.linspace(0.2, -0.2, 256))
+        if mode == "fused":
+            h8 = ops.head_mlp(feat, bias, w7, bn7, w8, bn8, N)
+        elif mode == "chain":
+            h7 = ops.bn_lrelu_rows(ops.linear(feat, w7), bn7, True, N, bias=bias)
+            h8 = ops.bn_lrelu_rows(ops.linear(h7, w8), bn8, True, N)
+        else:
+            v7 = feat @ w7.t() + bias.repeat_interleave(N, dim=0)
+            h7 = F.leaky_relu(bn7(v7), 0.2)
+            h8 = F.leaky_relu(bn8(h7 @ w8.t()), 0.2)
+        (h8 * up.to(dt)).sum().backward()
+        grads = [feat.grad, bias.grad, w7.grad, w8.grad, bn7.weight.grad, bn7.bias.grad, bn8.weight.grad, bn8.bias.grad]
+        state = [bn7.running_mean, bn7.running_var, bn8.running_mean, bn8.running_var, bn7.num_batches_tracked, bn8.num_batches_tracked]
+        return h8.detach(), grads, state
+
+    hf, gf, sf = run("fused")
+    hc, gc, sc = run("chain")
+    hr, gr, sr = run("fp64")
+    assert ((hf.double() - hr).abs().max() / hr.abs().max()).item() < 2e-5
+    assert ((hf - hc).abs().max() / hc.abs().max()).item() < 2e-6           # same FP32-accurate forward arithmetic
+    for a, b in zip(sf, sr):
+        torch.testing.assert_close(a.double(), b.double(), rtol=1e-5, atol=1e-6)
+    names = ["feat", "bias7", "w7", "w8", "gamma7", "beta7", "gamma8", "beta8"]
+    for n, a, c, r in zip(names, gf, gc, gr):
+        ef = ((a.double() - r).norm() / (r.norm() + 1e-30)).item()
+        ec = ((c.double() - r).norm() / (r.norm() + 1e-30)).item()
+        assert ef < max(2e-4, 3 * ec), (n, ef, ec)                           # 2-plane gradient GEMMs: 2^-17 per product
