@@ -359,8 +359,9 @@ tc_gemm_tn_kernel(const unsigned char* __restrict__ Ap, int KA_a, int ns_a, cons
   // operand units of this tile that exist (the rest of the stage stays zero)
   const int a_units = max(0, min(2, KA_a - 2 * mt)), b_units = max(0, min(BN / 64, KA_b - nt * (BN / 64)));
 
-  // zero the stages once: skipped (out-of-range) units must read as zeros
-  for (uint32_t i = threadIdx.x; i < STAGES * SM::stage / 16; i += blockDim.x) reinterpret_cast<uint4*>(tiles)[i] = make_uint4(0, 0, 0, 0);
+  // skipped (out-of-range) units must read as zeros: zero the stages once, only when this tile has such units
+  if (a_units < 2 || b_units < BN / 64)
+    for (uint32_t i = threadIdx.x; i < STAGES * SM::stage / 16; i += blockDim.x) reinterpret_cast<uint4*>(tiles)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       tc::mbar_init(full + s, 1);

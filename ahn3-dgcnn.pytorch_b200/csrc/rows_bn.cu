@@ -80,17 +80,19 @@ __global__ void __launch_bounds__(kRbThreads) rows_bn_reduce_kernel(RowsBn p, co
   }
 }
 
-// CTA = 32 channels x 32 part groups (1024 threads): group g adds the per-CTA partials g, g+32, ... (coalesced 256-byte
-// reads), the 32 group sums are added in a fixed order, all in FP64 (deterministic).  One warp per channel with
-// 8-byte strided reads made these two-value reductions cost 19 us each (5 launches per step).
+// CTA = 8 channels x 128 part groups (1024 threads): group g adds the per-CTA partials g, g+128, ... (a part row
+// contributes 64 contiguous bytes = two fully used sectors per statistic), then the group sums are added in a fixed order in
+// two levels, all in FP64 (deterministic).  C/8 CTAs: up to 9.7 MB of partials (C = 512) are read by 64 SMs, not by 16.
+constexpr int kFinCols = 8;
 __device__ __forceinline__ bool rows_bn_sum_partials(const double* __restrict__ partials, int nparts, int C, int& c, double& s, double& q) {
-  __shared__ double red[2][32][33];
-  const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
-  c = blockIdx.x * 32 + cl;
+  __shared__ double red[2][128][kFinCols + 1];
+  __shared__ double red2[2][8][kFinCols + 1];
+  const int cl = threadIdx.x & 7, g = threadIdx.x >> 3;
+  c = blockIdx.x * kFinCols + cl;
   double a = 0.0, b = 0.0;
   if (c < C) {
 #pragma unroll 4
-    for (int i = g; i < nparts; i += 32) {
+    for (int i = g; i < nparts; i += 128) {
       a += partials[static_cast<size_t>(i) * 2 * C + c];
       b += partials[static_cast<size_t>(i) * 2 * C + C + c];
     }
@@ -98,10 +100,19 @@ __device__ __forceinline__ bool rows_bn_sum_partials(const double* __restrict__ 
   red[0][g][cl] = a;
   red[1][g][cl] = b;
   __syncthreads();
-  if (g != 0 || c >= C) return false;
+  if (threadIdx.x < 64) {
+    const int sub = threadIdx.x >> 3;
+    double a2 = 0.0, b2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { a2 += red[0][sub * 16 + j][cl]; b2 += red[1][sub * 16 + j][cl]; }
+    red2[0][sub][cl] = a2;
+    red2[1][sub][cl] = b2;
+  }
+  __syncthreads();
+  if (threadIdx.x >= kFinCols || c >= C) return false;
   s = 0.0; q = 0.0;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) { s += red[0][j][cl]; q += red[1][j][cl]; }
+  for (int j = 0; j < 8; ++j) { s += red2[0][j][cl]; q += red2[1][j][cl]; }
   return true;
 }
 
@@ -361,7 +372,7 @@ extern "C" int dgcnn_rows_bn_lrelu_fwd(const float* y, int M, int C, const float
     int rpc;
     const int grid = rows_bn_grid(M, &rpc);
     rows_bn_reduce_kernel<false><<<grid, kRbThreads, 0, st>>>(p, nullptr, rpc, partials);
-    rows_bn_fwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partials, grid, C, static_cast<double>(M), gamma, beta, eps,
+    rows_bn_fwd_finalize_kernel<<<(C + kFinCols - 1) / kFinCols, 1024, 0, st>>>(partials, grid, C, static_cast<double>(M), gamma, beta, eps,
                                                                  momentum, running_mean, running_var, mean, rstd, aff);
   } else {
     rows_bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, eps, running_mean, running_var, aff);
@@ -386,7 +397,7 @@ extern "C" int dgcnn_rows_bn_lrelu_bwd(const float* dh, const float* y, int M, i
   int rpc;
   const int grid = rows_bn_grid(M, &rpc);
   rows_bn_reduce_kernel<true><<<grid, kRbThreads, 0, st>>>(p, dh, rpc, partials);
-  rows_bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partials, grid, C, static_cast<double>(M), gamma, rstd, dgamma, dbeta, coef);
+  rows_bn_bwd_finalize_kernel<<<(C + kFinCols - 1) / kFinCols, 1024, 0, st>>>(partials, grid, C, static_cast<double>(M), gamma, rstd, dgamma, dbeta, coef);
   const int blocks = rows_bn_apply_grid(M, C);
   rows_bn_apply_kernel<true, 0><<<blocks, kRbThreads, 0, st>>>(p, dh, coef, dy, nullptr, 0, 0, 0, nullptr);
   DG_CUDA(cudaGetLastError());
@@ -428,7 +439,7 @@ extern "C" int dgcnn_rows_bn_lrelu_fwd_planes(const float* y, int M, int C, cons
   int rpc;
   const int grid = rows_bn_grid(M, &rpc);
   rows_bn_reduce_kernel<false><<<grid, kRbThreads, 0, st>>>(p, nullptr, rpc, partials);
-  rows_bn_fwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partials, grid, C, static_cast<double>(M), gamma, beta, eps, momentum,
+  rows_bn_fwd_finalize_kernel<<<(C + kFinCols - 1) / kFinCols, 1024, 0, st>>>(partials, grid, C, static_cast<double>(M), gamma, beta, eps, momentum,
                                                                running_mean, running_var, mean, rstd, aff);
   const int Mpad = (M + 127) / 128 * 128;
   int rpc2;
@@ -460,7 +471,7 @@ extern "C" int dgcnn_rows_bn_lrelu_bwd_planes(const float* dh, const float* y, i
   int rpc;
   const int grid = rows_bn_grid(M, &rpc);
   rows_bn_reduce_kernel<true><<<grid, kRbThreads, 0, st>>>(p, dh, rpc, partials);
-  rows_bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partials, grid, C, static_cast<double>(M), gamma, rstd, dgamma, dbeta, coef);
+  rows_bn_bwd_finalize_kernel<<<(C + kFinCols - 1) / kFinCols, 1024, 0, st>>>(partials, grid, C, static_cast<double>(M), gamma, rstd, dgamma, dbeta, coef);
   const int Mpad = (M + 127) / 128 * 128;
   // dbias (the gradient of the per-block bias = per-block column sums of dy) comes out of the same pass
   DG_REQUIRE(!dbias || (bias && colsum_workspace && colsum_workspace_bytes >= dgcnn_rows_colsum_workspace_bytes(M, C, N)), DGCNN_E_INVALID,
