@@ -250,7 +250,9 @@ def roofline_of(per_kernel: dict, steps: int, B: int, N: int, peaks: dict, sm_mh
     kind = ("measured sustained dense bf16 tensor peak (MEASURED_PEAKS.json); the kernels issue 3 (bf16x2 split) or 6 (bf16x3) "
             "kind::f16 MMAs per algorithmic product for FP32-level accuracy, so the ceiling for ALGORITHMIC flops is peak/3 .. peak/6")
     traffic = None
-    try:        # measured DRAM bytes per launch from the committed `ncu --set full` capture (not a live number)
+    try:        # measured DRAM bytes per launch from the committed `ncu --set full` capture of the TRAINING shape (not a live number)
+        if (B, N) != (B_PER_GPU, NPTS):
+            raise KeyError("no capture at this shape")
         traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(dom, {}).get("bytes_per_launch")
     except Exception:
         pass
