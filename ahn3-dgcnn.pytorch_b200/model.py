@@ -175,6 +175,7 @@ class DGCNN(nn.Module):
     def _forward(self, x, depth, forced_idx):
         B, Fdim, N = x.shape
         self.last_idx = []
+        ops.clear_shared_planes()
         rows0 = ops.pack_rows(x.float() if x.dtype != torch.float32 else x)
         x1 = self._edge_block(rows0, self._graph(rows0, B, Fdim, N, 1, forced_idx), B, Fdim, N, 1, 2)
         if depth == 1:

@@ -276,6 +276,30 @@ def gemm_planes(a: Planes, b: Planes, nsplit: int, transposed: bool = False) -> 
     return d
 
 
+# Planes of activations that several autograd nodes of ONE step consume (feat: the head node's forward and the global
+# feature's backward).  Keyed by the tensor's memory and version; the model clears it at the start of every forward, and the
+# producers stay alive in the autograd graph until then, so an address cannot be reused under a live entry.
+_shared_planes = {}
+
+
+def _planes_key(x: torch.Tensor):
+    return (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x._version, str(x.device))
+
+
+def share_planes(x: torch.Tensor, planes: Planes) -> None:
+    _shared_planes[_planes_key(x)] = planes
+
+
+def shared_planes(x: torch.Tensor, nsplit: int) -> Planes:
+    """The planes registered for x if they hold at least nsplit planes, else a fresh split."""
+    pl = _shared_planes.get(_planes_key(x))
+    return pl if pl is not None and pl.nsplit >= nsplit else Planes(x, nsplit)
+
+
+def clear_shared_planes() -> None:
+    _shared_planes.clear()
+
+
 class TcLinear(torch.autograd.Function):
     """y = x @ w^T (x [M,K], w [N,K]) with all three GEMMs (y, dx, dw) on the tensor cores.
 
@@ -355,7 +379,7 @@ class GlobalFeature(torch.autograd.Function):
         dev = feat.device
         # dense parts on the tensor cores: dfeat = -feat (W^T diag(kappa) W) - b' W  (the sign is folded into the small matrix)
         gram_neg = tc_gemm((w * (-kappa)[:, None]).t(), w.t(), nsplit=GRAD_NSPLIT)      # [K,K] = -W^T diag(kappa) W (symmetric)
-        featp = Planes(feat, GRAD_NSPLIT)                                                # split once for both feature GEMMs
+        featp = shared_planes(feat, GRAD_NSPLIT)                                         # the head node's planes of feat, or one split for both GEMMs
         dfeat = gemm_planes(featp, Planes(gram_neg, GRAD_NSPLIT), GRAD_NSPLIT)
         cvec = torch.empty(K, dtype=torch.float32, device=dev)
         _call("dgcnn_vecmat_f32", dev, _ptr(bprime), _ptr(w), w.stride(0), E, K, -1.0, _ptr(cvec))
@@ -450,6 +474,7 @@ class HeadMlp(torch.autograd.Function):
         M = feat.shape[0]
         f32 = dict(dtype=torch.float32, device=dev)
         fp = Planes(feat.detach(), 3)
+        share_planes(feat.detach(), fp)                  # GlobalFeature.backward contracts over the same planes
         y7 = gemm_planes(fp, Planes(w7.detach(), 3), 3)
         C7 = y7.shape[1]
         bias_c = None if bias7 is None else bias7.detach().contiguous()
@@ -639,12 +664,13 @@ class EdgeConvTrain(torch.autograd.Function):
         vs = None if (lin or EDGECONV_IMPL == 0) else _v_scratch(B, Cn, N, dev)
         a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, None, COUT, vs)
 
-        uv = uv2 = fused = None
+        uv = uv2 = fused = xp = None
         if two and EDGECONV_IMPL == 0:
             # first conv of a two-conv block: y_a = U_j + V_i written per edge (BN_a needs batch statistics before conv_b
             # can start), no per-edge GEMM.  Also for the input block: y_a carries the centre term Wa2 x_i (~|W||x|) either
             # way, so forming x_j - x_i first buys no accuracy at the level of y_a (both are within a few 1e-8 |W||x|).
-            uv2 = tc_gemm(rows[:, :Cn], _lin_weight(wa, Cn))
+            xp = Planes(rows[:, :Cn], 3)                 # X planes: this GEMM now, the weight gradient in the backward
+            uv2 = gemm_planes(xp, Planes(_lin_weight(wa, Cn), 3), 3)
             if FUSED_BWD and GRAD_NSPLIT == 2 and k >= 8 and N >= 16:
                 # + the out-edge sums of y_a: with them (and the in-edge sums the backward accumulates) dz_a[E,64] is never formed
                 fused = torch.empty(M, COUT, **f32)
@@ -655,7 +681,8 @@ class EdgeConvTrain(torch.autograd.Function):
                       _ptr(partials))
         elif lin:
             # y = U_j + V_i: one point-level GEMM + a gather pass (extrema over k, batch sums); nothing per-edge in HBM
-            uv = tc_gemm(rows[:, :Cn], _lin_weight(wa, Cn))
+            xp = Planes(rows[:, :Cn], 3)
+            uv = gemm_planes(xp, Planes(_lin_weight(wa, Cn), 3), 3)
             _call("dgcnn_edgeconv_lin_extrema", dev, C.byref(a), _ptr(uv), uv.stride(0), _ptr(uv[:, COUT:]), uv.stride(0), _ptr(partials),
                   _ptr(ymax), _ptr(ymin), _ptr(amax), _ptr(amin))
         else:
@@ -679,6 +706,7 @@ class EdgeConvTrain(torch.autograd.Function):
         ctx.two = two
         ctx.lin = lin
         ctx.fused = fused
+        ctx.xp = xp
         ctx.uv2 = uv2                                   # [U | V] of a two-conv block: the backward gathers it instead of re-reading y_a
         ctx.save_for_backward(rows, idx, wa, wb if two else wa, gamma_a.detach(), gamma_b.detach() if two else gamma_a.detach(),
                               uv if lin else y_a, stat_a, stat_b if two else stat_a, ysel, arg)
@@ -766,7 +794,9 @@ class EdgeConvTrain(torch.autograd.Function):
             dx = gemm_planes(rsp, Planes(wcat.t(), GRAD_NSPLIT), GRAD_NSPLIT)
             if dx.shape != ctx.x_shape:                                 # rows padded to a multiple of 4 channels
                 dx = torch.nn.functional.pad(dx, (0, ctx.x_shape[1] - dx.shape[1]))
-        G = gemm_planes(rsp, Planes(X, GRAD_NSPLIT), GRAD_NSPLIT, transposed=True)        # [128, C] = [r|s]^T X
+        xp = ctx.xp if ctx.xp is not None else Planes(X, GRAD_NSPLIT)
+        ctx.xp = None
+        G = gemm_planes(rsp, xp, GRAD_NSPLIT, transposed=True)                            # [128, C] = [r|s]^T X
         dwa = torch.cat((G[:COUT] - G[COUT:], G[COUT:]), dim=1)
         # returns: x, idx, meta, w_a, gamma_a, beta_a, w_b, gamma_b, beta_b, bn_a, bn_b
         if two:
