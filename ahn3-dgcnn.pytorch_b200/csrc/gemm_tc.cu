@@ -343,7 +343,7 @@ tc_gemm_kernel(const unsigned char* __restrict__ Ap, const unsigned char* __rest
 template <int NS, int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 tc_gemm_tn_kernel(const unsigned char* __restrict__ Ap, int KA_a, int ns_a, const unsigned char* __restrict__ Bp, int KA_b, int ns_b,
-                  float* __restrict__ D, int ldd, int N1, int N2, int RT, int rt_per_split, size_t split_stride) {
+                  float* __restrict__ D, int ldd, int N1, int N2, int RT, int rt_per_split, size_t split_stride, int accumulate) {
   using SM = GemmSmem<NS, BN, STAGES>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -445,7 +445,21 @@ tc_gemm_tn_kernel(const unsigned char* __restrict__ Ap, int KA_a, int ns_a, cons
       const int n0 = nt * BN + c0;
       if (row < N1 && n0 < N2) {
         float* dst = D + static_cast<size_t>(row) * ldd + n0;
-        if (n0 + 32 <= N2 && (ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0) {
+        const bool vec = n0 + 32 <= N2 && (ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0;
+        if (accumulate) {
+          // every split adds its partial tile into the (zeroed) output: no partial tiles in HBM, no reduce pass; the
+          // summation order over the splits is not fixed (like the scatter reductions of the EdgeConv backward)
+          if (vec) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v[i]), "f"(v[i + 1]), "f"(v[i + 2]), "f"(v[i + 3])
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n0 + i < N2) atomicAdd(dst + i, v[i]);
+          }
+        } else if (vec) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         } else {
@@ -580,7 +594,7 @@ static int tn_splits(int N1, int N2, int BN, int RT) {
 }
 template <int NS, int BN, int STAGES>
 static int launch_gemm_tn(const unsigned char* Ap, int KA_a, int ns_a, const unsigned char* Bp, int KA_b, int ns_b, float* D, int ldd,
-                          int N1, int N2, int RT, float* partials, cudaStream_t st) {
+                          int N1, int N2, int RT, float* partials, bool atomic, cudaStream_t st) {
   using SM = GemmSmem<NS, BN, STAGES>;
   auto kern = tc_gemm_tn_kernel<NS, BN, STAGES>;
   DG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SM::bytes)));
@@ -588,12 +602,18 @@ static int launch_gemm_tn(const unsigned char* Ap, int KA_a, int ns_a, const uns
   const int per = (RT + splits - 1) / splits;
   dim3 grid((N2 + BN - 1) / BN, (N1 + 127) / 128, (RT + per - 1) / per);
   if (grid.z == 1) {
-    kern<<<grid, 192, SM::bytes, st>>>(Ap, KA_a, ns_a, Bp, KA_b, ns_b, D, ldd, N1, N2, RT, per, 0);
+    kern<<<grid, 192, SM::bytes, st>>>(Ap, KA_a, ns_a, Bp, KA_b, ns_b, D, ldd, N1, N2, RT, per, 0, 0);
+    DG_CUDA(cudaGetLastError());
+    return DGCNN_OK;
+  }
+  if (atomic) {
+    DG_CUDA(cudaMemset2DAsync(D, static_cast<size_t>(ldd) * 4, 0, static_cast<size_t>(N2) * 4, N1, st));
+    kern<<<grid, 192, SM::bytes, st>>>(Ap, KA_a, ns_a, Bp, KA_b, ns_b, D, ldd, N1, N2, RT, per, 0, 1);
     DG_CUDA(cudaGetLastError());
     return DGCNN_OK;
   }
   const size_t stride = static_cast<size_t>(N1) * N2;
-  kern<<<grid, 192, SM::bytes, st>>>(Ap, KA_a, ns_a, Bp, KA_b, ns_b, partials, N2, N1, N2, RT, per, stride);
+  kern<<<grid, 192, SM::bytes, st>>>(Ap, KA_a, ns_a, Bp, KA_b, ns_b, partials, N2, N1, N2, RT, per, stride, 0);
   DG_CUDA(cudaGetLastError());
   splitk_reduce_kernel<<<static_cast<int>(std::min<size_t>((stride + 255) / 256, 148 * 8)), 256, 0, st>>>(partials, stride, grid.z, D, ldd,
                                                                                                       N1, N2);
@@ -624,6 +644,7 @@ extern "C" int dgcnn_tc_split_planes_f32(const float* X, int64_t row_stride, int
 extern "C" size_t dgcnn_tc_gemm_planes_workspace_bytes(int mode, int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (mode == 0) return static_cast<size_t>(splitk_factor(M, N, (K + 63) / 64)) * M * N * sizeof(float) + 1024;
+  if (mode == 2) return 1024;      // the splits are added into D
   const int RT = (K + 63) / 64;
   return static_cast<size_t>(tn_splits(M, N, 128, RT)) * M * N * sizeof(float) + 1024;
 }
@@ -651,12 +672,12 @@ extern "C" int dgcnn_tc_gemm_planes_f32(int mode, const void* a_planes, int a_co
       return launch_gemm<2, 256, 2>(Ap, Bp, D, ldd, M, N, KA, partials, st, a_nsplit, b_nsplit);
     return launch_gemm<2, 128, 3>(Ap, Bp, D, ldd, M, N, KA, partials, st, a_nsplit, b_nsplit);
   }
-  DG_REQUIRE(mode == 1, DGCNN_E_INVALID, "tc_gemm_planes: mode must be 0 (A B^T) or 1 (A^T B)");
+  DG_REQUIRE(mode == 1 || mode == 2, DGCNN_E_INVALID, "tc_gemm_planes: mode must be 0 (A B^T), 1 (A^T B) or 2 (A^T B, splits added atomically)");
   // D[M,N] = sum_r A[r, m] B[r, n]: planes of A over [K rows, a_cols = M], of B over [K rows, b_cols = N]
   DG_REQUIRE(a_cols == M && b_cols == N, DGCNN_E_INVALID, "tc_gemm_planes: mode 1 needs a_cols == M and b_cols == N");
   const int RT = (K + 63) / 64, KA_a = (M + 63) / 64, KA_b = (N + 63) / 64;
-  if (nsplit == 3) return launch_gemm_tn<3, 128, 2>(Ap, KA_a, a_nsplit, Bp, KA_b, b_nsplit, D, ldd, M, N, RT, partials, st);
-  return launch_gemm_tn<2, 128, 3>(Ap, KA_a, a_nsplit, Bp, KA_b, b_nsplit, D, ldd, M, N, RT, partials, st);
+  if (nsplit == 3) return launch_gemm_tn<3, 128, 2>(Ap, KA_a, a_nsplit, Bp, KA_b, b_nsplit, D, ldd, M, N, RT, partials, mode == 2, st);
+  return launch_gemm_tn<2, 128, 3>(Ap, KA_a, a_nsplit, Bp, KA_b, b_nsplit, D, ldd, M, N, RT, partials, mode == 2, st);
 }
 
 // ---------------------------------------------------------------------------------------------

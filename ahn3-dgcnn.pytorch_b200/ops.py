@@ -21,6 +21,7 @@ from . import _lib
 COUT = 64
 TC_KNN_MIN_N = 256       # below this every key is a candidate anyway and the exact tile kernel is as fast
 EDGECONV_IMPL = 0        # dgcnn_edgeconv_args.impl: 0 = default (pipelined tcgen05), 1 = FP32 FMA, 2 = serial tcgen05 (A/B checks)
+ATOMIC_WGRAD = True      # row-contraction (weight-gradient) GEMMs add their row splits into D atomically; False = partial tiles + fixed-order reduce
 FUSED_HEAD = True        # training: conv7 -> bn7 -> conv8 -> bn8 as one autograd node, activations between BN and GEMM only as planes
 FUSED_BWD = True         # two-conv blocks: conv_b backward with the scatter fused in (no dz_a[E,64]); False = the two-pass kernels
 # bf16 planes per operand in the GRADIENT GEMMs (forward GEMMs always use 3 = FP32-accurate).  2 = 3 MMAs per product,
@@ -265,7 +266,7 @@ def gemm_planes(a: Planes, b: Planes, nsplit: int, transposed: bool = False) -> 
     dev = a.buf.device
     if transposed:
         assert a.R == b.R
-        M, N, K, mode = a.K, b.K, a.R, 1
+        M, N, K, mode = a.K, b.K, a.R, (2 if ATOMIC_WGRAD else 1)
     else:
         assert a.K == b.K
         M, N, K, mode = a.R, b.R, a.K, 0

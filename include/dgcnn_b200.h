@@ -218,6 +218,9 @@ int dgcnn_tc_gemm_f32(const float* A, int64_t a_row_stride, int64_t a_col_stride
  *   mode 1   D[M,N] = sum_r A[r,m] B[r,n]  planes of A over [K rows, a_cols = M], of B over [K rows, b_cols = N]: the
  *            contraction runs over the unit ROWS (MN-major operand descriptors), so a weight gradient dW = dY^T X reuses
  *            the planes of dY (made for the data gradient) and of X (made for the forward) — no transposing re-split.
+ *            The rows are split over the CTAs; partial tiles go through the workspace and are summed in a fixed order.
+ *   mode 2   mode 1 with the partial tiles ADDED into D by float reductions instead (D is zeroed first): no partial tiles in
+ *            HBM and no reduce pass, summation order over the splits not fixed.
  * a_nsplit / b_nsplit = planes stored per operand (2 or 3), nsplit <= both = planes used.  The layer sequence of a Linear:
  * forward split(X,3) -> mode 0; backward split(dY,2) -> mode 0 with split(W^T,2) for dX, mode 1 with X's planes for dW.  */
 size_t dgcnn_tc_planes_bytes(int R, int K, int nsplit);

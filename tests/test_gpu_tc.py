@@ -178,8 +178,15 @@ def test_row_contraction_gemm_matches_fp64(pkg, R, M, N, nsplit):
     A = (torch.randn(R, M, generator=g) * 2).to(DEV)
     B = torch.randn(R, N, generator=g).to(DEV)
     ap, bp = pkg.ops.Planes(A, 3), pkg.ops.Planes(B, nsplit)              # stored plane counts may differ from the used count
-    D = pkg.ops.gemm_planes(ap, bp, nsplit, transposed=True)
+    D = pkg.ops.gemm_planes(ap, bp, nsplit, transposed=True)                # default: row splits added atomically (mode 2)
+    old = pkg.ops.ATOMIC_WGRAD
+    try:
+        pkg.ops.ATOMIC_WGRAD = False
+        D1 = pkg.ops.gemm_planes(ap, bp, nsplit, transposed=True)           # partial tiles + fixed-order reduce (mode 1)
+    finally:
+        pkg.ops.ATOMIC_WGRAD = old
     torch.cuda.synchronize()
+    assert ((D - D1).abs() / (A.double().abs().t() @ B.double().abs()).float()).max().item() < 5e-7
     ref = A.double().t() @ B.double()
     scale = A.double().abs().t() @ B.double().abs()
     err = ((D.double() - ref).abs() / scale).max().item()
