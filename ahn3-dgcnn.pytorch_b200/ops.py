@@ -21,6 +21,7 @@ from . import _lib
 COUT = 64
 TC_KNN_MIN_N = 256       # below this every key is a candidate anyway and the exact tile kernel is as fast
 EDGECONV_IMPL = 0        # dgcnn_edgeconv_args.impl: 0 = default (pipelined tcgen05), 1 = FP32 FMA, 2 = serial tcgen05 (A/B checks)
+NARROW_LINEAR = True     # outputs <= 8 (classifier): streaming FP32-FMA kernel instead of padded tensor-core tiles
 ATOMIC_WGRAD = True      # row-contraction (weight-gradient) GEMMs add their row splits into D atomically; False = partial tiles + fixed-order reduce
 FUSED_HEAD = True        # training: conv7 -> bn7 -> conv8 -> bn8 as one autograd node, activations between BN and GEMM only as planes
 FUSED_BWD = True         # two-conv blocks: conv_b backward with the scatter fused in (no dz_a[E,64]); False = the two-pass kernels
@@ -542,9 +543,43 @@ def head_mlp(feat: torch.Tensor, bias7: Optional[torch.Tensor], w7: torch.Tensor
     return h8
 
 
+class LinearNarrow(torch.autograd.Function):
+    """y = x @ w^T for at most 8 outputs (the classifier, model.py:141): streaming FP32-FMA passes (csrc/linear_narrow.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        xd, wd = x.detach(), w.detach()
+        if xd.stride(1) != 1 or xd.stride(0) % 4 or xd.data_ptr() % 16:
+            xd = xd.contiguous()
+        if wd.stride(1) != 1:
+            wd = wd.contiguous()
+        M, K = xd.shape
+        NO = wd.shape[0]
+        y = torch.empty(M, NO, dtype=torch.float32, device=xd.device)
+        _call("dgcnn_linear_narrow_fwd_f32", xd.device, _ptr(xd), xd.stride(0), _ptr(wd), wd.stride(0), M, K, NO, _ptr(y), NO)
+        ctx.save_for_backward(xd, wd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xd, wd = ctx.saved_tensors
+        M, K = xd.shape
+        NO = wd.shape[0]
+        dy = dy.contiguous()
+        dx = torch.empty(M, K, dtype=torch.float32, device=xd.device) if ctx.needs_input_grad[0] else None
+        dw = torch.empty(NO, K, dtype=torch.float32, device=xd.device)
+        _call("dgcnn_linear_narrow_bwd_f32", xd.device, _ptr(xd), xd.stride(0), _ptr(dy), NO, _ptr(wd), wd.stride(0), M, K, NO,
+              _ptr(dx), K, _ptr(dw))
+        return dx, dw
+
+
 def linear(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
-    """x @ w^T on the tensor cores (tcgen05, FP32-accurate split); no library GEMM on the model path, whatever the shape."""
+    """x @ w^T without a library GEMM, whatever the shape: tensor cores (tcgen05, FP32-accurate split), or the streaming
+    FP32-FMA kernel when the output is a handful of columns (the classifier: tensor-core tiles would be 96 % padding)."""
     _need_cuda(x, "linear")
+    K, NO = x.shape[1], w.shape[0]
+    if NARROW_LINEAR and NO <= 8 and K % 4 == 0 and K <= (256 if NO > 4 else 512):
+        return LinearNarrow.apply(x, w)
     return TcLinear.apply(x, w)
 
 

@@ -256,6 +256,16 @@ int dgcnn_global_feature_bwd_sparse_f32(const float* feat, int ld_feat, const fl
                                         float* t1, void* stream);
 int dgcnn_vecmat_f32(const float* v, const float* w, int ld_w, int E, int K, float scale, float* c, void* stream);
 
+/* ---- narrow-output linear layer on the FP32 FMA pipe (the classifier conv9: 256 -> num_classes, model.py:141,187-193) ----
+ * y[M,NO] = x[M,K] W[NO,K]^T with 1 <= NO <= 8, K %% 4 == 0, K <= 512 (backward: K <= 256, or <= 512 with NO <= 4).  A
+ * streaming pass per direction (x read once, dx written once) instead of tensor-core tiles that are 96 % padding.
+ * Backward: dx (optional) = dy W, dW[NO,K] = dy^T x (zeroed, then accumulated with float reductions).              */
+int dgcnn_linear_narrow_supported(int K, int NO);
+int dgcnn_linear_narrow_fwd_f32(const float* x, int ld_x, const float* w, int ld_w, int M, int K, int NO, float* y, int ld_y,
+                                void* stream);
+int dgcnn_linear_narrow_bwd_f32(const float* x, int ld_x, const float* dy, int ld_dy, const float* w, int ld_w, int M, int K,
+                                int NO, float* dx, int ld_dx, float* dw, void* stream);
+
 /* ---- shared-MLP head: BatchNorm1d (+ per-block bias) + LeakyReLU(0.2) over point-major rows ---------------------------
  * Replaces `bn7(conv7(..))`, `bn8(conv8(..))` + LeakyReLU of reference model.py:131-139,179-184 on y[M,C] (row-major,
  * contiguous).  v = y + bias[row / N] (bias may be NULL: it carries the once-per-block global-feature half of conv7),

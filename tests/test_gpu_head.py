@@ -141,3 +141,28 @@ def test_head_mlp_node_matches_fp64_and_the_unfused_chain(pkg, B, N):
         ef = ((a.double() - r).norm() / (r.norm() + 1e-30)).item()
         ec = ((c.double() - r).norm() / (r.norm() + 1e-30)).item()
         assert ef < max(2e-4, 3 * ec), (n, ef, ec)                           # 2-plane gradient GEMMs: 2^-17 per product
+
+
+@pytest.mark.parametrize("M,K,NO", [(56000, 256, 5), (1003, 256, 8), (777, 128, 1), (4100, 512, 3), (300, 64, 5), (50, 20, 2)])
+def test_linear_narrow_matches_fp64(pkg, M, K, NO):
+    """ops.linear with <= 8 outputs (the classifier conv9, model.py:141): streaming FP32-FMA kernels, forward and backward."""
+    ops = pkg.ops
+    g = torch.Generator().manual_seed(M + K + NO)
+    x0 = torch.randn(M, K, generator=g).to(DEV)
+    w0 = (torch.randn(NO, K, generator=g) * 0.1).to(DEV)
+    up = torch.randn(M, NO, generator=g).to(DEV)
+    x, w = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+    y = ops.linear(x, w)
+    assert y.grad_fn is not None and "LinearNarrow" in type(y.grad_fn).__name__
+    (y * up).sum().backward()
+    xd, wd = x0.double().requires_grad_(True), w0.double().requires_grad_(True)
+    yd = xd @ wd.t()
+    (yd * up.double()).sum().backward()
+    scale = (x0.double().abs() @ w0.double().abs().t())
+    assert ((y.double() - yd).abs() / scale).max().item() < 2e-6
+    assert ((x.grad.double() - xd.grad).abs().max() / xd.grad.abs().max()).item() < 2e-6
+    assert ((w.grad.double() - wd.grad).norm() / wd.grad.norm()).item() < 2e-6
+    # a row-strided input (a column slice) goes through the same kernel
+    xs = torch.randn(M, K + 8, generator=g).to(DEV)
+    ys = ops.linear(xs[:, :K], w0)
+    assert ((ys.double() - xs[:, :K].double() @ w0.double().t()).abs() / (xs[:, :K].double().abs() @ w0.double().abs().t())).max().item() < 2e-6
