@@ -67,6 +67,9 @@ SIGNATURES = {
     "dgcnn_linear_narrow_supported": (c_int, [c_int, c_int]),
     "dgcnn_linear_narrow_fwd_f32": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
     "dgcnn_linear_narrow_bwd_f32": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _P]),
+    "dgcnn_linear_thin_supported": (c_int, [c_int, c_int]),
+    "dgcnn_linear_thin_fwd_f32": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
+    "dgcnn_linear_thin_bwd_f32": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _P]),
     "dgcnn_rows_bn_lrelu_fwd_planes": (c_int, [_P, c_int, c_int, _P, c_int, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, c_size_t,
                                                c_int, _P, c_size_t, _P]),
     "dgcnn_rows_bn_lrelu_bwd_planes": (c_int, [_P, _P, c_int, c_int, _P, c_int, _P, _P, _P, _P, c_size_t, c_int, _P, _P, _P, _P, c_size_t,

@@ -21,6 +21,7 @@ from . import _lib
 COUT = 64
 TC_KNN_MIN_N = 256       # below this every key is a candidate anyway and the exact tile kernel is as fast
 EDGECONV_IMPL = 0        # dgcnn_edgeconv_args.impl: 0 = default (pipelined tcgen05), 1 = FP32 FMA, 2 = serial tcgen05 (A/B checks)
+THIN_LINEAR = True       # inputs <= 8 channels (the input block's point-level GEMM): streaming FP32-FMA kernels
 NARROW_LINEAR = True     # outputs <= 8 (classifier): streaming FP32-FMA kernel instead of padded tensor-core tiles
 ATOMIC_WGRAD = True      # row-contraction (weight-gradient) GEMMs add their row splits into D atomically; False = partial tiles + fixed-order reduce
 FUSED_HEAD = True        # training: conv7 -> bn7 -> conv8 -> bn8 as one autograd node, activations between BN and GEMM only as planes
@@ -616,6 +617,20 @@ def _lin_weight(wa: torch.Tensor, Cn: int) -> torch.Tensor:
     return torch.cat((wa[:, :Cn], wa[:, Cn:] - wa[:, :Cn]), dim=0)
 
 
+def _uv_gemm(rows: torch.Tensor, ld: int, Cn: int, wlin: torch.Tensor, keep_planes: bool):
+    """[U | V] = X [Wa1 ; Wa2 - Wa1]^T ([M,128]) and, for the tensor-core form, the planes of X (reused by the weight gradient).
+    The 4-channel input block goes through the streaming thin-input kernel: K = 4 would be padded to a 64-wide atom."""
+    M = rows.shape[0]
+    if THIN_LINEAR and Cn <= 8 and _lib.load().dgcnn_linear_thin_supported(Cn, 2 * COUT):
+        uv = torch.empty(M, 2 * COUT, dtype=torch.float32, device=rows.device)
+        _call("dgcnn_linear_thin_fwd_f32", rows.device, _ptr(rows), ld, _ptr(wlin), wlin.stride(0), M, Cn, 2 * COUT, _ptr(uv), 2 * COUT)
+        return uv, None
+    if not keep_planes:
+        return tc_gemm(rows[:, :Cn], wlin), None
+    xp = Planes(rows[:, :Cn], 3)
+    return gemm_planes(xp, Planes(wlin, 3), 3), xp
+
+
 def eval_affine(gamma: torch.Tensor, beta: torch.Tensor, bn: BNState) -> torch.Tensor:
     """float[192] = running_mean | gamma/sqrt(running_var+eps) | beta."""
     return torch.cat((bn.running_mean, gamma * torch.rsqrt(bn.running_var + bn.eps), beta)).float().contiguous()
@@ -632,7 +647,7 @@ def edgeconv_eval(rows: torch.Tensor, idx: torch.Tensor, B: int, Cn: int, N: int
     if _use_lin(Cn, w_b):
         # single conv, 64 channels: y = U_j + V_i from ONE point-level GEMM, then a gather pass for the extrema over k
         M, dev = B * N, rows.device
-        uv = tc_gemm(rows[:, :Cn], _lin_weight(wa, Cn))
+        uv, _ = _uv_gemm(rows, ld, Cn, _lin_weight(wa, Cn), False)
         ymax, ymin = torch.empty(M, COUT, dtype=torch.float32, device=dev), torch.empty(M, COUT, dtype=torch.float32, device=dev)
         amax, amin = torch.empty(M, COUT, dtype=torch.uint8, device=dev), torch.empty(M, COUT, dtype=torch.uint8, device=dev)
         a = _args(rows, ld, idx, B, Cn, N, k, wa, None, None, COUT)
@@ -650,7 +665,7 @@ def edgeconv_eval(rows: torch.Tensor, idx: torch.Tensor, B: int, Cn: int, N: int
         # as per-edge MMAs) even though y_a takes a round trip through HBM.
         M, dev = B * N, rows.device
         partials, _ = _partials(dev)
-        uv = tc_gemm(rows[:, :Cn], _lin_weight(wa, Cn))
+        uv, _ = _uv_gemm(rows, ld, Cn, _lin_weight(wa, Cn), False)
         y_a = torch.empty(M * k, COUT, dtype=torch.float32, device=dev)
         ymax, ymin = torch.empty(M, COUT, dtype=torch.float32, device=dev), torch.empty(M, COUT, dtype=torch.float32, device=dev)
         amax, amin = torch.empty(M, COUT, dtype=torch.uint8, device=dev), torch.empty(M, COUT, dtype=torch.uint8, device=dev)
@@ -705,8 +720,7 @@ class EdgeConvTrain(torch.autograd.Function):
             # first conv of a two-conv block: y_a = U_j + V_i written per edge (BN_a needs batch statistics before conv_b
             # can start), no per-edge GEMM.  Also for the input block: y_a carries the centre term Wa2 x_i (~|W||x|) either
             # way, so forming x_j - x_i first buys no accuracy at the level of y_a (both are within a few 1e-8 |W||x|).
-            xp = Planes(rows[:, :Cn], 3)                 # X planes: this GEMM now, the weight gradient in the backward
-            uv2 = gemm_planes(xp, Planes(_lin_weight(wa, Cn), 3), 3)
+            uv2, xp = _uv_gemm(rows, ld, Cn, _lin_weight(wa, Cn), True)     # X planes: this GEMM now, the weight gradient in the backward
             if FUSED_BWD and GRAD_NSPLIT == 2 and k >= 8 and N >= 16:
                 # + the out-edge sums of y_a: with them (and the in-edge sums the backward accumulates) dz_a[E,64] is never formed
                 fused = torch.empty(M, COUT, **f32)
@@ -717,8 +731,7 @@ class EdgeConvTrain(torch.autograd.Function):
                       _ptr(partials))
         elif lin:
             # y = U_j + V_i: one point-level GEMM + a gather pass (extrema over k, batch sums); nothing per-edge in HBM
-            xp = Planes(rows[:, :Cn], 3)
-            uv = gemm_planes(xp, Planes(_lin_weight(wa, Cn), 3), 3)
+            uv, xp = _uv_gemm(rows, ld, Cn, _lin_weight(wa, Cn), True)
             _call("dgcnn_edgeconv_lin_extrema", dev, C.byref(a), _ptr(uv), uv.stride(0), _ptr(uv[:, COUT:]), uv.stride(0), _ptr(partials),
                   _ptr(ymax), _ptr(ymin), _ptr(amax), _ptr(amin))
         else:
@@ -743,6 +756,7 @@ class EdgeConvTrain(torch.autograd.Function):
         ctx.lin = lin
         ctx.fused = fused
         ctx.xp = xp
+        ctx.thin = (uv is not None or uv2 is not None) and xp is None
         ctx.uv2 = uv2                                   # [U | V] of a two-conv block: the backward gathers it instead of re-reading y_a
         ctx.save_for_backward(rows, idx, wa, wb if two else wa, gamma_a.detach(), gamma_b.detach() if two else gamma_a.detach(),
                               uv if lin else y_a, stat_a, stat_b if two else stat_a, ysel, arg)
@@ -824,15 +838,26 @@ class EdgeConvTrain(torch.autograd.Function):
         X = rows[:, :Cn]
         wa1, wa2 = wa[:, :Cn], wa[:, Cn:]
         dx = None
-        rsp = Planes(rs, GRAD_NSPLIT)                                   # split once: K-major for dX, row-contraction for dWa
-        if ctx.needs_input_grad[0]:
-            wcat = torch.cat((wa1, wa2 - wa1), dim=0)                   # [128, C]
-            dx = gemm_planes(rsp, Planes(wcat.t(), GRAD_NSPLIT), GRAD_NSPLIT)
-            if dx.shape != ctx.x_shape:                                 # rows padded to a multiple of 4 channels
-                dx = torch.nn.functional.pad(dx, (0, ctx.x_shape[1] - dx.shape[1]))
-        xp = ctx.xp if ctx.xp is not None else Planes(X, GRAD_NSPLIT)
+        if getattr(ctx, "thin", False):
+            # thin input (K <= 8): one streaming pass gives G = [r|s]^T X and, if asked for, dX = [r|s] [Wa1 ; Wa2-Wa1]
+            C4 = (Cn + 3) // 4 * 4
+            wcat = torch.cat((wa1, wa2 - wa1), dim=0).contiguous()      # [128, C]
+            G = torch.empty(2 * COUT, Cn, **f32)
+            dxp = torch.empty(M, C4, **f32) if ctx.needs_input_grad[0] else None
+            _call("dgcnn_linear_thin_bwd_f32", dev, _ptr(rows), ctx.ld, _ptr(rs), 2 * COUT, _ptr(wcat), Cn, M, Cn, 2 * COUT, _ptr(dxp), C4,
+                  _ptr(G))
+            if dxp is not None:
+                dx = dxp if dxp.shape == ctx.x_shape else torch.nn.functional.pad(dxp[:, :Cn], (0, ctx.x_shape[1] - Cn))
+        else:
+            rsp = Planes(rs, GRAD_NSPLIT)                               # split once: K-major for dX, row-contraction for dWa
+            if ctx.needs_input_grad[0]:
+                wcat = torch.cat((wa1, wa2 - wa1), dim=0)               # [128, C]
+                dx = gemm_planes(rsp, Planes(wcat.t(), GRAD_NSPLIT), GRAD_NSPLIT)
+                if dx.shape != ctx.x_shape:                             # rows padded to a multiple of 4 channels
+                    dx = torch.nn.functional.pad(dx, (0, ctx.x_shape[1] - dx.shape[1]))
+            xp = ctx.xp if ctx.xp is not None else Planes(X, GRAD_NSPLIT)
+            G = gemm_planes(rsp, xp, GRAD_NSPLIT, transposed=True)      # [128, C] = [r|s]^T X
         ctx.xp = None
-        G = gemm_planes(rsp, xp, GRAD_NSPLIT, transposed=True)                            # [128, C] = [r|s]^T X
         dwa = torch.cat((G[:COUT] - G[COUT:], G[COUT:]), dim=1)
         # returns: x, idx, meta, w_a, gamma_a, beta_a, w_b, gamma_b, beta_b, bn_a, bn_b
         if two:

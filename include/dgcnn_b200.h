@@ -265,6 +265,14 @@ int dgcnn_linear_narrow_fwd_f32(const float* x, int ld_x, const float* w, int ld
                                 void* stream);
 int dgcnn_linear_narrow_bwd_f32(const float* x, int ld_x, const float* dy, int ld_dy, const float* w, int ld_w, int M, int K,
                                 int NO, float* dx, int ld_dx, float* dw, void* stream);
+/* ---- thin-input linear layer (K <= 8: the point-level GEMM of the input block, X[M,4] [Wa1 ; Wa2 - Wa1]^T -> [U|V]) -------
+ * y[M,NO] = x[M,K] W[NO,K]^T, NO %% 4 == 0; x rows: ld_x >= round4(K) floats, columns beyond K zero.  Backward (NO = 128):
+ * dW[128,K] = g^T x (zeroed, then accumulated with float reductions) and, optionally, dx[M, round4(K)] = g W.          */
+int dgcnn_linear_thin_supported(int K, int NO);
+int dgcnn_linear_thin_fwd_f32(const float* x, int ld_x, const float* w, int ld_w, int M, int K, int NO, float* y, int ld_y,
+                              void* stream);
+int dgcnn_linear_thin_bwd_f32(const float* x, int ld_x, const float* g, int ld_g, const float* w, int ld_w, int M, int K,
+                              int NO, float* dx, int ld_dx, float* dw, void* stream);
 
 /* ---- shared-MLP head: BatchNorm1d (+ per-block bias) + LeakyReLU(0.2) over point-major rows ---------------------------
  * Replaces `bn7(conv7(..))`, `bn8(conv8(..))` + LeakyReLU of reference model.py:131-139,179-184 on y[M,C] (row-major,
