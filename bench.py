@@ -429,7 +429,7 @@ def run_ours(args, rank: int, local: int, world: int):
 
     # ---- CUDA graph of the step (one launch per step instead of ~220 kernel launches); with a gradient exchange (N > 1)
     # the graph covers forward + criterion + backward and the all-reduce + Adam stay eager --------------------------------
-    graphed = None
+    graphed, graph_scope = None, "fwd+criterion+bwd+adam"
     if not args.no_graph:
         graphs = __import__(entry.PKG_NAME + ".graphs", fromlist=["x"])
         try:
@@ -437,18 +437,31 @@ def run_ours(args, rank: int, local: int, world: int):
                 graphed = graphs.GraphedTrainStep(lambda x, y, m: eager_step(x, y, m), resident[0])
                 step = lambda x, y, m: graphed.run(x, y, m)
             else:
-                def fwd_bwd(x, y, m):
-                    bucket.zero()
-                    loss = ops.seg_loss(model(x), y, m)
-                    loss.backward()
-                    return loss
-                graphed = graphs.GraphedTrainStep(fwd_bwd, resident[0])
+                # NCCL collectives are capturable: the whole step (forward .. backward, the bucket all-reduce, Adam) is ONE graph
+                # on every rank; if this build of torch / NCCL refuses, the graph covers forward .. backward only
+                try:
+                    if args.no_graph_collective:
+                        raise RuntimeError("--no-graph-collective")
+                    graphed = graphs.GraphedTrainStep(lambda x, y, m: eager_step(x, y, m), resident[0])
+                    step = lambda x, y, m: graphed.run(x, y, m)
+                    graph_scope = "fwd+criterion+bwd+allreduce+adam"
+                except Exception as e2:
+                    print(f"note: all-reduce not captured ({e2!r}); graph = forward..backward", file=sys.stderr)
+                    torch.cuda.synchronize()
 
-                def step(x, y, m):
-                    loss = graphed.run(x, y, m)
-                    bucket.all_reduce_mean()
-                    opt.step()
-                    return loss
+                    def fwd_bwd(x, y, m):
+                        bucket.zero()
+                        loss = ops.seg_loss(model(x), y, m)
+                        loss.backward()
+                        return loss
+                    graphed = graphs.GraphedTrainStep(fwd_bwd, resident[0])
+                    graph_scope = "fwd+criterion+bwd"
+
+                    def step(x, y, m):
+                        loss = graphed.run(x, y, m)
+                        bucket.all_reduce_mean()
+                        opt.step()
+                        return loss
         except Exception as e:               # capture problems must not cost the bench line: fall back to eager launches
             print(f"warning: CUDA graph capture failed ({e!r}); eager launches", file=sys.stderr)
             torch.cuda.synchronize()
@@ -533,7 +546,7 @@ def run_ours(args, rank: int, local: int, world: int):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
-        "cuda_graph": graphed is not None,
+        "cuda_graph": graphed is not None, "cuda_graph_scope": graph_scope if graphed is not None else None,
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,
@@ -640,6 +653,7 @@ def main():
                     help="train = BASELINE configs[1]/[2] (the headline metric); infer = configs[3], sharded tile inference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-graph-collective", action="store_true", help="N > 1: keep the gradient all-reduce and Adam outside the graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-layer timings, the nsplit=3 step and the eager-GPU oracle run")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
