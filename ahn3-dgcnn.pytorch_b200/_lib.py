@@ -53,6 +53,11 @@ SIGNATURES = {
     "dgcnn_edgeconv_bwd_b_fused": (c_int, [_ARGS, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P]),
     "dgcnn_edgeconv_bwd_a_point_stats": (c_int, [c_int, _P, c_int, _P, c_int, _P, _P, c_int, _P, _P]),
     "dgcnn_edgeconv_bwd_a_point_apply": (c_int, [c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P]),
+    "dgcnn_edgeconv_bwd_a_lin_edges": (c_int, [_ARGS, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, c_int, _P, _P]),
+    "dgcnn_graph_transpose_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "dgcnn_graph_transpose": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "dgcnn_gather_in_edges_f32": (c_int, [_P, _P, _P, c_int, _P, c_int, _P]),
+    "dgcnn_global_feature_scatter_det_f32": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, _P, c_int, _P]),
     "dgcnn_edgeconv_bwd_a_lin": (c_int, [_ARGS, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "dgcnn_tc_gemm_colstats_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "dgcnn_tc_gemm_bn_lrelu_segmax_f32": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P,

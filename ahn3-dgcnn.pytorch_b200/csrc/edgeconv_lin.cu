@@ -98,7 +98,8 @@ template <bool DENSE_DZ>
 __global__ void __launch_bounds__(kThreads)
 ec_lin_bwd_a_kernel(const float* __restrict__ U, int ld_u, const float* __restrict__ V, int ld_v, const int32_t* __restrict__ idx,
                     int M, int N, int k, const float* __restrict__ dz_a, const float* __restrict__ g, const uint8_t* __restrict__ arg,
-                    const float* __restrict__ coef_a, float* __restrict__ s_out, float* __restrict__ r_out, int ld_rs) {
+                    const float* __restrict__ coef_a, float* __restrict__ s_out, float* __restrict__ r_out, int ld_rs,
+                    float* __restrict__ dy_edges) {
   const int c4 = threadIdx.x & 15, pl = threadIdx.x >> 4;
   const int c = 4 * c4;
   const float4 cA = *reinterpret_cast<const float4*>(coef_a + c);
@@ -132,7 +133,10 @@ ec_lin_bwd_a_kernel(const float* __restrict__ U, int ld_u, const float* __restri
       dy.z = cA.z * dz.z - cB.z - cC.z * __fadd_rn(u.z, v.z);
       dy.w = cA.w * dz.w - cB.w - cC.w * __fadd_rn(u.w, v.w);
       s.x += dy.x; s.y += dy.y; s.z += dy.z; s.w += dy.w;
-      atomicAdd(reinterpret_cast<float4*>(r_out + j * ld_rs + c), dy);
+      if (dy_edges)      // reproducible form: the per-edge gradient goes to HBM and is gathered in a fixed order (graph_transpose.cu)
+        *reinterpret_cast<float4*>(dy_edges + (static_cast<size_t>(gp) * k + slot) * kCout + c) = dy;
+      else
+        atomicAdd(reinterpret_cast<float4*>(r_out + j * ld_rs + c), dy);
     }
     *reinterpret_cast<float4*>(s_out + static_cast<size_t>(gp) * ld_rs + c) = s;
   }
@@ -189,23 +193,39 @@ extern "C" int dgcnn_edgeconv_lin_conv_a_train(const dgcnn_edgeconv_args* a, con
   return lin_conv_a(a, U, ld_u, V, ld_v, y_a, partials, ysum, nullptr, nullptr, stream, "edgeconv_lin_conv_a_train");
 }
 
-extern "C" int dgcnn_edgeconv_bwd_a_lin(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
-                                        const float* dz_a, const float* g, const uint8_t* arg, const float* coef_a, float* s,
-                                        float* r, int ld_rs, void* stream) {
-  int rc = lin_check(a, U, ld_u, V, ld_v, "edgeconv_bwd_a_lin");
+static int bwd_a_lin(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v, const float* dz_a, const float* g,
+                     const uint8_t* arg, const float* coef_a, float* s, float* r, int ld_rs, float* dy_edges, void* stream, const char* who) {
+  int rc = lin_check(a, U, ld_u, V, ld_v, who);
   if (rc) return rc;
-  DG_REQUIRE(coef_a && s && r && (dz_a || (g && arg)), DGCNN_E_INVALID, "edgeconv_bwd_a_lin: null pointer");
-  DG_REQUIRE(!dz_a || (reinterpret_cast<uintptr_t>(dz_a) & 15) == 0, DGCNN_E_INVALID, "edgeconv_bwd_a_lin: dz_a must be 16-byte aligned");
-  DG_REQUIRE(ld_rs >= kCout && ld_rs % 4 == 0 && ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(r)) & 15) == 0,
-             DGCNN_E_INVALID, "edgeconv_bwd_a_lin: s/r need 16-byte alignment and ld_rs %% 4 == 0, ld_rs >= 64");
+  DG_REQUIRE(coef_a && s && (r || dy_edges) && (dz_a || (g && arg)), DGCNN_E_INVALID, "%s: null pointer", who);
+  DG_REQUIRE(!dz_a || (reinterpret_cast<uintptr_t>(dz_a) & 15) == 0, DGCNN_E_INVALID, "%s: dz_a must be 16-byte aligned", who);
+  DG_REQUIRE(ld_rs >= kCout && ld_rs % 4 == 0 && ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(r) |
+                                                   reinterpret_cast<uintptr_t>(dy_edges)) & 15) == 0,
+             DGCNN_E_INVALID, "%s: s / r / dy_edges need 16-byte alignment and ld_rs %% 4 == 0, ld_rs >= 64", who);
   const int M = a->B * a->N;
   const int blocks = std::max(1, std::min((M + 15) / 16, 8 * std::max(1, num_sms())));
   if (dz_a)
     ec_lin_bwd_a_kernel<true><<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(U, ld_u, V, ld_v, a->idx, M, a->N, a->k, dz_a,
-                                                                                        g, arg, coef_a, s, r, ld_rs);
+                                                                                        g, arg, coef_a, s, r, ld_rs, dy_edges);
   else
     ec_lin_bwd_a_kernel<false><<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(U, ld_u, V, ld_v, a->idx, M, a->N, a->k, dz_a,
-                                                                                         g, arg, coef_a, s, r, ld_rs);
+                                                                                         g, arg, coef_a, s, r, ld_rs, dy_edges);
   DG_CUDA(cudaGetLastError());
   return DGCNN_OK;
+}
+
+extern "C" int dgcnn_edgeconv_bwd_a_lin(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
+                                        const float* dz_a, const float* g, const uint8_t* arg, const float* coef_a, float* s,
+                                        float* r, int ld_rs, void* stream) {
+  DG_REQUIRE(r, DGCNN_E_INVALID, "edgeconv_bwd_a_lin: null r");
+  return bwd_a_lin(a, U, ld_u, V, ld_v, dz_a, g, arg, coef_a, s, r, ld_rs, nullptr, stream, "edgeconv_bwd_a_lin");
+}
+
+/* the same pass with the per-edge gradient dy_a[E,64] written out instead of scattered (s as before): the reproducible form
+ * gathers r from it in a fixed order (dgcnn_graph_transpose + dgcnn_gather_in_edges_f32) */
+extern "C" int dgcnn_edgeconv_bwd_a_lin_edges(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
+                                              const float* dz_a, const float* g, const uint8_t* arg, const float* coef_a, float* s,
+                                              int ld_rs, float* dy_edges, void* stream) {
+  DG_REQUIRE(dy_edges, DGCNN_E_INVALID, "edgeconv_bwd_a_lin_edges: null dy_edges");
+  return bwd_a_lin(a, U, ld_u, V, ld_v, dz_a, g, arg, coef_a, s, nullptr, ld_rs, dy_edges, stream, "edgeconv_bwd_a_lin_edges");
 }

@@ -31,7 +31,8 @@ global_feature_bwd_sparse_kernel(const float* __restrict__ feat, int ldf, const 
       acc.x = __fmaf_rn(g, f.x, acc.x); acc.y = __fmaf_rn(g, f.y, acc.y);
       acc.z = __fmaf_rn(g, f.z, acc.z); acc.w = __fmaf_rn(g, f.w, acc.w);
       const float s = ae * g;
-      atomicAdd(reinterpret_cast<float4*>(dfeat + static_cast<size_t>(row) * lddf + k), make_float4(s * wv.x, s * wv.y, s * wv.z, s * wv.w));
+      if (dfeat)      // (null: the reproducible form scatters separately, dgcnn_global_feature_scatter_det_f32)
+        atomicAdd(reinterpret_cast<float4*>(dfeat + static_cast<size_t>(row) * lddf + k), make_float4(s * wv.x, s * wv.y, s * wv.z, s * wv.w));
     }
     *reinterpret_cast<float4*>(t1 + static_cast<size_t>(e) * K + k) = acc;
   }
@@ -65,7 +66,7 @@ using namespace dg;
 extern "C" int dgcnn_global_feature_bwd_sparse_f32(const float* feat, int ld_feat, const float* w, int ld_w, const int32_t* nstar,
                                                    const float* gdz, const float* a, int B, int E, int K, float* dfeat,
                                                    int ld_dfeat, float* t1, void* stream) {
-  DG_REQUIRE(feat && w && nstar && gdz && a && dfeat && t1, DGCNN_E_INVALID, "global_feature_bwd_sparse: null pointer");
+  DG_REQUIRE(feat && w && nstar && gdz && a && t1, DGCNN_E_INVALID, "global_feature_bwd_sparse: null pointer");
   DG_REQUIRE(B > 0 && E > 0 && K > 0 && K % 4 == 0 && ld_feat % 4 == 0 && ld_w % 4 == 0 && ld_dfeat % 4 == 0, DGCNN_E_INVALID,
              "global_feature_bwd_sparse: K and the row strides must be multiples of 4 (K=%d)", K);
   DG_REQUIRE(((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(dfeat) |

@@ -149,7 +149,7 @@ class DGCNN(nn.Module):
         if forced is not None and layer - 1 < len(forced) and forced[layer - 1] is not None:
             idx = forced[layer - 1].to(device=rows.device, dtype=torch.int32).reshape(B * N, self.k).contiguous()
         if idx is None:
-            idx = ops.knn_rows(rows.detach(), B, Cn, N, self.k, ordered=False)     # the blocks only need the SET
+            idx = ops.knn_rows(rows.detach(), B, Cn, N, self.k, ordered=ops.DETERMINISTIC)     # the blocks only need the SET
         self.last_idx.append(idx)
         return idx
 

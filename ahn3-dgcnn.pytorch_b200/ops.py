@@ -21,6 +21,7 @@ from . import _lib
 COUT = 64
 TC_KNN_MIN_N = 256       # below this every key is a candidate anyway and the exact tile kernel is as fast
 EDGECONV_IMPL = 0        # dgcnn_edgeconv_args.impl: 0 = default (pipelined tcgen05), 1 = FP32 FMA, 2 = serial tcgen05 (A/B checks)
+DETERMINISTIC = os.environ.get("DGCNN_DETERMINISTIC", "0") == "1"   # bit-reproducible gradients: no float atomics anywhere (slower, see set_deterministic)
 THIN_LINEAR = True       # inputs <= 8 channels (the input block's point-level GEMM): streaming FP32-FMA kernels
 NARROW_LINEAR = True     # outputs <= 8 (classifier): streaming FP32-FMA kernel instead of padded tensor-core tiles
 ATOMIC_WGRAD = True      # row-contraction (weight-gradient) GEMMs add their row splits into D atomically; False = partial tiles + fixed-order reduce
@@ -390,8 +391,15 @@ class GlobalFeature(torch.autograd.Function):
         # sparse parts in one pass: scatter of a dz W into dfeat, and t1 = dz^T feat
         t1 = torch.empty(E, K, dtype=torch.float32, device=dev)
         gdz_c = gdz.contiguous()
-        _call("dgcnn_global_feature_bwd_sparse_f32", dev, _ptr(feat), feat.stride(0), _ptr(w), w.stride(0), _ptr(nstar), _ptr(gdz_c),
-              _ptr(a.contiguous()), B, E, K, _ptr(dfeat), dfeat.stride(0), _ptr(t1))
+        a_c = a.contiguous()
+        if DETERMINISTIC:        # t1 only, then the scatter with one owner warp per target row
+            _call("dgcnn_global_feature_bwd_sparse_f32", dev, _ptr(feat), feat.stride(0), _ptr(w), w.stride(0), _ptr(nstar), _ptr(gdz_c),
+                  _ptr(a_c), B, E, K, _ptr(None), dfeat.stride(0), _ptr(t1))
+            _call("dgcnn_global_feature_scatter_det_f32", dev, _ptr(w), w.stride(0), _ptr(nstar), _ptr(gdz_c), _ptr(a_c), B, E, K,
+                  _ptr(dfeat), dfeat.stride(0))
+        else:
+            _call("dgcnn_global_feature_bwd_sparse_f32", dev, _ptr(feat), feat.stride(0), _ptr(w), w.stride(0), _ptr(nstar), _ptr(gdz_c),
+                  _ptr(a_c), B, E, K, _ptr(dfeat), dfeat.stride(0), _ptr(t1))
         # dW = a dz^T feat - b' colsum(feat)^T - diag(kappa) W (feat^T feat)
         f2 = gemm_planes(featp, featp, GRAD_NSPLIT, transposed=True)            # [K,K] = feat^T feat (row contraction, split over the points)
         wf2 = tc_gemm(w, f2, nsplit=GRAD_NSPLIT)                                # f2 is symmetric: W f2 = W f2^T
@@ -617,6 +625,29 @@ def _lin_weight(wa: torch.Tensor, Cn: int) -> torch.Tensor:
     return torch.cat((wa[:, :Cn], wa[:, Cn:] - wa[:, :Cn]), dim=0)
 
 
+def set_deterministic(on: bool = True) -> None:
+    """Bit-reproducible training step: every scatter becomes a fixed-order gather (csrc/graph_transpose.cu: the kNN table is
+    transposed once per graph), the weight-gradient GEMMs reduce their row splits in a fixed order, and the layers whose
+    streaming kernels accumulate with atomics go back to the tensor-core path; the model asks for its neighbour tables in the
+    reference's best-first order (the order inside a neighbour SET depends on the low bits of the filter's channel means,
+    which are summed with float atomics).  About 1.5x the step time; the forward pass is
+    unchanged (it has no atomics whose order matters: the segmented max uses integer atomicMax)."""
+    global DETERMINISTIC, FUSED_BWD, ATOMIC_WGRAD, NARROW_LINEAR, THIN_LINEAR
+    DETERMINISTIC = on
+    FUSED_BWD = ATOMIC_WGRAD = NARROW_LINEAR = THIN_LINEAR = not on
+
+
+def _scatter_r_deterministic(a, idx, B, N, k, dy_edges, r, dev) -> None:
+    """r[j] = sum of dy_edges over the in-edges of j in ascending edge id (CSR transpose of the kNN table)."""
+    lib = _lib.load()
+    M = B * N
+    in_start = torch.empty(M + 1, dtype=torch.int32, device=dev)
+    in_edge = torch.empty(M * k, dtype=torch.int32, device=dev)
+    ws = torch.empty(lib.dgcnn_graph_transpose_workspace_bytes(B, N), dtype=torch.uint8, device=dev)
+    _call("dgcnn_graph_transpose", dev, _ptr(idx), B, N, k, _ptr(in_start), _ptr(in_edge), _ptr(ws), ws.numel())
+    _call("dgcnn_gather_in_edges_f32", dev, _ptr(dy_edges), _ptr(in_start), _ptr(in_edge), M, _ptr(r), r.stride(0))
+
+
 def _uv_gemm(rows: torch.Tensor, ld: int, Cn: int, wlin: torch.Tensor, keep_planes: bool):
     """[U | V] = X [Wa1 ; Wa2 - Wa1]^T ([M,128]) and, for the tensor-core form, the planes of X (reused by the weight gradient).
     The 4-channel input block goes through the streaming thin-input kernel: K = 4 would be padded to a 64-wide atom."""
@@ -826,8 +857,14 @@ class EdgeConvTrain(torch.autograd.Function):
                 dz_a, coef_a, dga = None, coef_l, dgl
             if ctx.lin or ctx.uv2 is not None:
                 uv = y_a if ctx.lin else ctx.uv2            # [U | V] (saved in y_a's place for the single-conv block)
-                _call("dgcnn_edgeconv_bwd_a_lin", dev, C.byref(a), _ptr(uv), uv.stride(0), _ptr(uv[:, COUT:]), uv.stride(0), _ptr(dz_a),
-                      _ptr(g), _ptr(arg), _ptr(coef_a), _ptr(s), _ptr(r), 2 * COUT)
+                if DETERMINISTIC:
+                    dy_edges = torch.empty(E, COUT, **f32)
+                    _call("dgcnn_edgeconv_bwd_a_lin_edges", dev, C.byref(a), _ptr(uv), uv.stride(0), _ptr(uv[:, COUT:]), uv.stride(0),
+                          _ptr(dz_a), _ptr(g), _ptr(arg), _ptr(coef_a), _ptr(s), 2 * COUT, _ptr(dy_edges))
+                    _scatter_r_deterministic(a, idx, B, N, k, dy_edges, r, dev)
+                else:
+                    _call("dgcnn_edgeconv_bwd_a_lin", dev, C.byref(a), _ptr(uv), uv.stride(0), _ptr(uv[:, COUT:]), uv.stride(0), _ptr(dz_a),
+                          _ptr(g), _ptr(arg), _ptr(coef_a), _ptr(s), _ptr(r), 2 * COUT)
                 ctx.uv2 = None
             else:
                 _call("dgcnn_edgeconv_bwd_a", dev, C.byref(a), _ptr(y_a), _ptr(dz_a), _ptr(g), _ptr(arg), _ptr(coef_a),
@@ -930,3 +967,7 @@ def seg_predict(logits: torch.Tensor, min_class_confidence: float = 0.8, unclass
     _call("dgcnn_seg_predict_f32", z.device, _ptr(z), z.stride(0), z.stride(1), z.stride(2), B, Cn, N,
           float(min_class_confidence), int(unclassified), _ptr(pred), _ptr(conf))
     return (pred, conf) if return_conf else pred
+
+
+if DETERMINISTIC:
+    set_deterministic(True)

@@ -177,6 +177,24 @@ int dgcnn_edgeconv_bwd_a_lin(const dgcnn_edgeconv_args* a, const float* U, int l
                              const float* dz_a, const float* g, const uint8_t* arg, const float* coef_a, float* s, float* r,
                              int ld_rs, void* stream);
 
+/* ---- reproducible gradients (opt-in; csrc/graph_transpose.cu) ------------------------------------------------------------
+ * The default backward adds per-edge gradients into their neighbour's row with float reductions: the summation order, and
+ * with it the last bits of the gradients, varies from run to run.  The reproducible form writes the per-edge gradient
+ * (dgcnn_edgeconv_bwd_a_lin_edges: dy_edges[B*N*k,64], s as usual), transposes the kNN table once per graph
+ * (dgcnn_graph_transpose: in_start[B*N+1], in_edge[B*N*k] = the in-edges e = i*k+slot of every point, ascending) and
+ * gathers r in that order (dgcnn_gather_in_edges_f32).  dgcnn_global_feature_scatter_det_f32 is the owner-per-row form of
+ * the scatter inside dgcnn_global_feature_bwd_sparse_f32 (call that one with dfeat = NULL for t1 only).               */
+int dgcnn_edgeconv_bwd_a_lin_edges(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
+                                   const float* dz_a, const float* g, const uint8_t* arg, const float* coef_a, float* s,
+                                   int ld_rs, float* dy_edges, void* stream);
+size_t dgcnn_graph_transpose_workspace_bytes(int B, int N);
+int dgcnn_graph_transpose(const int32_t* idx, int B, int N, int k, int32_t* in_start, int32_t* in_edge, void* workspace,
+                          size_t workspace_bytes, void* stream);
+int dgcnn_gather_in_edges_f32(const float* dy_edges, const int32_t* in_start, const int32_t* in_edge, int M, float* r, int ld_r,
+                              void* stream);
+int dgcnn_global_feature_scatter_det_f32(const float* w, int ld_w, const int32_t* nstar, const float* gdz, const float* a, int B,
+                                         int E, int K, float* dfeat, int ld_dfeat, void* stream);
+
 /* ---- backward of a two-conv block with NO per-edge gradient tensor in HBM (csrc/edgeconv_bwd_pipe.cu) -------------------
  * BN_a's backward is affine in (dz_a, y_a) and conv_a's backward only needs in-edge / out-edge sums, so the sums are taken
  * of the raw quantities and the affine map is applied per POINT afterwards:
