@@ -34,15 +34,17 @@ sweep = []
 for C in (4, 64, 128):
     for N in (1000, 2000, 4000, 7000, 8000, 16000, 32000, 64000):
         for k in (20, 30, 40):
-            B = 1
-            x = (torch.randn(B, C, N, generator=torch.Generator().manual_seed(N + C)) ).cuda()
-            rows = ops.pack_rows(x)
-            try:
-                ms = timeit(lambda: ops.knn_rows(rows, B, C, N, k), n=3, warm=1)
-            except Exception as e:
-                ms = None
-            sweep.append({"C": C, "N": N, "k": k, "ms": None if ms is None else round(ms, 3), "tflops_alg": None if ms is None else round(2.0 * N * N * C / ms / 1e9, 2)})
-    print("knn sweep C", C, [(s["N"], s["k"], s["ms"]) for s in sweep if s["C"] == C], flush=True)
+            # B = 1 (the survey's single-cloud sweep) and a batch that fills the GPU (8 clouds up to N = 8000)
+            for B in ((1, 8) if N <= 8000 else (1,)):
+                x = (torch.randn(B, C, N, generator=torch.Generator().manual_seed(N + C)) ).cuda()
+                rows = ops.pack_rows(x)
+                try:
+                    ms = timeit(lambda: ops.knn_rows(rows, B, C, N, k), n=5, warm=3)
+                except Exception as e:
+                    ms = None
+                sweep.append({"C": C, "N": N, "k": k, "B": B, "ms": None if ms is None else round(ms, 3),
+                              "tflops_alg": None if ms is None else round(2.0 * B * N * N * C / ms / 1e9, 2)})
+    print("knn sweep C", C, [(s["B"], s["N"], s["k"], s["ms"]) for s in sweep if s["C"] == C], flush=True)
 out["knn_sweep"] = sweep
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "infer_r1.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "infer_r2.json"), "w"), indent=1)
