@@ -64,6 +64,10 @@ SIGNATURES = {
                                                   c_float, c_float, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "dgcnn_global_feature_bwd_sparse_f32": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, c_int, c_int, c_int, _P, c_int, _P, _P]),
     "dgcnn_vecmat_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_float, _P, _P]),
+    "dgcnn_global_feature_bwd_coef_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P]),
+    "dgcnn_global_feature_bwd_dw_f32": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P]),
+    "dgcnn_edgeconv_lin_weight_f32": (c_int, [_P, c_int, _P, _P]),
+    "dgcnn_edgeconv_lin_weight_bwd_f32": (c_int, [_P, c_int, _P, _P]),
     "dgcnn_rows_bn_supported": (c_int, [c_int]),
     "dgcnn_rows_bn_workspace_bytes": (c_size_t, [c_int]),
     "dgcnn_rows_bn_lrelu_fwd": (c_int, [_P, c_int, c_int, _P, c_int, _P, _P, c_float, c_float, c_int, _P, _P, _P, _P, _P, _P,

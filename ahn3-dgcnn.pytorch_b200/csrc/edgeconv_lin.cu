@@ -229,3 +229,39 @@ extern "C" int dgcnn_edgeconv_bwd_a_lin_edges(const dgcnn_edgeconv_args* a, cons
   DG_REQUIRE(dy_edges, DGCNN_E_INVALID, "edgeconv_bwd_a_lin_edges: null dy_edges");
   return bwd_a_lin(a, U, ld_u, V, ld_v, dz_a, g, arg, coef_a, s, nullptr, ld_rs, dy_edges, stream, "edgeconv_bwd_a_lin_edges");
 }
+
+// ---- the weight of the linearised first convolution and its adjoint (one launch each instead of slice/subtract/concatenate) ----
+namespace dg {
+__global__ void lin_weight_kernel(const float* __restrict__ wa, int C, float* __restrict__ wlin) {
+  // wa [64, 2C] = [Wa1 | Wa2]  ->  wlin [128, C] = [Wa1 ; Wa2 - Wa1]
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kCout * C) return;
+  const int o = i / C, c = i - o * C;
+  const float w1 = wa[o * 2 * C + c], w2 = wa[o * 2 * C + C + c];
+  wlin[i] = w1;
+  wlin[kCout * C + i] = w2 - w1;
+}
+__global__ void lin_weight_bwd_kernel(const float* __restrict__ G, int C, float* __restrict__ dwa) {
+  // G [128, C] = [r | s]^T X  ->  dwa [64, 2C] = [ (r - s)^T X | s^T X ]
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kCout * C) return;
+  const int o = i / C, c = i - o * C;
+  const float gr = G[i], gs = G[kCout * C + i];
+  dwa[o * 2 * C + c] = gr - gs;
+  dwa[o * 2 * C + C + c] = gs;
+}
+}  // namespace dg
+
+extern "C" int dgcnn_edgeconv_lin_weight_f32(const float* wa, int C, float* wlin, void* stream) {
+  DG_REQUIRE(wa && wlin && C > 0, DGCNN_E_INVALID, "edgeconv_lin_weight: bad arguments");
+  dg::lin_weight_kernel<<<(kCout * C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(wa, C, wlin);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}
+
+extern "C" int dgcnn_edgeconv_lin_weight_bwd_f32(const float* G, int C, float* dwa, void* stream) {
+  DG_REQUIRE(G && dwa && C > 0, DGCNN_E_INVALID, "edgeconv_lin_weight_bwd: bad arguments");
+  dg::lin_weight_bwd_kernel<<<(kCout * C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(G, C, dwa);
+  DG_CUDA(cudaGetLastError());
+  return DGCNN_OK;
+}

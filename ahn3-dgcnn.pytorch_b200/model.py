@@ -134,9 +134,9 @@ class DGCNN(nn.Module):
                                           None if conv_b is None else conv_b.weight,
                                           None if bn_b is None else bn_b.weight,
                                           None if bn_b is None else bn_b.bias, st_a, st_b)
-            bn_a.num_batches_tracked.add_(1)
+            ops.bump_batches(bn_a)
             if bn_b is not None:
-                bn_b.num_batches_tracked.add_(1)
+                ops.bump_batches(bn_b)
             return out
         aff_a = ops.eval_affine(bn_a.weight.detach(), bn_a.bias.detach(), st_a)
         aff_b = None if bn_b is None else ops.eval_affine(bn_b.weight.detach(), bn_b.bias.detach(), st_b)
@@ -168,7 +168,11 @@ class DGCNN(nn.Module):
         if x.dim() != 3 or x.size(1) != self.num_features:
             raise RuntimeError(f"expected input [B, {self.num_features}, N], got {tuple(x.shape)}")
         if self.training:
-            return self._forward(x, depth, forced_idx)
+            ops.defer_batches()
+            try:
+                return self._forward(x, depth, forced_idx)
+            finally:
+                ops.flush_batches()          # num_batches_tracked of every BatchNorm passed: one launch
         with torch.no_grad():            # the inference kernels are not differentiable
             return self._forward(x, depth, forced_idx)
 
@@ -199,7 +203,7 @@ class DGCNN(nn.Module):
             g = ops.GlobalFeature.apply(feat, self.conv6[0].weight.squeeze(-1), bn6.weight, bn6.bias, _bn_state(bn6),
                                         self.training, B, N)               # [B,emb] global feature
             if self.training:
-                bn6.num_batches_tracked.add_(1)
+                ops.bump_batches(bn6)
         else:                            # blocks shorter than one epilogue row group: materialise [M,emb] (tiny)
             g = self._dense(feat, 6).view(B, N, -1).max(dim=1)[0]
         if depth == 6:

@@ -304,6 +304,35 @@ def clear_shared_planes() -> None:
     _shared_planes.clear()
 
 
+# `num_batches_tracked += 1` of every BatchNorm a training forward went through (nn.BatchNorm's bookkeeping): collected and
+# applied as ONE multi-tensor launch at the end of the forward instead of eight scalar kernels.
+_pending_batches = []
+_defer_batches = False
+
+
+def defer_batches() -> None:
+    """From now until flush_batches() the counters are collected instead of bumped one by one (DGCNN.forward)."""
+    global _defer_batches
+    _defer_batches = True
+
+
+def bump_batches(bn_mod) -> None:
+    if bn_mod.num_batches_tracked is None:
+        return
+    if _defer_batches:
+        _pending_batches.append(bn_mod.num_batches_tracked)
+    else:
+        bn_mod.num_batches_tracked.add_(1)
+
+
+def flush_batches() -> None:
+    global _defer_batches
+    _defer_batches = False
+    if _pending_batches:
+        torch._foreach_add_(_pending_batches, 1)
+        _pending_batches.clear()
+
+
 class TcLinear(torch.autograd.Function):
     """y = x @ w^T (x [M,K], w [N,K]) with all three GEMMs (y, dx, dw) on the tensor cores.
 
@@ -369,29 +398,29 @@ class GlobalFeature(torch.autograd.Function):
             raise RuntimeError("GlobalFeature: the inference form (running statistics) is not differentiable")
         M = feat.shape[0]
         B, E = ysel.shape
-        mean, rstd = stat[0], stat[1]
-        a = gamma * rstd
-        yhat = (ysel - mean) * rstd
-        z = yhat * gamma + beta
-        gdz = dg * torch.where(z > 0, 1.0, 0.2)                        # [B,E]: dz at the arg-max entries
-        s1, s2 = gdz.sum(0), (gdz * yhat).sum(0)
-        kappa = a * (s2 / M) * rstd
-        bprime = a * (s1 / M) - kappa * mean
         K = feat.shape[1]
         if K % 4 or feat.stride(1) != 1 or w.stride(1) != 1:
             raise RuntimeError("GlobalFeature: feature width must be a multiple of 4 with unit inner stride")
         dev = feat.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        # per-channel coefficients in one launch: gdz [B,E] (dz at the arg-max entries), coef = a | kappa | b' | s1 | s2,
+        # and -diag(kappa) W, the left operand of the small matrix below
+        gdz_c = torch.empty(B, E, **f32)
+        coef = torch.empty(5, E, **f32)
+        wneg = torch.empty(E, K, **f32)
+        dg = dg.contiguous()
+        _call("dgcnn_global_feature_bwd_coef_f32", dev, _ptr(dg), _ptr(ysel), _ptr(stat[0]), _ptr(stat[1]), _ptr(gamma), _ptr(beta),
+              _ptr(w), w.stride(0), B, E, K, M, 0.2, _ptr(gdz_c), _ptr(coef), _ptr(wneg))
+        a_c, bprime, s1, s2 = coef[0], coef[2], coef[3], coef[4]
         # dense parts on the tensor cores: dfeat = -feat (W^T diag(kappa) W) - b' W  (the sign is folded into the small matrix)
-        gram_neg = tc_gemm((w * (-kappa)[:, None]).t(), w.t(), nsplit=GRAD_NSPLIT)      # [K,K] = -W^T diag(kappa) W (symmetric)
+        gram_neg = tc_gemm(wneg.t(), w.t(), nsplit=GRAD_NSPLIT)                          # [K,K] = -W^T diag(kappa) W (symmetric)
         featp = shared_planes(feat, GRAD_NSPLIT)                                         # the head node's planes of feat, or one split for both GEMMs
         dfeat = gemm_planes(featp, Planes(gram_neg, GRAD_NSPLIT), GRAD_NSPLIT)
-        cvec = torch.empty(K, dtype=torch.float32, device=dev)
+        cvec = torch.empty(K, **f32)
         _call("dgcnn_vecmat_f32", dev, _ptr(bprime), _ptr(w), w.stride(0), E, K, -1.0, _ptr(cvec))
         dfeat.add_(cvec)
         # sparse parts in one pass: scatter of a dz W into dfeat, and t1 = dz^T feat
-        t1 = torch.empty(E, K, dtype=torch.float32, device=dev)
-        gdz_c = gdz.contiguous()
-        a_c = a.contiguous()
+        t1 = torch.empty(E, K, **f32)
         if DETERMINISTIC:        # t1 only, then the scatter with one owner warp per target row
             _call("dgcnn_global_feature_bwd_sparse_f32", dev, _ptr(feat), feat.stride(0), _ptr(w), w.stride(0), _ptr(nstar), _ptr(gdz_c),
                   _ptr(a_c), B, E, K, _ptr(None), dfeat.stride(0), _ptr(t1))
@@ -403,7 +432,9 @@ class GlobalFeature(torch.autograd.Function):
         # dW = a dz^T feat - b' colsum(feat)^T - diag(kappa) W (feat^T feat)
         f2 = gemm_planes(featp, featp, GRAD_NSPLIT, transposed=True)            # [K,K] = feat^T feat (row contraction, split over the points)
         wf2 = tc_gemm(w, f2, nsplit=GRAD_NSPLIT)                                # f2 is symmetric: W f2 = W f2^T
-        dw = a[:, None] * t1 - bprime[:, None] * rows_colsum(feat, M) - kappa[:, None] * wf2
+        colsum = rows_colsum(feat, M).contiguous()                              # [1,K]
+        dw = torch.empty(E, K, **f32)
+        _call("dgcnn_global_feature_bwd_dw_f32", dev, _ptr(coef), _ptr(t1), _ptr(colsum), _ptr(wf2), E, K, _ptr(dw))
         return dfeat, dw, s2, s1, None, None, None, None
 
 
@@ -466,7 +497,7 @@ def bn_lrelu_rows(y: torch.Tensor, bn_mod, training: bool, N: int, bias: Optiona
     st = BNState(bn_mod.running_mean, bn_mod.running_var, bn_mod.eps, mom)
     h = RowsBnLrelu.apply(y, bias, bn_mod.weight, bn_mod.bias, st, training, N)
     if training:
-        bn_mod.num_batches_tracked.add_(1)
+        bump_batches(bn_mod)
     return h
 
 
@@ -547,8 +578,8 @@ def _bn_state_of(bn_mod) -> BNState:
 def head_mlp(feat: torch.Tensor, bias7: Optional[torch.Tensor], w7: torch.Tensor, bn7, w8: torch.Tensor, bn8, N: int) -> torch.Tensor:
     """Training-mode conv7(points part) + bn7 + LReLU + conv8 + bn8 + LReLU on point-major rows (see HeadMlp)."""
     h8 = HeadMlp.apply(feat, bias7, w7, bn7.weight, bn7.bias, w8, bn8.weight, bn8.bias, _bn_state_of(bn7), _bn_state_of(bn8), N)
-    bn7.num_batches_tracked.add_(1)
-    bn8.num_batches_tracked.add_(1)
+    bump_batches(bn7)
+    bump_batches(bn8)
     return h8
 
 
@@ -622,7 +653,9 @@ def _use_lin(Cn: int, w_b) -> bool:
 
 def _lin_weight(wa: torch.Tensor, Cn: int) -> torch.Tensor:
     """[Wa1 ; Wa2 - Wa1] ([128, C]): X @ this^T = [U | V] with y[(i,j)] = U_j + V_i."""
-    return torch.cat((wa[:, :Cn], wa[:, Cn:] - wa[:, :Cn]), dim=0)
+    wlin = torch.empty(2 * COUT, Cn, dtype=torch.float32, device=wa.device)
+    _call("dgcnn_edgeconv_lin_weight_f32", wa.device, _ptr(wa), Cn, _ptr(wlin))
+    return wlin
 
 
 def set_deterministic(on: bool = True) -> None:
@@ -746,12 +779,13 @@ class EdgeConvTrain(torch.autograd.Function):
         vs = None if (lin or EDGECONV_IMPL == 0) else _v_scratch(B, Cn, N, dev)
         a = _args(rows, ld, idx, B, Cn, N, k, wa, wb, None, COUT, vs)
 
-        uv = uv2 = fused = xp = None
+        uv = uv2 = fused = xp = wlin = None
         if two and EDGECONV_IMPL == 0:
             # first conv of a two-conv block: y_a = U_j + V_i written per edge (BN_a needs batch statistics before conv_b
             # can start), no per-edge GEMM.  Also for the input block: y_a carries the centre term Wa2 x_i (~|W||x|) either
             # way, so forming x_j - x_i first buys no accuracy at the level of y_a (both are within a few 1e-8 |W||x|).
-            uv2, xp = _uv_gemm(rows, ld, Cn, _lin_weight(wa, Cn), True)     # X planes: this GEMM now, the weight gradient in the backward
+            wlin = _lin_weight(wa, Cn)
+            uv2, xp = _uv_gemm(rows, ld, Cn, wlin, True)     # X planes: this GEMM now, the weight gradient in the backward
             if FUSED_BWD and GRAD_NSPLIT == 2 and k >= 8 and N >= 16:
                 # + the out-edge sums of y_a: with them (and the in-edge sums the backward accumulates) dz_a[E,64] is never formed
                 fused = torch.empty(M, COUT, **f32)
@@ -762,7 +796,8 @@ class EdgeConvTrain(torch.autograd.Function):
                       _ptr(partials))
         elif lin:
             # y = U_j + V_i: one point-level GEMM + a gather pass (extrema over k, batch sums); nothing per-edge in HBM
-            uv, xp = _uv_gemm(rows, ld, Cn, _lin_weight(wa, Cn), True)
+            wlin = _lin_weight(wa, Cn)
+            uv, xp = _uv_gemm(rows, ld, Cn, wlin, True)
             _call("dgcnn_edgeconv_lin_extrema", dev, C.byref(a), _ptr(uv), uv.stride(0), _ptr(uv[:, COUT:]), uv.stride(0), _ptr(partials),
                   _ptr(ymax), _ptr(ymin), _ptr(amax), _ptr(amin))
         else:
@@ -789,6 +824,7 @@ class EdgeConvTrain(torch.autograd.Function):
         ctx.xp = xp
         ctx.thin = (uv is not None or uv2 is not None) and xp is None
         ctx.uv2 = uv2                                   # [U | V] of a two-conv block: the backward gathers it instead of re-reading y_a
+        ctx.wlin = wlin                                 # [Wa1 ; Wa2 - Wa1]: the data gradient multiplies by it again
         ctx.save_for_backward(rows, idx, wa, wb if two else wa, gamma_a.detach(), gamma_b.detach() if two else gamma_a.detach(),
                               uv if lin else y_a, stat_a, stat_b if two else stat_a, ysel, arg)
         ctx.x_shape = tuple(x.shape)
@@ -819,16 +855,19 @@ class EdgeConvTrain(torch.autograd.Function):
         _call("dgcnn_bn_bwd_reduce", dev, _ptr(partials), COUT, float(E), _ptr(gamma_last), _ptr(last[0]), _ptr(last[1]),
                                            _ptr(dgl[0]), _ptr(dgl[1]), _ptr(coef_l))
         dw_b = dga = None
-        rs = torch.zeros(M, 2 * COUT, **f32)            # [ r | s ]: scatter target and per-point sums, one GEMM operand
-        r, s = rs[:, :COUT], rs[:, COUT:]
         fused = ctx.fused if (two and GRAD_NSPLIT == 2) else None
         ctx.fused = None
+        # [ r | s ]: scatter target and per-point sums, one GEMM operand; the fused form also needs the in-edge sums of y_a
+        # [M,64] and the in-degrees [M]: one zero fill for all of them
+        zbuf = torch.zeros(M * 2 * COUT + (M * COUT + M if fused is not None else 0), **f32)
+        rs = zbuf[:M * 2 * COUT].view(M, 2 * COUT)
+        r, s = rs[:, :COUT], rs[:, COUT:]
         if fused is not None:
             # conv_b backward with the scatter fused in (raw in-edge sums -> r, out-edge sums -> s), then BN_a's backward
             # per POINT: its batch sums from U, V, r, s and the affine map with the forward's graph sums of y_a
             uv = ctx.uv2
             dw_b = torch.empty(COUT, COUT, **f32)
-            zin = torch.zeros(M * COUT + M, **f32)          # in-edge sums of y_a [M,64] | in-degrees [M]
+            zin = zbuf[M * 2 * COUT:]                       # in-edge sums of y_a [M,64] | in-degrees [M]
             yin, cnt = zin[:M * COUT].view(M, COUT), zin[M * COUT:]
             _call("dgcnn_edgeconv_bwd_b_fused", dev, C.byref(a), _ptr(y_a), _ptr(stat_a[2:]), _ptr(g), _ptr(arg), _ptr(coef_l),
                   _ptr(r), _ptr(s), 2 * COUT, _ptr(yin), _ptr(cnt), _ptr(dw_b), _ptr(dw_partials))
@@ -873,12 +912,12 @@ class EdgeConvTrain(torch.autograd.Function):
         #   dX  = r Wa1 + s (Wa2 - Wa1)            = [r|s] @ [Wa1 ; Wa2-Wa1]
         #   dWa = [(r - s)^T X | s^T X]            from G = [r|s]^T X  (contraction over the points, split-K)
         X = rows[:, :Cn]
-        wa1, wa2 = wa[:, :Cn], wa[:, Cn:]
         dx = None
+        wcat = ctx.wlin                                                 # [128, C]
+        ctx.wlin = None
         if getattr(ctx, "thin", False):
             # thin input (K <= 8): one streaming pass gives G = [r|s]^T X and, if asked for, dX = [r|s] [Wa1 ; Wa2-Wa1]
             C4 = (Cn + 3) // 4 * 4
-            wcat = torch.cat((wa1, wa2 - wa1), dim=0).contiguous()      # [128, C]
             G = torch.empty(2 * COUT, Cn, **f32)
             dxp = torch.empty(M, C4, **f32) if ctx.needs_input_grad[0] else None
             _call("dgcnn_linear_thin_bwd_f32", dev, _ptr(rows), ctx.ld, _ptr(rs), 2 * COUT, _ptr(wcat), Cn, M, Cn, 2 * COUT, _ptr(dxp), C4,
@@ -888,14 +927,16 @@ class EdgeConvTrain(torch.autograd.Function):
         else:
             rsp = Planes(rs, GRAD_NSPLIT)                               # split once: K-major for dX, row-contraction for dWa
             if ctx.needs_input_grad[0]:
-                wcat = torch.cat((wa1, wa2 - wa1), dim=0)               # [128, C]
+                if wcat is None:
+                    wcat = _lin_weight(wa, Cn)
                 dx = gemm_planes(rsp, Planes(wcat.t(), GRAD_NSPLIT), GRAD_NSPLIT)
                 if dx.shape != ctx.x_shape:                             # rows padded to a multiple of 4 channels
                     dx = torch.nn.functional.pad(dx, (0, ctx.x_shape[1] - dx.shape[1]))
             xp = ctx.xp if ctx.xp is not None else Planes(X, GRAD_NSPLIT)
             G = gemm_planes(rsp, xp, GRAD_NSPLIT, transposed=True)      # [128, C] = [r|s]^T X
         ctx.xp = None
-        dwa = torch.cat((G[:COUT] - G[COUT:], G[COUT:]), dim=1)
+        dwa = torch.empty(COUT, 2 * Cn, **f32)                          # [(r - s)^T X | s^T X]
+        _call("dgcnn_edgeconv_lin_weight_bwd_f32", dev, _ptr(G), Cn, _ptr(dwa))
         # returns: x, idx, meta, w_a, gamma_a, beta_a, w_b, gamma_b, beta_b, bn_a, bn_b
         if two:
             return (dx, None, None, dwa.view(COUT, 2 * Cn, 1, 1), dga[0], dga[1], dw_b.view(COUT, COUT, 1, 1),
@@ -923,7 +964,12 @@ class SegLoss(torch.autograd.Function):
         dev = logits.device
         labels = labels.to(device=dev, dtype=torch.int64).reshape(B, N).contiguous()
         if mask is not None:
-            mask = mask.to(device=dev).reshape(B, N).ne(0).to(torch.uint8).contiguous()
+            mask = mask.to(device=dev).reshape(B, N)
+            if mask.dtype == torch.bool:
+                mask = mask.contiguous().view(torch.uint8)             # same bytes; the kernel tests `!= 0`
+            elif mask.dtype != torch.uint8:
+                mask = mask.ne(0).to(torch.uint8)
+            mask = mask.contiguous()
         z = logits.detach()
         loss = torch.empty((), dtype=torch.float32, device=dev)
         need_grad = logits.requires_grad

@@ -176,6 +176,10 @@ int dgcnn_edgeconv_lin_conv_a(const dgcnn_edgeconv_args* a, const float* U, int 
 int dgcnn_edgeconv_bwd_a_lin(const dgcnn_edgeconv_args* a, const float* U, int ld_u, const float* V, int ld_v,
                              const float* dz_a, const float* g, const uint8_t* arg, const float* coef_a, float* s, float* r,
                              int ld_rs, void* stream);
+/* the weight of that point-level GEMM and its adjoint: wa[64,2C] = [Wa1 | Wa2] (the reference's conv weight, model.py:116-130)
+ * -> wlin[128,C] = [Wa1 ; Wa2 - Wa1];  G[128,C] = [r|s]^T X -> dwa[64,2C] = [G_r - G_s | G_s].  Dense, contiguous.      */
+int dgcnn_edgeconv_lin_weight_f32(const float* wa, int C, float* wlin, void* stream);
+int dgcnn_edgeconv_lin_weight_bwd_f32(const float* G, int C, float* dwa, void* stream);
 
 /* ---- reproducible gradients (opt-in; csrc/graph_transpose.cu) ------------------------------------------------------------
  * The default backward adds per-edge gradients into their neighbour's row with float reductions: the summation order, and
@@ -273,6 +277,16 @@ int dgcnn_global_feature_bwd_sparse_f32(const float* feat, int ld_feat, const fl
                                         const float* gdz, const float* a, int B, int E, int K, float* dfeat, int ld_dfeat,
                                         float* t1, void* stream);
 int dgcnn_vecmat_f32(const float* v, const float* w, int ld_w, int E, int K, float scale, float* c, void* stream);
+/* the per-channel coefficients of that backward in one launch (reference: autograd through model.py:133-135,172-175):
+ *   gdz[b,e] = dg[b,e] * LReLU'(gamma_e yhat + beta_e), yhat = (ysel[b,e] - mean_e) rstd_e;
+ *   coef[5,E] = a = gamma rstd | kappa = a (s2 / M) rstd | b' = a (s1 / M) - kappa mean | s1 = sum_b gdz (dbeta) |
+ *               s2 = sum_b gdz yhat (dgamma);   wneg[E,K] = -kappa_e w[e,:]  (dense, row stride K).
+ * dgcnn_global_feature_bwd_dw_f32: dw[e,k] = a_e t1[e,k] - b'_e colsum[k] - kappa_e wf2[e,k] (all dense [E,K] / [K]).   */
+int dgcnn_global_feature_bwd_coef_f32(const float* dg, const float* ysel, const float* mean, const float* rstd,
+                                      const float* gamma, const float* beta, const float* w, int ld_w, int B, int E, int K,
+                                      int M, float slope, float* gdz, float* coef, float* wneg, void* stream);
+int dgcnn_global_feature_bwd_dw_f32(const float* coef, const float* t1, const float* colsum, const float* wf2, int E, int K,
+                                    float* dw, void* stream);
 
 /* ---- narrow-output linear layer on the FP32 FMA pipe (the classifier conv9: 256 -> num_classes, model.py:141,187-193) ----
  * y[M,NO] = x[M,K] W[NO,K]^T with 1 <= NO <= 8, K %% 4 == 0, K <= 512 (backward: K <= 256, or <= 512 with NO <= 4).  A
