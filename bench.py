@@ -364,6 +364,10 @@ def run_ours(args, rank: int, local: int, world: int):
     parallel.broadcast_parameters(model)
     model.train()
     bucket = parallel.GradBucket(model.parameters())
+    overlap = world > 1 and args.overlap_collective and ops.FUSED_HEAD
+    if overlap:
+        # opt-in: conv6..conv9 (97 % of the bucket) are exchanged while the EdgeConv backward is still running
+        bucket.overlap_from(model.conv6[0].weight)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True, capturable=not args.no_graph)
 
     nbuf = 4
@@ -547,6 +551,9 @@ def run_ours(args, rank: int, local: int, world: int):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "cuda_graph": graphed is not None, "cuda_graph_scope": graph_scope if graphed is not None else None,
+        "collective": None if world == 1 else ("all-reduce of conv6..conv9 (97 % of the 3.92 MB bucket) started from an autograd hook while the "
+                                               "EdgeConv backward runs, the rest after the backward" if overlap else
+                                               "one all-reduce of the 3.92 MB bucket after the backward"),
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,
@@ -653,6 +660,9 @@ def main():
                     help="train = BASELINE configs[1]/[2] (the headline metric); infer = configs[3], sharded tile inference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--overlap-collective", action="store_true",
+                    help="N > 1: exchange the head's weight gradients from an autograd hook while the EdgeConv backward runs "
+                         "(GradBucket.overlap_from; measured: no gain, see DESIGN.md §6) instead of one all-reduce after the backward")
     ap.add_argument("--no-graph-collective", action="store_true", help="N > 1: keep the gradient all-reduce and Adam outside the graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-layer timings, the nsplit=3 step and the eager-GPU oracle run")
     args = ap.parse_args()
