@@ -35,12 +35,14 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
 
 
 class GradBucket:
-    """All parameter gradients as views of ONE flat buffer, so the data-parallel exchange is one or two all-reduces.
+    """All parameter gradients as views of ONE flat buffer, so the data-parallel exchange is one all-reduce.
 
-    3.92 MB for the reference configuration: the transfer itself is latency-bound on NVLink 5 (tens of microseconds), but an
-    all-reduce also waits for the slowest rank.  `overlap_from(p)` therefore starts the exchange of the bucket's tail (97 %
-    of it: the head's weights) as soon as those gradients are complete, on NCCL's own stream, while the EdgeConv backward
-    (1 ms) is still running; only the small front segment is exchanged after the last backward kernel.
+    3.92 MB for the reference configuration: latency-bound on NVLink 5 (tens of microseconds), so one collective per
+    step, launched after the last backward kernel.  `overlap_from(p)` is the opt-in alternative: the bucket's tail (97 %
+    of it: the head's weights) is exchanged from an autograd hook as soon as those gradients are complete, on the process
+    group's own stream, while the EdgeConv backward is still running.  Measured on 2 x B200 (tools/diag_overlap.py): 4.23
+    ms per eagerly launched step either way — the exchange is too short to matter — so bench.py keeps the single
+    all-reduce.  (A CUDA graph that captured a collective must be destroyed before the process group is.)
     """
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
