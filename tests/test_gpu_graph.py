@@ -62,3 +62,27 @@ def test_graphed_step_matches_eager_steps():
     bn = [mod for mod in m2.modules() if hasattr(mod, "num_batches_tracked")]
     if bn:
         assert int(bn[0].num_batches_tracked) == int([mod for mod in m1.modules() if hasattr(mod, "num_batches_tracked")][0].num_batches_tracked)
+
+
+@pytest.mark.gpu
+def test_graphed_forward_matches_eager_forward():
+    """graphs.GraphedForward: the replayed eval forward (+ epilogue) equals the eagerly launched one, call after call."""
+    pkg = entry.load_package()
+    from importlib import import_module
+    graphs = import_module(entry.PKG_NAME + ".graphs")
+    torch.cuda.set_device(0)
+    torch.manual_seed(3)
+    m = pkg.DGCNN(5, 4, 20, cuda=True).eval()
+    xs = [common.points(40 + s, 1, 4, 1000, "unit").to(DEV) for s in range(3)]        # the README shape (cfg1)
+    g = graphs.GraphedForward(m, xs[0])
+    for x in xs:
+        want = m(x)
+        got = g.run(x).clone()
+        assert got.shape == want.shape == (1, 5, 1000)
+        assert float((got - want).abs().max()) <= 1e-5 * max(1.0, float(want.abs().max()))
+    gp = graphs.GraphedForward(m, xs[0], post=lambda z: pkg.ops.seg_predict(z, 0.3))
+    assert torch.equal(gp.run(xs[1]), pkg.ops.seg_predict(m(xs[1]), 0.3))
+    with pytest.raises(RuntimeError):
+        g.run(torch.zeros(1, 4, 999, device=DEV))
+    with pytest.raises(RuntimeError):
+        graphs.GraphedForward(m.train(), xs[0])

@@ -5,6 +5,7 @@ sys.path.insert(0, ROOT)
 import torch
 import __graft_entry__ as entry
 pkg = entry.load_package(); ops = pkg.ops
+graphs = __import__(entry.PKG_NAME + ".graphs", fromlist=["x"])
 
 def timeit(fn, n=5, warm=2):
     for _ in range(warm): fn()
@@ -27,11 +28,16 @@ for name, B, N, k in (("cfg1 B=1 N=1000 k=20", 1, 1000, 20), ("cfg2-shape B=8 N=
     ms = timeit(lambda: net(x))
     ops.LOG.reset(timing=True); net(x); torch.cuda.synchronize(); ker = {kk: round(v[1], 3) for kk, v in ops.LOG.summary().items()}; ops.LOG.reset()
     out[name] = {"ms": round(ms, 3), "points_per_s": round(B * N / ms * 1e3), "kernels_ms": ker}
+    if B * N <= 100000:          # launch-bound shapes: the same forward replayed from a CUDA graph (graphs.GraphedForward)
+        gf = graphs.GraphedForward(net, x)
+        msg = timeit(lambda: gf.run(x), n=20, warm=3)
+        out[name]["ms_cuda_graph"] = round(msg, 3)
+        del gf
     print(name, out[name], flush=True)
     del net, x; torch.cuda.empty_cache()
 # kNN sweep
 sweep = []
-for C in (4, 64, 128):
+for C in (() if os.environ.get("NO_SWEEP") else (4, 64, 128)):
     for N in (1000, 2000, 4000, 7000, 8000, 16000, 32000, 64000):
         for k in (20, 30, 40):
             # B = 1 (the survey's single-cloud sweep) and a batch that fills the GPU (8 clouds up to N = 8000)
