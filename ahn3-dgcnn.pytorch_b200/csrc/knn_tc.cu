@@ -515,34 +515,45 @@ knn_tc_scan_kernel(const unsigned char* __restrict__ tiles, int N, int T, int nk
         m32 = (m32 << 16) | (((mq[0] << 4) | mq[1]) << 8) | ((mq[2] << 4) | mq[3]);
       }
       if (CH == 1) m32 <<= 16;
-      if (m32 != 0u) {
-        // rare per thread (a third of the tiles), but some lane of the warp has a hit on almost every tile: park the
-        // scores so that the hit columns can be indexed, then append the hits two at a time (two independent shared-memory
-        // reads and stores in flight; one at a time, every store waited for its read and the next read for the store's
-        // source registers)
+      // Hits are rare per thread (a third of the tiles) but some lane of the warp has one on almost every tile.  A thread
+      // with hits parks its scores so that the hit columns can be indexed.  The first two hits (all of them for 99 % of the
+      // thread-tiles) are handled without a loop: their scores are read back here, the candidate stores are issued only
+      // AFTER the next tile's accumulator has been fetched and combined with its key norms — the shared-memory round trip
+      // that every store used to wait for is hidden behind that independent work.  Further hits take the loop.
+      const bool has = m32 != 0u;
+      if (has) {
         float4* p4 = reinterpret_cast<float4*>(park);
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4)
             p4[(ch * 4 + q4) ^ psw] = make_float4(sc[ch][4 * q4], sc[ch][4 * q4 + 1], sc[ch][4 * q4 + 2], sc[ch][4 * q4 + 3]);
-        uint32_t m = m32;
-        do {
-          const int e0 = __clz(m);                            // lowest column first
-          m &= ~(0x80000000u >> e0);
-          const bool two = m != 0u;
-          const int e1 = two ? __clz(m) : e0;
-          m &= ~(0x80000000u >> e1);
-          const float s0 = park[(((e0 >> 2) ^ psw) << 2) | (e0 & 3)];
-          const float s1 = park[(((e1 >> 2) ^ psw) << 2) | (e1 & 3)];
-          if (n < kSubCands) wp[0] = make_uint2(static_cast<uint32_t>(j0 + e0), __float_as_uint(s0));
-          if (two && n + 1 < kSubCands) wp[1] = make_uint2(static_cast<uint32_t>(j0 + e1), __float_as_uint(s1));
-          const int add = two ? 2 : 1;
-          wp += add;
-          n += add;
-        } while (m);
+      }
+      uint32_t m = m32;
+      const int e0 = has ? __clz(m) : 0;                      // lowest column first
+      m &= ~(0x80000000u >> e0);
+      const bool two = m != 0u;
+      const int e1 = two ? __clz(m) : e0;
+      m &= ~(0x80000000u >> e1);
+      float s0 = 0.f, s1 = 0.f;
+      if (has) s0 = park[(((e0 >> 2) ^ psw) << 2) | (e0 & 3)];
+      if (two) s1 = park[(((e1 >> 2) ^ psw) << 2) | (e1 & 3)];
+      uint2* const wq = wp;                                   // slots of the first two hits
+      const bool st0 = has && n < kSubCands, st1 = two && n + 1 < kSubCands;
+      const uint32_t k0 = static_cast<uint32_t>(j0 + e0), k1 = static_cast<uint32_t>(j0 + e1);
+      const int add = has ? (two ? 2 : 1) : 0;
+      wp += add;
+      n += add;
+      while (m) {                                             // a third, fourth, ... hit of this thread in this tile
+        const int e = __clz(m);
+        m &= ~(0x80000000u >> e);
+        if (n < kSubCands) *wp = make_uint2(static_cast<uint32_t>(j0 + e), __float_as_uint(park[(((e >> 2) ^ psw) << 2) | (e & 3)]));
+        ++wp;
+        ++n;
       }
       if (i + 1 < TT) finish_loads(i + 1, rn, sc);
+      if (st0) wq[0] = make_uint2(k0, __float_as_uint(s0));
+      if (st1) wq[1] = make_uint2(k1, __float_as_uint(s1));
     }
     if (row_ok) cnt4[g * 4 + cq] = n;
   }
