@@ -271,22 +271,16 @@ struct KnnScan {
   static constexpr int kAccs = kStages;
   static constexpr int CH = KEYS / 64;                                      // 16-column chunks per thread and tile
   static constexpr int QC = KEYS / 4;                                       // columns per column quarter
-  // a stage = the planes of one key tile (1024-byte aligned for the SWIZZLE_128B descriptors); the tile's key norms go
-  // to a ring of their own (second bulk copy on the same barrier), so that the stages carry no alignment padding
-  static constexpr uint32_t stage_bytes = (Tile::norm_off + 1023u) & ~1023u;
+  static constexpr uint32_t stage_bytes = (Tile::bytes + 1023u) & ~1023u;
   static constexpr uint32_t a_plane = 128 * 128;                            // one plane of one atom of the 128 query rows
   static constexpr uint32_t a_bytes = KA * 2 * a_plane;
   static constexpr uint32_t b_off = a_bytes;
-  static constexpr uint32_t norm_ring_off = b_off + kStages * stage_bytes;  // [kStages][KEYS] floats
-  static constexpr uint32_t scr_off = norm_ring_off + kStages * KEYS * 4;   // per-thread score park / pass-1 group maxima [128][68]
-  // score park: the thread's CH * 16 scores of a tile.  One chunk: 16 floats + 4 of padding (conflict-free 16-byte
-  // stores).  Two chunks: 32 floats, no room for padding — the 16-byte granules of a row are XOR-swizzled by the lane.
-  static constexpr uint32_t scr_stride = CH == 1 ? 20 : 32;
+  static constexpr uint32_t scr_off = b_off + kStages * stage_bytes;        // per-thread score park (16 floats + pad) /
+  static constexpr uint32_t scr_stride = 20;                                //   pass-1 group maxima [128][68]
   static constexpr uint32_t scr_bytes = kScanWarps * 32 * scr_stride * 4;
   static constexpr uint32_t tau_off = scr_off + scr_bytes;
   static constexpr uint32_t bar_off = tau_off + 128 * 4;
   static constexpr uint32_t bytes = bar_off + 256;
-  static_assert(bytes <= 232448, "scan kernel: shared memory budget");
   static constexpr uint32_t tmem_cols = kAccs * KEYS <= 256 ? 256 : 512;        // power of two >= kAccs * KEYS
   static_assert(128 * 68 * 4 <= scr_bytes, "group maxima must fit in the score park");
 };
@@ -353,10 +347,8 @@ knn_tc_scan_kernel(const unsigned char* __restrict__ tiles, int N, int T, int nk
         const int s = l % kStages;
         // pass-1 sample tiles are spread over the block (robust against spatially sorted inputs)
         const int tile = l < T1 ? static_cast<int>((static_cast<long long>(l) * Tk) / T1) : l - T1;
-        const unsigned char* src = btiles + static_cast<size_t>(tile) * Tile::bytes;
         tc::mbar_arrive_expect_tx(full + s, Tile::bytes);
-        tc::bulk_g2s(Bs + s * S::stage_bytes, src, Tile::norm_off, full + s);
-        tc::bulk_g2s(sm + S::norm_ring_off + s * KEYS * 4, src + Tile::norm_off, KEYS * 4, full + s);
+        tc::bulk_g2s(Bs + s * S::stage_bytes, btiles + static_cast<size_t>(tile) * Tile::bytes, Tile::bytes, full + s);
       };
       const uint64_t da = tc::smem_desc_sw128(tc::smem_u32(As));
       const uint32_t a_lo = static_cast<uint32_t>(da), hi = static_cast<uint32_t>(da >> 32);
@@ -418,7 +410,7 @@ knn_tc_scan_kernel(const unsigned char* __restrict__ tiles, int N, int T, int nk
     };
     auto finish_loads = [&](int i, uint32_t (&r)[CH][16], float (&sc)[CH][16]) {
       const int s = i % kStages, a = i % kAccs;
-      const float4* kn4 = reinterpret_cast<const float4*>(sm + S::norm_ring_off + s * KEYS * 4) + cq * (QC / 4);
+      const float4* kn4 = reinterpret_cast<const float4*>(Bs + s * S::stage_bytes + Tile::norm_off) + cq * (QC / 4);
       float4 kk[CH][4];
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch)
@@ -486,7 +478,6 @@ knn_tc_scan_kernel(const unsigned char* __restrict__ tiles, int N, int T, int nk
     // ---- pass 2: collect every key above tau --------------------------------------------------------------------------
     uint2* wp = reinterpret_cast<uint2*>(cand + (g * 4 + cq) * kSubCands);       // next free slot of this thread's sub-buffer
     float* park = scr + (warp * 32 + lane) * S::scr_stride;
-    const int psw = CH == 1 ? 0 : (lane & 7);              // granule swizzle of the unpadded two-chunk park
     const float tau_eff = row_ok ? tau : INFINITY;       // rows past the end of the block collect nothing
     const float2 tau2 = make_float2(tau_eff, tau_eff), neg1 = make_float2(-1.0f, -1.0f);
     int n = 0;
@@ -496,12 +487,10 @@ knn_tc_scan_kernel(const unsigned char* __restrict__ tiles, int N, int T, int nk
       uint32_t rn[CH][16];
       if (i + 1 < TT) issue_loads(i + 1, rn);              // next tile's accumulator -> registers while this one is scanned
       const int j0 = (i - T1) * KEYS + cq * QC;
-      // sign(tau - score) of the thread's column e (= ch * 16 + c) ends up in bit 31 - e.  Four independent 4-bit chains
-      // per chunk: one 16-deep chain of dependent funnel shifts left the warp waiting on the 4-cycle ALU latency with only
-      // 4 warps per scheduler.  Both chunks are evaluated before the (divergent) hit path.
-      uint32_t m32 = 0u;
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch) {
+        // sign(tau - score) of column c ends up in bit 15 - c.  Four independent 4-bit chains: one 16-deep chain of
+        // dependent funnel shifts left the warp waiting on the 4-cycle ALU latency with only 4 warps per scheduler.
         uint32_t mq[4];
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
@@ -512,48 +501,24 @@ knn_tc_scan_kernel(const unsigned char* __restrict__ tiles, int N, int T, int nk
           mm = shift_in_sign(mm, d1.x);
           mq[q4] = shift_in_sign(mm, d1.y);
         }
-        m32 = (m32 << 16) | (((mq[0] << 4) | mq[1]) << 8) | ((mq[2] << 4) | mq[3]);
-      }
-      if (CH == 1) m32 <<= 16;
-      // Hits are rare per thread (a third of the tiles) but some lane of the warp has one on almost every tile.  A thread
-      // with hits parks its scores so that the hit columns can be indexed.  The first two hits (all of them for 99 % of the
-      // thread-tiles) are handled without a loop: their scores are read back here, the candidate stores are issued only
-      // AFTER the next tile's accumulator has been fetched and combined with its key norms — the shared-memory round trip
-      // that every store used to wait for is hidden behind that independent work.  Further hits take the loop.
-      const bool has = m32 != 0u;
-      if (has) {
-        float4* p4 = reinterpret_cast<float4*>(park);
+        const uint32_t mask = (((mq[0] << 4) | mq[1]) << 8) | ((mq[2] << 4) | mq[3]);
+        if (mask != 0u) {
+          // rare per thread (a few % of the chunks): park the 16 scores so that the hit columns can be indexed
+          float4* p4 = reinterpret_cast<float4*>(park);
 #pragma unroll
-        for (int ch = 0; ch < CH; ++ch)
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            p4[(ch * 4 + q4) ^ psw] = make_float4(sc[ch][4 * q4], sc[ch][4 * q4 + 1], sc[ch][4 * q4 + 2], sc[ch][4 * q4 + 3]);
-      }
-      uint32_t m = m32;
-      const int e0 = has ? __clz(m) : 0;                      // lowest column first
-      m &= ~(0x80000000u >> e0);
-      const bool two = m != 0u;
-      const int e1 = two ? __clz(m) : e0;
-      m &= ~(0x80000000u >> e1);
-      float s0 = 0.f, s1 = 0.f;
-      if (has) s0 = park[(((e0 >> 2) ^ psw) << 2) | (e0 & 3)];
-      if (two) s1 = park[(((e1 >> 2) ^ psw) << 2) | (e1 & 3)];
-      uint2* const wq = wp;                                   // slots of the first two hits
-      const bool st0 = has && n < kSubCands, st1 = two && n + 1 < kSubCands;
-      const uint32_t k0 = static_cast<uint32_t>(j0 + e0), k1 = static_cast<uint32_t>(j0 + e1);
-      const int add = has ? (two ? 2 : 1) : 0;
-      wp += add;
-      n += add;
-      while (m) {                                             // a third, fourth, ... hit of this thread in this tile
-        const int e = __clz(m);
-        m &= ~(0x80000000u >> e);
-        if (n < kSubCands) *wp = make_uint2(static_cast<uint32_t>(j0 + e), __float_as_uint(park[(((e >> 2) ^ psw) << 2) | (e & 3)]));
-        ++wp;
-        ++n;
+          for (int q4 = 0; q4 < 4; ++q4) p4[q4] = make_float4(sc[ch][4 * q4], sc[ch][4 * q4 + 1], sc[ch][4 * q4 + 2], sc[ch][4 * q4 + 3]);
+          uint32_t m = mask;
+          const int jc = j0 + ch * 16 + 15;
+          do {
+            const int pos = 31 - __clz(m);                    // highest set bit first = lowest column first (c = 15 - pos)
+            m ^= 1u << pos;
+            if (n < kSubCands) *wp = make_uint2(static_cast<uint32_t>(jc - pos), __float_as_uint(park[15 - pos]));
+            ++wp;
+            ++n;
+          } while (m);
+        }
       }
       if (i + 1 < TT) finish_loads(i + 1, rn, sc);
-      if (st0) wq[0] = make_uint2(k0, __float_as_uint(s0));
-      if (st1) wq[1] = make_uint2(k1, __float_as_uint(s1));
     }
     if (row_ok) cnt4[g * 4 + cq] = n;
   }

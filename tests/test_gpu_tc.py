@@ -199,3 +199,20 @@ def test_row_contraction_gemm_matches_fp64(pkg, R, M, N, nsplit):
     erry = ((Y.double() - refy).abs() / (A.double().abs() @ W.double().abs().t())).max().item()
     # short contractions (M = 4, 5 terms) do not average: the rigorous per-element bound of the 2-plane split is 3 * 2^-16
     assert erry < (4e-6 if nsplit == 3 else (4.7e-5 if M < 64 else 1.3e-5)), erry
+
+
+@pytest.mark.gpu
+def test_knn_tc_repeated_small_blocks_equal_exact_kernel(pkg):
+    """Stress for pipeline races: many calls at the README shape (8 CTAs, 10 key tiles each) with the caching allocator's
+    free blocks poisoned between calls; every table must equal the exact kernel's.  (A rebuilt hit path of the scan kernel
+    passed all other tests and failed this one once in 300 calls; it was reverted.)"""
+    ops = pkg.ops
+    for (B, C, N, k) in ((1, 64, 1000, 20), (1, 4, 1000, 20)):
+        x = torch.randn(B, C, N, generator=torch.Generator().manual_seed(C + N)).to(DEV)
+        rows = ops.pack_rows(x)
+        ref = ops.knn_rows(rows, B, C, N, k, method="exact").sort(1)[0]
+        for it in range(400):
+            junk = torch.full((1 << 22,), float("nan"), device=DEV)
+            del junk
+            idx = ops.knn_rows(rows, B, C, N, k, method="tc", ordered=(it % 2 == 1)).sort(1)[0]
+            assert torch.equal(idx, ref), (B, C, N, k, it)
