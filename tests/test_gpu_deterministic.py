@@ -50,6 +50,27 @@ def test_deterministic_mode_is_bit_reproducible_and_matches_the_default():
         assert ((a - b).norm() / (a.norm() + 1e-30)).item() < 5e-4
 
 
+@pytest.mark.parametrize("B,N", [(2, 1500), (1, 1000)])
+def test_default_step_repeats_within_rounding(B, N):
+    """Stress for rare pipeline races on the DEFAULT path (float reductions, neighbour sets in any order): 30 repetitions of
+    the same step with a poisoned allocator in between must agree with the first one to rounding — a tile computed from a
+    buffer that was overwritten too early shows up as a gross error in the loss or in some gradient."""
+    pkg = entry.load_package()
+    x = common.points(311 + N, B, 4, N, "real").to(DEV)
+    g = torch.Generator().manual_seed(8)
+    y = torch.randint(0, 5, (B, N), generator=g).to(DEV)
+    mask = (torch.rand(B, N, generator=g) < 0.7).to(DEV)
+    w = common.weights(312, 5, 4, 1024)
+    l0, g0 = _step(pkg, x, y, mask, w)
+    for it in range(30):
+        junk = torch.full((1 << 23,), float("nan"), device=DEV)
+        del junk
+        l1, g1 = _step(pkg, x, y, mask, w)
+        assert abs(float(l1) - float(l0)) <= 2e-5 * abs(float(l0)), (it, float(l0), float(l1))
+        for i, (a, b) in enumerate(zip(g0, g1)):
+            assert ((a - b).norm() / (a.norm() + 1e-30)).item() < 2e-3, (it, i)
+
+
 @pytest.mark.parametrize("B,N,k", [(2, 700, 20), (1, 300, 7), (3, 257, 48)])
 def test_graph_transpose_lists_every_in_edge_in_order(B, N, k):
     pkg = entry.load_package()
