@@ -913,8 +913,7 @@ class EdgeConvTrain(torch.autograd.Function):
         #   dWa = [(r - s)^T X | s^T X]            from G = [r|s]^T X  (contraction over the points, split-K)
         X = rows[:, :Cn]
         dx = None
-        wcat = ctx.wlin                                                 # [128, C]
-        ctx.wlin = None
+        wcat = ctx.wlin if ctx.wlin is not None else _lin_weight(wa, Cn)     # [128, C] = [Wa1 ; Wa2 - Wa1]
         if getattr(ctx, "thin", False):
             # thin input (K <= 8): one streaming pass gives G = [r|s]^T X and, if asked for, dX = [r|s] [Wa1 ; Wa2-Wa1]
             C4 = (Cn + 3) // 4 * 4
@@ -927,8 +926,6 @@ class EdgeConvTrain(torch.autograd.Function):
         else:
             rsp = Planes(rs, GRAD_NSPLIT)                               # split once: K-major for dX, row-contraction for dWa
             if ctx.needs_input_grad[0]:
-                if wcat is None:
-                    wcat = _lin_weight(wa, Cn)
                 dx = gemm_planes(rsp, Planes(wcat.t(), GRAD_NSPLIT), GRAD_NSPLIT)
                 if dx.shape != ctx.x_shape:                             # rows padded to a multiple of 4 channels
                     dx = torch.nn.functional.pad(dx, (0, ctx.x_shape[1] - dx.shape[1]))
