@@ -10,7 +10,10 @@ pkg = entry.load_package(); ops = pkg.ops
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 dev = "cuda:0"
 bad = {}
-for (B, C, N, k, kind) in ((1, 4, 1000, 20, "unit"), (1, 64, 1000, 20, "randn"), (2, 4, 515, 30, "real"), (1, 4, 1000, 20, "real")):
+SHAPES = ((1, 4, 1000, 20, "unit"), (1, 64, 1000, 20, "randn"), (2, 4, 515, 30, "real"), (1, 4, 1000, 20, "real"))
+if len(sys.argv) > 2 and sys.argv[2] == "big":      # the training shapes and a C = 128 case
+    SHAPES = ((8, 64, 7000, 30, "randn"), (8, 4, 7000, 30, "real"), (3, 64, 2000, 30, "randn"), (2, 128, 3000, 20, "randn"))
+for (B, C, N, k, kind) in SHAPES:
     x = common.points(5, B, C, N, kind if kind != "randn" else "unit").to(dev)
     if kind == "randn":
         x = torch.randn(B, C, N, device=dev)
